@@ -1,0 +1,183 @@
+// common.cuh -- device-side helpers shared by all kernels of libshafa_cuda.
+// sm_100a only.  Nothing here is GEMM-shaped: these are HBM-bound byte/bit
+// kernels, so the helpers are about coalesced 16-byte access, warp scans and the
+// decoupled look-back chain (Merrill & Garland) used by every single-pass kernel.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace shafa {
+
+constexpr unsigned FULL = 0xffffffffu;
+
+__device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }
+__device__ __forceinline__ unsigned warp_id() { return threadIdx.x >> 5; }
+
+// ---- streaming 16-byte access -------------------------------------------------
+__device__ __forceinline__ uint4 ld_stream16(const void *p)
+{
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void st_stream16(void *p, uint4 v)
+{
+    asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y),
+                 "r"(v.z), "r"(v.w)
+                 : "memory");
+}
+__device__ __forceinline__ void st_stream4(void *p, uint32_t v)
+{
+    asm volatile("st.global.L1::no_allocate.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// byte j (0..15) of a uint4 in memory order
+__device__ __forceinline__ uint32_t byte_of(const uint4 &v, int j)
+{
+    const uint32_t w = (j < 4) ? v.x : (j < 8) ? v.y : (j < 12) ? v.z : v.w;
+    return (w >> ((j & 3) * 8)) & 0xffu;
+}
+
+// ---- look-back descriptors ------------------------------------------------------
+// One 64-bit word per tile: [63:62] state, [61:0] value, so state and value are
+// published by a single store and no fence is needed.
+constexpr uint64_t DESC_INVALID = 0, DESC_AGG = 1, DESC_PREFIX = 2;
+constexpr uint64_t DESC_VALUE_MASK = (1ull << 62) - 1;
+
+__device__ __forceinline__ uint64_t desc_pack(uint64_t state, uint64_t value) { return (state << 62) | value; }
+__device__ __forceinline__ uint64_t desc_state(uint64_t d) { return d >> 62; }
+__device__ __forceinline__ uint64_t desc_value(uint64_t d) { return d & DESC_VALUE_MASK; }
+
+__device__ __forceinline__ void desc_store(uint64_t *p, uint64_t v)
+{
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ uint64_t desc_load(const uint64_t *p)
+{
+    uint64_t v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// ---- warp primitives ------------------------------------------------------------
+__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v)
+{
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t t = __shfl_up_sync(FULL, v, d);
+        if (lane_id() >= (unsigned)d) v += t;
+    }
+    return v;
+}
+__device__ __forceinline__ uint64_t warp_sum64(uint64_t v)
+{
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(FULL, v, d);
+    return v;
+}
+
+// Exclusive scan of one uint32 per thread over a CTA of NT threads (NT multiple
+// of 32, <= 1024).  `smem` needs NT/32 + 1 words.  Returns the exclusive prefix;
+// *total receives the CTA total.  Contains two __syncthreads().
+template <int NT>
+__device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t *smem, uint32_t *total)
+{
+    constexpr int NW = NT / 32;
+    const uint32_t incl = warp_incl_scan(v);
+    if (lane_id() == 31) smem[warp_id()] = incl;
+    __syncthreads();
+    if (warp_id() == 0) {
+        uint32_t w = (lane_id() < NW) ? smem[lane_id()] : 0u;
+        uint32_t wi = warp_incl_scan(w);
+        if (lane_id() < NW) smem[lane_id()] = wi - w;
+        if (lane_id() == NW - 1) smem[NW] = wi;
+    }
+    __syncthreads();
+    *total = smem[NW];
+    return smem[warp_id()] + incl - v;
+}
+
+// Decoupled look-back (Merrill & Garland) over a chain of tiles [first, tile).
+// Called by all 32 lanes of ONE warp.  Walks the predecessors of `tile` back to
+// the nearest one that has published an inclusive prefix and returns the sum of
+// everything in between (= the exclusive prefix of `tile`).  Tiles before
+// `first` count as an inclusive prefix of 0.
+__device__ __forceinline__ uint64_t lookback_read(const uint64_t *desc, int64_t tile, int64_t first)
+{
+    const unsigned lane = lane_id();
+    uint64_t excl = 0;
+    int64_t pos = tile - 1;
+    for (;;) {
+        const int64_t idx = pos - (int64_t)lane;
+        uint64_t d = desc_pack(DESC_PREFIX, 0);
+        if (idx >= first) d = desc_load(desc + idx);
+        while (__any_sync(FULL, desc_state(d) == DESC_INVALID)) {
+            if (idx >= first && desc_state(d) == DESC_INVALID) d = desc_load(desc + idx);
+        }
+        const unsigned pm = __ballot_sync(FULL, desc_state(d) == DESC_PREFIX);
+        const unsigned upto = pm ? (unsigned)(__ffs(pm) - 1) : 31u;  // lanes 0..upto contribute
+        excl += warp_sum64(lane <= upto ? desc_value(d) : 0ull);
+        if (pm) break;
+        pos -= 32;
+    }
+    return excl;
+}
+
+// Publish this tile's aggregate, look back, publish the inclusive prefix; returns
+// the exclusive prefix.  Values must stay below 2^62.
+__device__ __forceinline__ uint64_t lookback_sum(uint64_t *desc, int64_t tile, int64_t first, uint64_t aggregate)
+{
+    const unsigned lane = lane_id();
+    if (tile == first) {
+        if (lane == 0) desc_store(desc + tile, desc_pack(DESC_PREFIX, aggregate));
+        return 0;
+    }
+    if (lane == 0) desc_store(desc + tile, desc_pack(DESC_AGG, aggregate));
+    const uint64_t excl = lookback_read(desc, tile, first);
+    if (lane == 0) desc_store(desc + tile, desc_pack(DESC_PREFIX, excl + aggregate));
+    return excl;
+}
+
+// bit j of the result = (byte j of v equals the byte before it); `prev` is the
+// byte preceding byte 0
+__device__ __forceinline__ uint32_t eq_prev_mask16(const uint4 &v, uint32_t prev)
+{
+    const uint32_t sx = (v.x << 8) | (prev & 0xffu);
+    const uint32_t sy = __funnelshift_l(v.x, v.y, 8);
+    const uint32_t sz = __funnelshift_l(v.y, v.z, 8);
+    const uint32_t sw = __funnelshift_l(v.z, v.w, 8);
+    auto nib = [](uint32_t a, uint32_t b) -> uint32_t {
+        const uint32_t m = __vcmpeq4(a, b) & 0x01010101u;
+        return (m | (m >> 7) | (m >> 14) | (m >> 21)) & 0xFu;
+    };
+    return nib(v.x, sx) | (nib(v.y, sy) << 4) | (nib(v.z, sz) << 8) | (nib(v.w, sw) << 12);
+}
+
+// bit j = (byte j of v == 0)
+__device__ __forceinline__ uint32_t zero_mask16(const uint4 &v)
+{
+    auto nib = [](uint32_t a) -> uint32_t {
+        const uint32_t m = __vcmpeq4(a, 0u) & 0x01010101u;
+        return (m | (m >> 7) | (m >> 14) | (m >> 21)) & 0xFu;
+    };
+    return nib(v.x) | (nib(v.y) << 4) | (nib(v.z) << 8) | (nib(v.w) << 12);
+}
+
+// Largest b with tile0[b] <= t  (tile0 has nb+1 monotone entries, tile0[nb] = total)
+__device__ __forceinline__ uint32_t find_block(const uint64_t *__restrict__ tile0, uint32_t nb, uint64_t t)
+{
+    uint32_t lo = 0, hi = nb;  // invariant: tile0[lo] <= t < tile0[hi]
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (__ldg(tile0 + mid) <= t)
+            lo = mid;
+        else
+            hi = mid;
+    }
+    return lo;
+}
+
+}  // namespace shafa

@@ -1,0 +1,343 @@
+// core.h -- per-thread arithmetic of the Shafa kernels, as host+device inline
+// functions.  The CUDA kernels call these from their tiles; tests/cpu/emu.cpp
+// calls the very same functions from a sequential tile emulator, so the rules
+// (RLE emission, RLE parse automaton, Shannon-Fano split, bit packing, prefix
+// decode) are checked against the oracle on the CPU before any GPU time is spent.
+//
+// Reference rules restated here (paths under /root/reference/src/modules):
+//   RLE encode   f.c:29-55      RLE decode  d.c:144-186
+//   SF split     t.c:130-152    bit packing c.c:52-83     prefix decode d.c:514-551
+#pragma once
+
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define SHAFA_HD __host__ __device__ __forceinline__
+#else
+#define SHAFA_HD inline
+#endif
+
+namespace shafa {
+
+SHAFA_HD int ctz32(uint32_t x)
+{
+#if defined(__CUDA_ARCH__)
+    return __ffs((int)x) - 1;
+#else
+    return __builtin_ctz(x);
+#endif
+}
+SHAFA_HD int clz32(uint32_t x)
+{
+#if defined(__CUDA_ARCH__)
+    return __clz((int)x);
+#else
+    return x ? __builtin_clz(x) : 32;
+#endif
+}
+SHAFA_HD uint32_t bswap32(uint32_t x)
+{
+#if defined(__CUDA_ARCH__)
+    return __byte_perm(x, 0, 0x0123);
+#else
+    return __builtin_bswap32(x);
+#endif
+}
+
+// =============================================================================
+// RLE encode (f.c:29-55) as a per-position rule.
+//
+// Let k be the offset of position p inside its maximal equal-byte run (runs are
+// cut at block edges), c = k mod 255 and rem the run length remaining from p
+// (capped at 255).  The greedy loop of the reference emits, at p:
+//   c == 0            : {0,sym,rem} if sym == 0 or rem >= 4, else the literal sym
+//   1 <= c <= 3       : the literal sym if sym != 0 and c + rem < 4
+//   otherwise         : nothing
+// "Heads" are the first positions of runs; `heads` is a bitmask over tile
+// positions (bit p of word p>>5) that also has every position at or past the
+// block end set, and must be readable up to bit p+255 for any queried p.
+// =============================================================================
+
+constexpr int RLE_TILE = 4096;          // bytes per tile
+constexpr int RLE_ITEMS = 16;           // bytes per thread
+constexpr int RLE_HALO = 288;           // look-ahead positions kept after the tile
+constexpr int RLE_HEAD_WORDS = (RLE_TILE + RLE_HALO) / 32;
+
+// distance from p to the next head strictly after p, capped at 255 (= min(rem,255))
+SHAFA_HD uint32_t rle_run_remaining(const uint32_t *heads, uint32_t p)
+{
+    uint32_t q = p + 1;
+    const uint32_t end = p + 256;  // inspect positions p+1 .. p+255
+    while (q < end) {
+        const uint32_t w = heads[q >> 5] >> (q & 31);
+        if (w) {
+            const uint32_t d = q + (uint32_t)ctz32(w) - p;
+            return d < 255 ? d : 255;
+        }
+        q = (q | 31u) + 1;
+    }
+    return 255;
+}
+
+struct RleEmit {
+    uint32_t lit;     // bit j: position j emits a literal
+    uint32_t tri;     // bit j: position j emits a triple
+    uint32_t cnt[4];  // count byte of the triple at position j = (cnt[j>>2] >> 8*(j&3)) & 255
+    uint32_t bytes;   // bytes emitted by this thread
+};
+
+// Decide what the RLE_ITEMS positions starting at tile position p0 emit.
+// `sym(j)` = byte at p0+j; nvalid = number of positions of this thread inside
+// the block (0..16); c0 = (k mod 255) at p0, used when p0 is not a head.
+template <typename SymFn>
+SHAFA_HD RleEmit rle_emit_thread(const uint32_t *heads, uint32_t p0, int nvalid, uint32_t c0, SymFn sym)
+{
+    RleEmit e;
+    e.lit = e.tri = e.bytes = 0;
+    e.cnt[0] = e.cnt[1] = e.cnt[2] = e.cnt[3] = 0;
+    uint32_t c = c0;
+#pragma unroll
+    for (int j = 0; j < RLE_ITEMS; j++) {
+        if (j < nvalid) {
+            const uint32_t p = p0 + (uint32_t)j;
+            if ((heads[p >> 5] >> (p & 31)) & 1u) c = 0;
+            if (c <= 3) {
+                const uint32_t s = sym(j);
+                const uint32_t rem = rle_run_remaining(heads, p);
+                if (c == 0) {
+                    if (s == 0 || rem >= 4) {
+                        e.tri |= 1u << j;
+                        e.cnt[j >> 2] |= rem << (8 * (j & 3));
+                        e.bytes += 3;
+                    } else {
+                        e.lit |= 1u << j;
+                        e.bytes += 1;
+                    }
+                } else if (s != 0 && c + rem < 4) {
+                    e.lit |= 1u << j;
+                    e.bytes += 1;
+                }
+            }
+            c = (c == 254) ? 0 : c + 1;
+        }
+    }
+    return e;
+}
+
+// Write this thread's emitted bytes to dst (dst points at the thread's first
+// output byte).  Returns bytes written (== e.bytes).
+template <typename SymFn>
+SHAFA_HD uint32_t rle_write_thread(const RleEmit &e, uint8_t *dst, SymFn sym)
+{
+    uint32_t o = 0;
+#pragma unroll
+    for (int j = 0; j < RLE_ITEMS; j++) {
+        if ((e.tri >> j) & 1u) {
+            dst[o] = 0;
+            dst[o + 1] = (uint8_t)sym(j);
+            dst[o + 2] = (uint8_t)((e.cnt[j >> 2] >> (8 * (j & 3))) & 255u);
+            o += 3;
+        } else if ((e.lit >> j) & 1u) {
+            dst[o++] = (uint8_t)sym(j);
+        }
+    }
+    return o;
+}
+
+// =============================================================================
+// RLE decode (d.c:144-186) as a 3-state automaton over the RLE bytes:
+//   state 0 (start)      : byte 0x00 -> state 1, else literal (emit 1) -> state 0
+//   state 1 (expect sym) : any byte -> state 2
+//   state 2 (expect cnt) : emit cnt copies of the previous byte (1 if cnt == 0) -> state 0
+// A thread summarises its bytes [j0, j1) as a map entry-state -> exit-state,
+// packed 2 bits per entry state; maps compose associatively.
+// =============================================================================
+
+constexpr uint32_t FSM_IDENTITY = 0u | (1u << 2) | (2u << 4);
+
+SHAFA_HD uint32_t fsm_apply(uint32_t map, uint32_t state) { return (map >> (2 * state)) & 3u; }
+// first a, then b
+SHAFA_HD uint32_t fsm_compose(uint32_t a, uint32_t b)
+{
+    return fsm_apply(b, fsm_apply(a, 0)) | (fsm_apply(b, fsm_apply(a, 1)) << 2) | (fsm_apply(b, fsm_apply(a, 2)) << 4);
+}
+SHAFA_HD bool fsm_is_const(uint32_t m) { return fsm_apply(m, 0) == fsm_apply(m, 1) && fsm_apply(m, 1) == fsm_apply(m, 2); }
+
+// zmask bit q = (valid byte q == 0); the thread's valid bytes are [0, n), n <= 16
+// (callers shift the mask so that the first valid byte is bit 0).
+// ex[q] = exit state when the automaton is in state 0 at position q; past the
+// end an overshoot of 0/1/2 positions means state 0 / 2 (count pending) / 1 (sym
+// pending).  ex[q] = zero(q) ? ex[q+3] : ex[q+1], evaluated right to left in
+// three rolling registers so that it unrolls without local memory.
+SHAFA_HD uint32_t fsm_thread_map(uint32_t zmask, int n)
+{
+    uint32_t a = 0, b = 2, c = 1;  // ex[q+1], ex[q+2], ex[q+3] for q = n-1
+#pragma unroll
+    for (int q = RLE_ITEMS - 1; q >= 0; q--) {
+        if (q < n) {
+            const uint32_t v = ((zmask >> q) & 1u) ? c : a;
+            c = b;
+            b = a;
+            a = v;
+        }
+    }
+    // entry 0: state 0 at position 0 -> ex[0]; entry 1: sym at 0, count at 1 -> ex[2];
+    // entry 2: count at 0 -> ex[1]
+    return a | (c << 2) | (b << 4);
+}
+
+// Walk the thread's n valid bytes from entry state `state`; `byte(q)` returns
+// byte q, prev = the byte just before byte 0 (needed when entering in state 2).
+// emit(len, sym) is called once per record, in order.  Returns the exit state.
+template <typename ByteFn, typename EmitFn>
+SHAFA_HD uint32_t rle_parse_thread(uint32_t state, int n, uint32_t prev, ByteFn byte, EmitFn emit)
+{
+    uint32_t s = state, last = prev;
+#pragma unroll
+    for (int q = 0; q < RLE_ITEMS; q++) {
+        if (q < n) {
+            const uint32_t v = byte(q);
+            if (s == 0) {
+                if (v == 0)
+                    s = 1;
+                else
+                    emit(1u, v);
+            } else if (s == 1) {
+                s = 2;
+            } else {
+                emit(v ? v : 1u, last);  // d.c:179-184: count 0 -> one copy
+                s = 0;
+            }
+            last = v;
+        }
+    }
+    return s;
+}
+
+// =============================================================================
+// Shannon-Fano split (t.c:130-152): among d in [lo, hi-1] the SMALLEST d that
+// minimises |2*(P[d+1]-P[lo]) - (P[hi+1]-P[lo])|.  P is the exclusive prefix of
+// the rank-sorted counts (P[0] = 0, P[r+1] = sum of ranks 0..r); every count in
+// [lo, hi] is > 0, so the sequence is strictly V-shaped and a binary search for
+// the crossing point plus one comparison reproduces the reference's
+// first-local-minimum scan (strict '<' keeps the smaller d on ties).
+// =============================================================================
+SHAFA_HD int sf_split(const uint32_t *P, int lo, int hi)
+{
+    const uint64_t base = P[lo];
+    const uint64_t T = (uint64_t)P[hi + 1] - base;
+    int a = lo, c = hi;
+    while (a < c) {  // smallest d with 2*left(d) >= T
+        const int m = (a + c) >> 1;
+        if (2 * ((uint64_t)P[m + 1] - base) >= T)
+            c = m;
+        else
+            a = m + 1;
+    }
+    const int dstar = a;
+    if (dstar == lo) return lo;
+    const uint64_t dif1 = T - 2 * ((uint64_t)P[dstar] - base);  // at dstar-1, positive
+    if (dstar == hi) return hi - 1;
+    const uint64_t dif2 = 2 * ((uint64_t)P[dstar + 1] - base) - T;  // at dstar, >= 0
+    return (dif1 <= dif2) ? dstar - 1 : dstar;
+}
+
+// =============================================================================
+// Bit packing (c.c:52-83): codes are concatenated MSB-first.  Output is handled
+// as big-endian 32-bit words (bit 31 of word w = stream bit 32*w) that are
+// byte-swapped when stored.
+// =============================================================================
+
+constexpr int ENC_SHORT_MAX = 26;                          // fast path: code + 5-bit length in one word
+SHAFA_HD uint32_t enc_entry(uint64_t code, uint32_t len) { return ((uint32_t)code << 5) | len; }
+
+// 64-bit window starting at bit `q` of a big-endian word array
+SHAFA_HD uint64_t bit_window(const uint32_t *words, uint32_t q)
+{
+    const uint32_t i = q >> 5, sh = q & 31u;
+    const uint64_t hi = ((uint64_t)words[i] << 32) | words[i + 1];
+    return sh ? ((hi << sh) | (uint64_t)(words[i + 2] >> (32 - sh))) : hi;
+}
+
+// =============================================================================
+// Prefix decode (d.c:514-551) with a 12-bit first-level table and a sorted
+// fallback for longer codes.  A Shannon-Fano code (any prefix-free code) sorted
+// by its left-aligned bits has the property that the code matching a window is
+// the LARGEST left-aligned code <= window.
+// =============================================================================
+constexpr int DEC_LUT_BITS = 12;
+constexpr int DEC_LUT_SIZE = 1 << DEC_LUT_BITS;
+constexpr uint32_t DEC_LONG = 0xFF;   // lut entry low byte: 1..12 length, 0 invalid, 0xFF -> fallback
+
+struct DecTables {
+    const uint16_t *lut;     // [4096]  (sym << 8) | len
+    const uint64_t *sleft;   // [256] left-aligned codes, ascending (absent = ~0)
+    const uint8_t *slen;     // [256]
+    const uint8_t *ssym;     // [256]
+};
+
+// returns code length (>= 1) and *sym, or 0 if the window matches no code
+SHAFA_HD uint32_t dec_symbol(const DecTables &t, uint64_t window, uint32_t *sym)
+{
+    const uint32_t e = t.lut[window >> (64 - DEC_LUT_BITS)];
+    const uint32_t l = e & 0xFFu;
+    if (l - 1u < (uint32_t)DEC_LUT_BITS) {
+        *sym = e >> 8;
+        return l;
+    }
+    if (l != DEC_LONG) return 0;
+    int lo = 0, hi = 256;  // count of entries <= window
+    while (lo < hi) {
+        const int m = (lo + hi) >> 1;
+        if (t.sleft[m] <= window)
+            lo = m + 1;
+        else
+            hi = m;
+    }
+    if (lo == 0) return 0;
+    const int r = lo - 1;
+    const uint32_t len = t.slen[r];
+    if (len == 0) return 0;
+    if ((window >> (64 - len)) != (t.sleft[r] >> (64 - len))) return 0;
+    *sym = t.ssym[r];
+    return len;
+}
+
+constexpr int DEC_SUB_BITS = 128;                      // sub-sequence (one thread)
+constexpr int DEC_THREADS = 256;                       // sub-sequences per sequence (one CTA)
+constexpr int DEC_SEQ_BYTES = DEC_SUB_BITS * DEC_THREADS / 8;  // 4096
+constexpr int DEC_SEQ_WORDS = DEC_SEQ_BYTES / 4;       // 1024
+constexpr int DEC_WORDS_PAD = 4;                       // look-ahead words after the sequence
+
+struct DecSub {
+    uint32_t end;    // bit position (relative to the sequence) where decoding stopped
+    uint32_t count;  // symbols that START inside [start, stop)
+    uint32_t bad;    // a window matched no code
+};
+
+// Decode from bit `start` until reaching `stop` (both relative to the sequence
+// words).  If out != nullptr the symbols are stored to out[0..] while fewer
+// than `max_out` have been written.
+SHAFA_HD DecSub dec_subsequence(const uint32_t *words, const DecTables &t, uint32_t start, uint32_t stop,
+                                uint8_t *out, uint32_t max_out)
+{
+    DecSub r;
+    r.count = 0;
+    r.bad = 0;
+    uint32_t q = start;
+    while (q < stop) {
+        uint32_t sym = 0;
+        uint32_t l = dec_symbol(t, bit_window(words, q), &sym);
+        if (l == 0) {
+            r.bad = 1;
+            l = 1;
+        }
+        if (out && r.count < max_out) out[r.count] = (uint8_t)sym;
+        r.count++;
+        q += l;
+    }
+    r.end = q;
+    return r;
+}
+
+}  // namespace shafa

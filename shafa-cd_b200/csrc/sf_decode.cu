@@ -1,0 +1,421 @@
+// sf_decode.cu -- Shannon-Fano prefix decode (reference create_tree +
+// shafa_block_decompressor, d.c:422-551), parallel inside a block.
+//
+// The .shaf format has no sync points, so this is self-synchronising
+// sub-sequence decoding (Weissenberger & Schmidt, ICPP'18):
+//   k_dec_tables   per block: codes sorted by left-aligned bits + 12-bit LUT
+//   k_dec_sync     one CTA per 4 KiB "sequence" of a block's payload, one thread
+//                  per 128-bit sub-sequence: decode speculatively from the
+//                  sub-sequence start, then repeatedly restart from where the
+//                  left neighbour really ended until nothing changes
+//   k_dec_stitch   across sequence boundaries: feed each sequence the true end
+//                  of its predecessor and re-walk until it meets the recorded
+//                  state; repeated while anything changed
+//   k_dec_count / k_dec_scan   symbols per sequence -> output offsets
+//   k_dec_write    final decode from the agreed start points, symbols written
+//                  at their scanned offsets, clipped at the block's symbol count
+// Algorithmic bytes: Z (payload in) + S (symbols out).
+#include "common.cuh"
+#include "core.h"
+#include "internal.h"
+
+namespace shafa {
+
+// ---- tables -----------------------------------------------------------------------------
+struct DecTablesGlobal {
+    uint16_t *lut;    // [nb][4096]
+    uint64_t *sleft;  // [nb][256]
+    uint8_t *slen;    // [nb][256]
+    uint8_t *ssym;    // [nb][256]
+};
+
+__global__ void __launch_bounds__(256)
+k_dec_tables(const uint8_t *__restrict__ lens, const uint64_t *__restrict__ codes, DecTablesGlobal g)
+{
+    __shared__ uint64_t left[256];
+    __shared__ uint8_t len_s[256];
+    __shared__ uint64_t sl[256];
+    __shared__ uint8_t sn[256];
+    __shared__ uint8_t ss[256];
+    const unsigned s = threadIdx.x;
+    const uint64_t b = blockIdx.x;
+    const uint32_t l = lens[b * 256 + s];
+    const uint64_t c = codes[b * 256 + s];
+    const uint64_t lf = l ? (c << (64 - l)) : ~0ull;
+    left[s] = lf;
+    len_s[s] = (uint8_t)l;
+    __syncthreads();
+    // order by (left-aligned code, absent last, symbol)
+    uint32_t rank = 0;
+    for (int t = 0; t < 256; t++) {
+        const uint64_t o = left[t];
+        const uint32_t ol = len_s[t];
+        const bool before = (o < lf) || (o == lf && ((ol != 0 && l == 0) || ((ol != 0) == (l != 0) && (unsigned)t < s)));
+        rank += before;
+    }
+    sl[rank] = lf;
+    sn[rank] = (uint8_t)l;
+    ss[rank] = (uint8_t)s;
+    __syncthreads();
+    g.sleft[b * 256 + s] = sl[s];
+    g.slen[b * 256 + s] = sn[s];
+    g.ssym[b * 256 + s] = ss[s];
+    for (int e = s; e < DEC_LUT_SIZE; e += 256) {
+        const uint64_t window = (uint64_t)e << (64 - DEC_LUT_BITS);
+        int lo = 0, hi = 256;
+        while (lo < hi) {
+            const int m = (lo + hi) >> 1;
+            if (sl[m] <= window)
+                lo = m + 1;
+            else
+                hi = m;
+        }
+        uint16_t entry = 0;
+        if (lo > 0) {
+            const int r = lo - 1;
+            const uint32_t rl = sn[r];
+            if (rl != 0 && rl <= (uint32_t)DEC_LUT_BITS && (window >> (64 - rl)) == (sl[r] >> (64 - rl)))
+                entry = (uint16_t)(((uint32_t)ss[r] << 8) | rl);
+            else
+                entry = (uint16_t)DEC_LONG;
+        }
+        g.lut[b * DEC_LUT_SIZE + e] = entry;
+    }
+}
+
+// ---- shared helpers -----------------------------------------------------------------------
+struct DecPlan {
+    const uint64_t *pay_off;  // [nb]
+    const uint64_t *z;        // [nb]
+    const uint64_t *n;        // [nb] symbols per block
+    const uint64_t *out_off;  // [nb] output offset of each block
+    const uint64_t *seq0;     // [nb+1] first sequence of each block
+    uint32_t nb;
+};
+
+struct DecShared {
+    uint32_t words[DEC_SEQ_WORDS + DEC_WORDS_PAD];
+    uint16_t lut[DEC_LUT_SIZE];
+    uint64_t sleft[256];
+    uint8_t slen[256];
+    uint8_t ssym[256];
+    uint32_t ends[DEC_THREADS];
+    uint32_t scan[DEC_THREADS / 32 + 1];
+    uint32_t block;
+};
+
+// load tables + the sequence's payload words (big-endian) into shared memory
+__device__ __forceinline__ void dec_load_sequence(DecShared &sh, const DecTablesGlobal &g, const uint8_t *payload,
+                                                  uint64_t pay_off, uint64_t z, uint64_t seq_in_block, uint32_t b)
+{
+    const unsigned tid = threadIdx.x;
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(g.lut + (uint64_t)b * DEC_LUT_SIZE);
+        uint4 *dst = reinterpret_cast<uint4 *>(sh.lut);
+        for (int i = tid; i < DEC_LUT_SIZE * 2 / 16; i += DEC_THREADS) dst[i] = src[i];
+        sh.sleft[tid] = g.sleft[(uint64_t)b * 256 + tid];
+        sh.slen[tid] = g.slen[(uint64_t)b * 256 + tid];
+        sh.ssym[tid] = g.ssym[(uint64_t)b * 256 + tid];
+    }
+    const uint64_t byte0 = seq_in_block * DEC_SEQ_BYTES;  // offset of this sequence in the block's payload
+    const uint64_t slot = (z + 15) & ~15ull;              // readable bytes of the block's slot
+    const uint8_t *base = payload + pay_off;
+    for (int i = tid; i < (DEC_SEQ_WORDS + DEC_WORDS_PAD) / 4; i += DEC_THREADS) {
+        const uint64_t o = byte0 + (uint64_t)i * 16;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (o < slot) v = ld_stream16(base + o);
+        uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const uint64_t bo = o + 4 * k;  // bytes at or past z read as zero
+            uint32_t x = w[k];
+            if (bo >= z)
+                x = 0;
+            else if (bo + 4 > z)
+                x &= (0xffffffffu >> (8 * (uint32_t)(bo + 4 - z)));
+            sh.words[i * 4 + k] = bswap32(x);
+        }
+    }
+}
+
+__device__ __forceinline__ DecTables dec_tables_of(const DecShared &sh)
+{
+    DecTables t;
+    t.lut = sh.lut;
+    t.sleft = sh.sleft;
+    t.slen = sh.slen;
+    t.ssym = sh.ssym;
+    return t;
+}
+
+// sub-sequence record: low 8 bits = start offset inside the sub-sequence (< 64),
+// high 8 bits... counts can reach 128, so: bits [6:0] start, bits [15:7] count
+__device__ __forceinline__ uint16_t sub_pack(uint32_t start, uint32_t count) { return (uint16_t)(start | (count << 7)); }
+__device__ __forceinline__ uint32_t sub_start(uint16_t v) { return v & 127u; }
+__device__ __forceinline__ uint32_t sub_count(uint16_t v) { return v >> 7; }
+
+// ---- phase 1: synchronise inside each sequence ----------------------------------------------
+__global__ void __launch_bounds__(DEC_THREADS)
+k_dec_sync(const uint8_t *__restrict__ payload, DecPlan plan, DecTablesGlobal g, uint16_t *__restrict__ sub_info,
+           uint32_t *__restrict__ seq_end, uint32_t *__restrict__ err)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    DecShared &sh = *reinterpret_cast<DecShared *>(smem_raw);
+    const unsigned tid = threadIdx.x;
+    const uint64_t seq = blockIdx.x;
+    if (tid == 0) sh.block = find_block(plan.seq0, plan.nb, seq);
+    __syncthreads();
+    const uint32_t b = sh.block;
+    const uint64_t sib = seq - plan.seq0[b];
+    const uint64_t z = plan.z[b];
+    dec_load_sequence(sh, g, payload, plan.pay_off[b], z, sib, b);
+    __syncthreads();
+    const DecTables t = dec_tables_of(sh);
+    // bits of this sequence that exist in the payload
+    const uint64_t bits_left = (z - sib * DEC_SEQ_BYTES) * 8;
+    const uint32_t limit = bits_left < (uint64_t)DEC_SEQ_BYTES * 8 ? (uint32_t)bits_left : DEC_SEQ_BYTES * 8;
+    const uint32_t sub_lo = tid * DEC_SUB_BITS;
+    const uint32_t sub_hi = sub_lo + DEC_SUB_BITS;
+    const uint32_t stop = sub_hi < limit ? sub_hi : limit;
+
+    uint32_t start = 0, bad = 0;
+    DecSub r = dec_subsequence(sh.words, t, sub_lo + start, stop, nullptr, 0);
+    uint32_t my_end = r.end > sub_hi ? r.end - sub_hi : 0;  // overshoot into the next sub-sequence
+    bad = r.bad;
+    for (;;) {
+        sh.ends[tid] = my_end;
+        __syncthreads();
+        const uint32_t want = tid ? sh.ends[tid - 1] : 0u;
+        const int changed = (want != start);
+        if (!__syncthreads_or(changed)) break;
+        if (changed) {
+            start = want;
+            r = dec_subsequence(sh.words, t, sub_lo + start, stop, nullptr, 0);
+            my_end = r.end > sub_hi ? r.end - sub_hi : 0;
+            bad = r.bad;
+        }
+    }
+    sub_info[seq * DEC_THREADS + tid] = sub_pack(start, r.count);
+    if (tid == DEC_THREADS - 1) seq_end[seq] = my_end;
+    (void)bad;  // a speculative start may hit garbage; errors are judged in k_dec_write
+    (void)err;
+}
+
+// ---- phase 2: stitch sequences together -------------------------------------------------------
+// one thread per sequence; reads payload bytes straight from global memory (only a
+// few sub-sequences per sequence are ever touched)
+__device__ __forceinline__ uint64_t window_global(const uint8_t *base, uint64_t z, uint64_t bit)
+{
+    const uint64_t byte = bit >> 3;
+    uint64_t hi = 0;
+    uint32_t lo = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) hi = (hi << 8) | (byte + k < z ? base[byte + k] : 0u);
+    lo = (byte + 8 < z) ? base[byte + 8] : 0u;
+    const uint32_t sh = (uint32_t)(bit & 7u);
+    return sh ? ((hi << sh) | (lo >> (8 - sh))) : hi;
+}
+
+__global__ void __launch_bounds__(128)
+k_dec_stitch(const uint8_t *__restrict__ payload, DecPlan plan, DecTablesGlobal g, uint16_t *__restrict__ sub_info,
+             uint32_t *__restrict__ seq_end, uint64_t nseq, uint32_t *__restrict__ changed_flag)
+{
+    const uint64_t seq = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (seq >= nseq) return;
+    const uint32_t b = find_block(plan.seq0, plan.nb, seq);
+    const uint64_t sib = seq - plan.seq0[b];
+    if (sib == 0) return;  // first sequence of a block starts at bit 0 by definition
+    uint32_t cur = seq_end[seq - 1];
+    const uint64_t z = plan.z[b];
+    const uint8_t *base = payload + plan.pay_off[b];
+    DecTables t;
+    t.lut = g.lut + (uint64_t)b * DEC_LUT_SIZE;
+    t.sleft = g.sleft + (uint64_t)b * 256;
+    t.slen = g.slen + (uint64_t)b * 256;
+    t.ssym = g.ssym + (uint64_t)b * 256;
+    const uint64_t seq_bit0 = sib * DEC_SEQ_BYTES * 8;
+    const uint64_t total_bits = z * 8;
+    bool touched = false;
+    for (uint32_t k = 0; k < DEC_THREADS; k++) {
+        const uint64_t gi = seq * DEC_THREADS + k;
+        const uint16_t rec = sub_info[gi];
+        if (sub_start(rec) == cur) break;  // met the recorded state: everything after is already right
+        const uint64_t lo = seq_bit0 + (uint64_t)k * DEC_SUB_BITS;
+        const uint64_t hi = lo + DEC_SUB_BITS;
+        const uint64_t stop = hi < total_bits ? hi : total_bits;
+        uint64_t q = lo + cur;
+        uint32_t count = 0;
+        while (q < stop) {
+            uint32_t sym;
+            uint32_t l = dec_symbol(t, window_global(base, z, q), &sym);
+            if (!l) l = 1;
+            q += l;
+            count++;
+        }
+        sub_info[gi] = sub_pack(cur, count);
+        touched = true;
+        cur = q > hi ? (uint32_t)(q - hi) : 0u;
+        if (k == DEC_THREADS - 1 && seq_end[seq] != cur) seq_end[seq] = cur;
+    }
+    if (touched) atomicOr(changed_flag, 1u);
+}
+
+// ---- phase 3: symbols per sequence, offsets ---------------------------------------------------
+__global__ void __launch_bounds__(DEC_THREADS)
+k_dec_count(const uint16_t *__restrict__ sub_info, uint32_t *__restrict__ seq_count)
+{
+    __shared__ uint32_t scan[DEC_THREADS / 32 + 1];
+    const uint64_t seq = blockIdx.x;
+    uint32_t total;
+    block_excl_scan<DEC_THREADS>(sub_count(sub_info[seq * DEC_THREADS + threadIdx.x]), scan, &total);
+    if (threadIdx.x == 0) seq_count[seq] = total;
+}
+
+// one CTA per block: exclusive scan of its sequences' counts; checks the block holds >= n symbols
+__global__ void __launch_bounds__(256)
+k_dec_scan(DecPlan plan, const uint32_t *__restrict__ seq_count, uint64_t *__restrict__ seq_excl,
+           uint32_t *__restrict__ err)
+{
+    __shared__ uint32_t scan[9];
+    __shared__ unsigned long long s_carry;
+    const uint32_t b = blockIdx.x;
+    const uint64_t s0 = plan.seq0[b], s1 = plan.seq0[b + 1];
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (uint64_t base = s0; base < s1; base += 256) {
+        const uint64_t i = base + threadIdx.x;
+        const uint32_t v = i < s1 ? seq_count[i] : 0u;
+        uint32_t total;
+        const uint32_t excl = block_excl_scan<256>(v, scan, &total);
+        if (i < s1) seq_excl[i] = s_carry + excl;
+        __syncthreads();
+        if (threadIdx.x == 0) s_carry += total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && s_carry < plan.n[b]) atomicOr(err, 8u);  // payload too short for n symbols
+}
+
+// ---- phase 4: final decode + write --------------------------------------------------------------
+__global__ void __launch_bounds__(DEC_THREADS)
+k_dec_write(const uint8_t *__restrict__ payload, DecPlan plan, DecTablesGlobal g,
+            const uint16_t *__restrict__ sub_info, const uint64_t *__restrict__ seq_excl, uint8_t *__restrict__ out,
+            uint32_t *__restrict__ err)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    DecShared &sh = *reinterpret_cast<DecShared *>(smem_raw);
+    const unsigned tid = threadIdx.x;
+    const uint64_t seq = blockIdx.x;
+    if (tid == 0) sh.block = find_block(plan.seq0, plan.nb, seq);
+    __syncthreads();
+    const uint32_t b = sh.block;
+    const uint64_t sib = seq - plan.seq0[b];
+    const uint64_t z = plan.z[b];
+    dec_load_sequence(sh, g, payload, plan.pay_off[b], z, sib, b);
+    const uint16_t rec = sub_info[seq * DEC_THREADS + tid];
+    uint32_t total;
+    const uint32_t excl = block_excl_scan<DEC_THREADS>(sub_count(rec), sh.scan, &total);  // also fences the loads above
+    const DecTables t = dec_tables_of(sh);
+    const uint64_t bits_left = (z - sib * DEC_SEQ_BYTES) * 8;
+    const uint32_t limit = bits_left < (uint64_t)DEC_SEQ_BYTES * 8 ? (uint32_t)bits_left : DEC_SEQ_BYTES * 8;
+    const uint32_t sub_lo = tid * DEC_SUB_BITS;
+    const uint32_t sub_hi = sub_lo + DEC_SUB_BITS;
+    const uint32_t stop = sub_hi < limit ? sub_hi : limit;
+    const uint64_t n = plan.n[b];
+    const uint64_t first = seq_excl[seq] + excl;  // index of this thread's first symbol inside the block
+    if (first >= n) return;                        // only padding garbage from here on
+    const uint64_t room = n - first;
+    uint8_t *dst = out + plan.out_off[b] + first;
+    const DecSub r = dec_subsequence(sh.words, t, sub_lo + sub_start(rec), stop, dst,
+                                     room > 0xffffffffull ? 0xffffffffu : (uint32_t)room);
+    // a bad window only matters if it produced one of the n real symbols
+    if (r.bad) atomicOr(err, 16u);
+}
+
+// ---- launcher -------------------------------------------------------------------------------------
+int launch_sf_decode(shafa_cuda_ctx *ctx, const uint8_t *d_payload, const uint64_t *h_payload_off,
+                     const uint64_t *h_z, const uint64_t *h_n, uint64_t nb, const uint8_t *d_len,
+                     const uint64_t *d_code, uint8_t *d_sym, uint32_t *d_err)
+{
+    if (nb == 0) return SHAFA_SUCCESS;
+    // plan arrays: pay_off[nb] z[nb] n[nb] out_off[nb] seq0[nb+1]
+    const size_t plan_words = 5 * nb + 1;
+    uint64_t *hp = (uint64_t *)pinned_get(ctx, plan_words * sizeof(uint64_t));
+    uint64_t *dp = (uint64_t *)scratch_get(ctx, SCR_PLAN, plan_words * sizeof(uint64_t));
+    if (!hp || !dp) return SHAFA_LACK_OF_MEMORY;
+    uint64_t nseq = 0, out_off = 0;
+    for (uint64_t b = 0; b < nb; b++) {
+        if (h_payload_off[b] & 15) return set_error(ctx, SHAFA_FILE_STREAM_FAILED, "sf_decode: payload offset not 16-byte aligned");
+        hp[b] = h_payload_off[b];
+        hp[nb + b] = h_z[b];
+        hp[2 * nb + b] = h_n[b];
+        hp[3 * nb + b] = out_off;
+        hp[4 * nb + b] = nseq;
+        out_off += h_n[b];
+        nseq += (h_z[b] + DEC_SEQ_BYTES - 1) / DEC_SEQ_BYTES;
+        if (h_n[b] != 0 && h_z[b] == 0) return set_error(ctx, SHAFA_FILE_UNRECOGNIZABLE, "sf_decode: block %llu has symbols but an empty payload", (unsigned long long)b);
+    }
+    hp[5 * nb] = nseq;
+    if (nseq == 0) return SHAFA_SUCCESS;
+    if (nseq > 0x7fffffffull) return set_error(ctx, SHAFA_LACK_OF_MEMORY, "sf_decode: too many sequences");
+    SHAFA_CUDA_TRY(ctx, cudaMemcpyAsync(dp, hp, plan_words * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+    DecPlan plan;
+    plan.pay_off = dp;
+    plan.z = dp + nb;
+    plan.n = dp + 2 * nb;
+    plan.out_off = dp + 3 * nb;
+    plan.seq0 = dp + 4 * nb;
+    plan.nb = (uint32_t)nb;
+
+    // tables
+    const size_t lut_bytes = nb * DEC_LUT_SIZE * sizeof(uint16_t);
+    const size_t tab_bytes = lut_bytes + nb * 256 * (sizeof(uint64_t) + 2);
+    uint8_t *tab = (uint8_t *)scratch_get(ctx, SCR_DEC_LUT, tab_bytes);
+    if (!tab) return SHAFA_LACK_OF_MEMORY;
+    DecTablesGlobal g;
+    g.sleft = (uint64_t *)tab;
+    g.lut = (uint16_t *)(tab + nb * 256 * sizeof(uint64_t));
+    g.slen = tab + nb * 256 * sizeof(uint64_t) + lut_bytes;
+    g.ssym = g.slen + nb * 256;
+
+    uint16_t *sub_info = (uint16_t *)scratch_get(ctx, SCR_DEC_SUB, nseq * DEC_THREADS * sizeof(uint16_t));
+    // seq arrays: seq_end u32[nseq], seq_count u32[nseq], seq_excl u64[nseq]
+    uint8_t *seqbuf = (uint8_t *)scratch_get(ctx, SCR_DEC_SEQ, nseq * 16 + 64);
+    uint32_t *flag = misc_ptr(ctx, MISC_FLAG);
+    if (!sub_info || !seqbuf || !flag) return SHAFA_LACK_OF_MEMORY;
+    uint64_t *seq_excl = (uint64_t *)seqbuf;
+    uint32_t *seq_end = (uint32_t *)(seqbuf + nseq * 8);
+    uint32_t *seq_count = seq_end + nseq;
+
+    static bool attr_done = false;
+    const size_t smem = sizeof(DecShared);
+    if (!attr_done) {
+        SHAFA_CUDA_TRY(ctx, cudaFuncSetAttribute(k_dec_sync, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SHAFA_CUDA_TRY(ctx, cudaFuncSetAttribute(k_dec_write, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done = true;
+    }
+    SHAFA_LAUNCH(ctx, "dec_tables", k_dec_tables, dim3((unsigned)nb), dim3(256), 0, d_len, d_code, g);
+    SHAFA_LAUNCH(ctx, "dec_sync", k_dec_sync, dim3((unsigned)nseq), dim3(DEC_THREADS), smem, d_payload, plan, g,
+                 sub_info, seq_end, d_err);
+    SHAFA_CHECK_LAUNCH(ctx);
+    // stitch until a pass changes nothing (normally 1-2 passes)
+    uint32_t *h_flag = (uint32_t *)pinned_get(ctx, 64);
+    if (!h_flag) return SHAFA_LACK_OF_MEMORY;
+    for (uint64_t pass = 0;; pass++) {
+        SHAFA_CUDA_TRY(ctx, cudaMemsetAsync(flag, 0, 4, ctx->stream));
+        SHAFA_LAUNCH(ctx, "dec_stitch", k_dec_stitch, dim3((unsigned)((nseq + 127) / 128)), dim3(128), 0, d_payload,
+                     plan, g, sub_info, seq_end, nseq, flag);
+        SHAFA_CHECK_LAUNCH(ctx);
+        SHAFA_CUDA_TRY(ctx, cudaMemcpyAsync(h_flag, flag, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        SHAFA_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        if (*h_flag == 0) break;
+        if (pass > nseq + 2) return set_error(ctx, SHAFA_FILE_UNRECOGNIZABLE, "sf_decode: stitching did not converge");
+    }
+    SHAFA_LAUNCH(ctx, "dec_count", k_dec_count, dim3((unsigned)nseq), dim3(DEC_THREADS), 0, sub_info, seq_count);
+    SHAFA_LAUNCH(ctx, "dec_scan", k_dec_scan, dim3((unsigned)nb), dim3(256), 0, plan, seq_count, seq_excl, d_err);
+    SHAFA_LAUNCH(ctx, "dec_write", k_dec_write, dim3((unsigned)nseq), dim3(DEC_THREADS), smem, d_payload, plan, g,
+                 sub_info, seq_excl, d_sym, d_err);
+    SHAFA_CHECK_LAUNCH(ctx);
+    return SHAFA_SUCCESS;
+}
+
+}  // namespace shafa

@@ -1,0 +1,374 @@
+// sf_encode.cu -- Shannon-Fano bit packing (reference compress_to_buffer +
+// binary_coding, c.c:52-83,91-237): per block, the codes of its symbols
+// concatenated MSB-first and zero padded to a byte.
+//
+// Single pass over the symbol stream (algorithmic bytes S + Z):
+//   * exact payload sizes come from histogram x code length (k_sf_block_bits),
+//     so every block gets a 16-byte aligned payload slot before encoding starts;
+//   * tiles are 4096-byte aligned windows of the stream intersected with the
+//     block (aligned 16-byte loads even for the ragged .rle stream);
+//   * per tile: conflict-free code LUT lookups (one private bank per lane),
+//     CTA scan of bit lengths, decoupled look-back along the block's tiles for
+//     the tile's bit offset, packing into big-endian words in shared memory, and
+//     coalesced word stores.  A 32-bit word that straddles two tiles is written
+//     by the tile holding its last bit, which re-encodes the <= 31 preceding
+//     symbols, so no output word is ever touched twice and no memset/atomics on
+//     global memory are needed.
+//   * blocks whose longest code exceeds 26 bits (never seen on real data; the
+//     format allows it) take k_sf_encode_long, a simple one-CTA-per-block kernel.
+#include "common.cuh"
+#include "core.h"
+#include "internal.h"
+
+namespace shafa {
+
+constexpr int ENC_THREADS = 256;
+constexpr int ENC_ITEMS = 16;
+constexpr int ENC_TILE = ENC_THREADS * ENC_ITEMS;  // 4096
+constexpr int ENC_COPIES = 32;                     // one LUT copy per lane -> no bank conflicts
+constexpr int ENC_STAGE_WORDS = ENC_TILE * ENC_SHORT_MAX / 32 + 8;
+
+// ---- exact sizes -------------------------------------------------------------------
+// one warp per block: bits = sum hist*len; flags: bit0 = has a code > ENC_SHORT_MAX,
+// bit1 = a symbol occurs but has no code
+__global__ void __launch_bounds__(256)
+k_sf_block_bits(const uint64_t *__restrict__ hist, const uint8_t *__restrict__ lens, uint32_t nb,
+                uint64_t *__restrict__ bits_out, uint32_t *__restrict__ flags_out)
+{
+    const uint32_t b = blockIdx.x * 8 + warp_id();
+    if (b >= nb) return;
+    uint64_t bits = 0;
+    uint32_t fl = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const int s = k * 32 + lane_id();
+        const uint64_t h = hist[(uint64_t)b * 256 + s];
+        const uint32_t l = lens[(uint64_t)b * 256 + s];
+        bits += h * l;
+        if (l > (uint32_t)ENC_SHORT_MAX) fl |= 1u;
+        if (h != 0 && l == 0) fl |= 2u;
+    }
+    bits = warp_sum64(bits);
+    fl = __reduce_or_sync(FULL, fl);
+    if (lane_id() == 0) {
+        bits_out[b] = bits;
+        flags_out[b] = fl;
+    }
+}
+
+// single CTA: z[b] = ceil(bits/8), payload_off[b] = exclusive scan of roundup16(z)
+// summary[0] = total payload bytes, summary[1] = OR of flags
+__global__ void __launch_bounds__(1024)
+k_sf_offsets(const uint64_t *__restrict__ bits, const uint32_t *__restrict__ flags, uint32_t nb,
+             uint64_t *__restrict__ z_out, uint64_t *__restrict__ off_out, uint64_t *__restrict__ summary)
+{
+    __shared__ uint64_t warp_tot[32];
+    __shared__ uint64_t s_carry;
+    __shared__ uint32_t s_flags;
+    if (threadIdx.x == 0) {
+        s_carry = 0;
+        s_flags = 0;
+    }
+    __syncthreads();
+    uint32_t fl = 0;
+    for (uint32_t base = 0; base < nb; base += 1024) {
+        const uint32_t b = base + threadIdx.x;
+        uint64_t z = 0, a = 0;
+        if (b < nb) {
+            z = (bits[b] + 7) >> 3;
+            a = (z + 15) & ~15ull;
+            fl |= flags[b];
+        }
+        // inclusive warp scan (64-bit)
+        uint64_t incl = a;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint64_t t = __shfl_up_sync(FULL, incl, d);
+            if (lane_id() >= (unsigned)d) incl += t;
+        }
+        if (lane_id() == 31) warp_tot[warp_id()] = incl;
+        __syncthreads();
+        uint64_t wbase = 0;
+        for (unsigned w = 0; w < warp_id(); w++) wbase += warp_tot[w];
+        const uint64_t carry = s_carry;
+        if (b < nb) {
+            z_out[b] = z;
+            off_out[b] = carry + wbase + incl - a;
+        }
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = carry + wbase + incl;
+        __syncthreads();
+    }
+    fl = __reduce_or_sync(FULL, fl);
+    if (lane_id() == 0 && fl) atomicOr(&s_flags, fl);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        summary[0] = s_carry;
+        summary[1] = s_flags;
+    }
+}
+
+// ---- fast path ------------------------------------------------------------------------
+struct EncShared {
+    uint32_t lut[256 * ENC_COPIES];   // lut[sym*32 + lane]
+    uint32_t stage[ENC_STAGE_WORDS];  // big-endian words of this tile's bit range
+    uint32_t entry[256];
+    uint32_t scan[ENC_THREADS / 32 + 1];
+    uint64_t prefix;
+    uint32_t ticket;
+    uint32_t block;
+};
+
+__global__ void __launch_bounds__(ENC_THREADS)
+k_sf_encode(const uint8_t *__restrict__ in, const uint64_t *__restrict__ off, const uint64_t *__restrict__ tile0,
+            uint32_t nb, const uint8_t *__restrict__ lens, const uint64_t *__restrict__ codes,
+            const uint64_t *__restrict__ pay_off, uint8_t *__restrict__ payload, uint64_t *__restrict__ desc,
+            uint32_t *__restrict__ counter, uint32_t *__restrict__ err)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    EncShared &sh = *reinterpret_cast<EncShared *>(smem_raw);
+    const unsigned tid = threadIdx.x, lane = lane_id(), warp = warp_id();
+    const uint64_t total_tiles = tile0[nb];
+    uint32_t cur_block = 0xffffffffu;
+    bool cur_long = false;
+    uint32_t bad = 0;
+
+    for (;;) {
+        __syncthreads();  // everyone is done with the previous tile's shared state
+        if (tid == 0) {
+            const uint32_t t = atomicAdd(counter, 1u);
+            sh.ticket = t;
+            if (t < total_tiles) sh.block = find_block(tile0, nb, t);
+        }
+        __syncthreads();
+        const uint64_t t = sh.ticket;
+        if (t >= total_tiles) break;
+        const uint32_t b = sh.block;
+        if (b != cur_block) {
+            cur_block = b;
+            const uint32_t l = lens[(uint64_t)b * 256 + tid];
+            const uint64_t c = codes[(uint64_t)b * 256 + tid];
+            cur_long = __syncthreads_or(l > (uint32_t)ENC_SHORT_MAX) != 0;
+            if (!cur_long) {
+                sh.entry[tid] = enc_entry(c, l);
+                __syncthreads();
+#pragma unroll 4
+                for (int i = 0; i < ENC_COPIES; i++) {
+                    const int idx = i * ENC_THREADS + tid;  // consecutive lanes -> consecutive banks
+                    sh.lut[idx] = sh.entry[idx / ENC_COPIES];
+                }
+                __syncthreads();
+            }
+        }
+        if (cur_long) continue;  // k_sf_encode_long owns this block
+
+        const uint64_t lo = off[b], hi = off[b + 1];
+        const uint64_t first_tile = tile0[b];
+        const bool is_first = (t == first_tile);
+        const bool is_last = (t + 1 == tile0[b + 1]);
+        const uint64_t base = (lo / ENC_TILE + (t - first_tile)) * ENC_TILE;
+        const uint64_t pos = base + (uint64_t)tid * ENC_ITEMS;
+
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (pos + 16 > lo && pos < hi) v = ld_stream16(in + pos);
+        uint32_t e[ENC_ITEMS];
+        uint32_t bits = 0;
+#pragma unroll
+        for (int j = 0; j < ENC_ITEMS; j++) {
+            const uint64_t p = pos + j;
+            const bool valid = (p >= lo) && (p < hi);
+            const uint32_t ee = valid ? sh.lut[byte_of(v, j) * ENC_COPIES + lane] : 0u;
+            if (valid && (ee & 31u) == 0) bad = 1;
+            e[j] = ee;
+            bits += ee & 31u;
+        }
+        uint32_t tile_bits;
+        const uint32_t excl = block_excl_scan<ENC_THREADS>(bits, sh.scan, &tile_bits);
+        if (warp == 0) {
+            const uint64_t pfx = lookback_sum(desc, (int64_t)t, (int64_t)first_tile, tile_bits);
+            if (lane == 0) sh.prefix = pfx;
+        }
+        __syncthreads();
+        const uint64_t P = sh.prefix;               // bits of this block before this tile
+        const uint64_t E = P + tile_bits;
+        const uint64_t W0 = P >> 5;
+        const uint32_t nwords = (uint32_t)(((E + 31) >> 5) - W0);
+        for (uint32_t k = tid; k < nwords; k += ENC_THREADS) sh.stage[k] = 0;
+        __syncthreads();
+
+        // ---- pack this thread's codes ----
+        {
+            const uint64_t p = P + excl;
+            uint32_t wrel = (uint32_t)((p >> 5) - W0);
+            uint32_t filled = (uint32_t)(p & 31u);
+            bool shared_first = filled != 0;  // first word also holds bits of the previous thread
+            uint64_t acc = 0;
+#pragma unroll
+            for (int j = 0; j < ENC_ITEMS; j++) {
+                const uint32_t l = e[j] & 31u;
+                if (l) {
+                    acc |= (uint64_t)(e[j] >> 5) << (64 - filled - l);
+                    filled += l;
+                    if (filled >= 32) {
+                        const uint32_t w = (uint32_t)(acc >> 32);
+                        if (shared_first)
+                            atomicOr(&sh.stage[wrel], w);
+                        else
+                            sh.stage[wrel] = w;
+                        shared_first = false;
+                        wrel++;
+                        acc <<= 32;
+                        filled -= 32;
+                    }
+                }
+            }
+            if (filled && (acc >> 32)) atomicOr(&sh.stage[wrel], (uint32_t)(acc >> 32));
+        }
+        // ---- leading partial word: bits of the symbols just before this tile ----
+        if (warp == 1 && !is_first && (P & 31u)) {
+            const uint32_t r = (uint32_t)(P & 31u);
+            const uint64_t tile_lo = base;  // not the first tile => base > lo
+            uint32_t ee = 0;
+            if (tile_lo >= lo + 1 + lane) ee = sh.lut[(uint32_t)in[tile_lo - 1 - lane] * ENC_COPIES + lane];
+            const uint32_t l = ee & 31u;
+            const uint32_t s_incl = warp_incl_scan(l);
+            const uint32_t s_prev = s_incl - l;  // bits of nearer symbols
+            uint32_t w = 0;
+            if (l && s_prev < r) {
+                const uint32_t room = r - s_prev;  // 1..31 bits of the word still free towards the MSB side
+                const uint32_t part = (ee >> 5) & ((1u << room) - 1u);
+                w = part << (32 - r + s_prev);
+            }
+            w = __reduce_or_sync(FULL, w);
+            if (lane == 0 && w) atomicOr(&sh.stage[0], w);
+        }
+        __syncthreads();
+        // ---- store the words this tile owns: those whose last bit lies in [P, E) ----
+        {
+            const uint64_t wend = is_last ? ((E + 31) >> 5) : (E >> 5);
+            uint32_t *out32 = reinterpret_cast<uint32_t *>(payload + pay_off[b]);
+            for (uint64_t w = W0 + tid; w < wend; w += ENC_THREADS) st_stream4(out32 + w, bswap32(sh.stage[w - W0]));
+        }
+    }
+    if (bad) atomicOr(err, 4u);
+}
+
+// ---- generic path: any code length up to 64 bits, one CTA per block ---------------------
+__global__ void __launch_bounds__(256)
+k_sf_encode_long(const uint8_t *__restrict__ in, const uint64_t *__restrict__ off, uint32_t nb,
+                 const uint8_t *__restrict__ lens, const uint64_t *__restrict__ codes,
+                 const uint64_t *__restrict__ pay_off, const uint64_t *__restrict__ z, uint8_t *__restrict__ payload,
+                 uint32_t *__restrict__ err)
+{
+    __shared__ uint64_t s_code[256];
+    __shared__ uint32_t s_len[256];
+    __shared__ uint32_t scan[9];
+    __shared__ unsigned long long s_carry;
+    const unsigned tid = threadIdx.x;
+    const uint32_t b = blockIdx.x;
+    const uint32_t l = lens[(uint64_t)b * 256 + tid];
+    s_len[tid] = l;
+    s_code[tid] = codes[(uint64_t)b * 256 + tid];
+    if (tid == 0) s_carry = 0;
+    if (!__syncthreads_or(l > (uint32_t)ENC_SHORT_MAX)) return;  // fast path handled it
+    const uint64_t lo = off[b], hi = off[b + 1];
+    uint32_t *out32 = reinterpret_cast<uint32_t *>(payload + pay_off[b]);
+    const uint64_t nwords = (z[b] + 3) >> 2;
+    for (uint64_t w = tid; w < nwords; w += 256) out32[w] = 0;
+    __syncthreads();
+    uint32_t bad = 0;
+    for (uint64_t base = lo; base < hi; base += 256 * 8) {
+        const uint64_t p0 = base + (uint64_t)tid * 8;
+        uint32_t bits = 0;
+        uint8_t sy[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            sy[j] = (p0 + j < hi) ? in[p0 + j] : 0;
+            if (p0 + j < hi) {
+                bits += s_len[sy[j]];
+                if (s_len[sy[j]] == 0) bad = 1;
+            }
+        }
+        uint32_t total;
+        const uint32_t excl = block_excl_scan<256>(bits, scan, &total);
+        uint64_t q = s_carry + excl;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            if (p0 + j < hi) {
+                uint32_t len = s_len[sy[j]];
+                const uint64_t code = s_code[sy[j]];
+                while (len) {
+                    const uint32_t room = 32 - (uint32_t)(q & 31u);
+                    const uint32_t take = len < room ? len : room;
+                    const uint32_t piece = (uint32_t)((code >> (len - take)) & ((take == 32) ? 0xffffffffu : ((1u << take) - 1u)));
+                    // big-endian word, stored byte-swapped
+                    atomicOr(out32 + (q >> 5), bswap32(piece << (room - take)));
+                    q += take;
+                    len -= take;
+                }
+            }
+        }
+        __syncthreads();
+        if (tid == 0) s_carry += total;
+        __syncthreads();
+    }
+    if (bad) atomicOr(err, 4u);
+}
+
+int launch_sf_sizes(shafa_cuda_ctx *ctx, const uint64_t *d_hist, const uint8_t *d_len, uint64_t nb, uint64_t *d_bits,
+                    uint32_t *d_flags, uint64_t *d_z, uint64_t *d_payload_off, uint64_t *d_summary)
+{
+    SHAFA_LAUNCH(ctx, "sf_block_bits", k_sf_block_bits, dim3((unsigned)((nb + 7) / 8)), dim3(256), 0, d_hist, d_len,
+                 (uint32_t)nb, d_bits, d_flags);
+    SHAFA_LAUNCH(ctx, "sf_offsets", k_sf_offsets, dim3(1), dim3(1024), 0, d_bits, d_flags, (uint32_t)nb, d_z,
+                 d_payload_off, d_summary);
+    SHAFA_CHECK_LAUNCH(ctx);
+    return SHAFA_SUCCESS;
+}
+
+int launch_sf_encode(shafa_cuda_ctx *ctx, const uint8_t *d_sym, const uint64_t *h_off, uint64_t nb,
+                     const uint8_t *d_len, const uint64_t *d_code, const uint64_t *d_payload_off, const uint64_t *d_z,
+                     uint8_t *d_payload, bool any_long, uint32_t *d_err)
+{
+    static int max_ctas_per_sm = 0;
+    const size_t smem = sizeof(EncShared);
+    if (!max_ctas_per_sm) {
+        SHAFA_CUDA_TRY(ctx, cudaFuncSetAttribute(k_sf_encode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SHAFA_CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_ctas_per_sm, k_sf_encode, ENC_THREADS, smem));
+        if (max_ctas_per_sm < 1) max_ctas_per_sm = 1;
+    }
+    // plan: [off (nb+1)] [tile0 (nb+1)]
+    uint64_t *hp = (uint64_t *)pinned_get(ctx, (nb + 1) * 2 * sizeof(uint64_t));
+    uint64_t *dp = (uint64_t *)scratch_get(ctx, SCR_PLAN, (nb + 1) * 2 * sizeof(uint64_t));
+    if (!hp || !dp) return SHAFA_LACK_OF_MEMORY;
+    uint64_t tiles = 0;
+    for (uint64_t b = 0; b < nb; b++) {
+        hp[b] = h_off[b];
+        hp[nb + 1 + b] = tiles;
+        const uint64_t lo = h_off[b], hi = h_off[b + 1];
+        if (hi < lo) return set_error(ctx, SHAFA_FILE_STREAM_FAILED, "sf_encode: offsets not monotone");
+        if (hi > lo) tiles += (hi - 1) / ENC_TILE - lo / ENC_TILE + 1;
+    }
+    hp[nb] = h_off[nb];
+    hp[2 * nb + 1] = tiles;
+    if (tiles > 0xfffffff0ull) return set_error(ctx, SHAFA_LACK_OF_MEMORY, "sf_encode: too many tiles");
+    SHAFA_CUDA_TRY(ctx, cudaMemcpyAsync(dp, hp, (nb + 1) * 2 * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+    uint64_t *desc = (uint64_t *)scratch_get(ctx, SCR_DESC, (tiles + 1) * sizeof(uint64_t));
+    uint32_t *counter = misc_ptr(ctx, MISC_COUNTER);
+    if (!desc || !counter) return SHAFA_LACK_OF_MEMORY;
+    SHAFA_CUDA_TRY(ctx, cudaMemsetAsync(desc, 0, (tiles + 1) * sizeof(uint64_t), ctx->stream));
+    SHAFA_CUDA_TRY(ctx, cudaMemsetAsync(counter, 0, 4, ctx->stream));
+    if (tiles) {
+        uint64_t grid = (uint64_t)ctx->sm_count * max_ctas_per_sm;
+        if (grid > tiles) grid = tiles;
+        SHAFA_LAUNCH(ctx, "sf_encode", k_sf_encode, dim3((unsigned)grid), dim3(ENC_THREADS), smem, d_sym, dp, dp + nb + 1,
+                     (uint32_t)nb, d_len, d_code, d_payload_off, d_payload, desc, counter, d_err);
+        if (any_long)
+            SHAFA_LAUNCH(ctx, "sf_encode_long", k_sf_encode_long, dim3((unsigned)nb), dim3(256), 0, d_sym, dp,
+                         (uint32_t)nb, d_len, d_code, d_payload_off, d_z, d_payload, d_err);
+    }
+    SHAFA_CHECK_LAUNCH(ctx);
+    return SHAFA_SUCCESS;
+}
+
+}  // namespace shafa

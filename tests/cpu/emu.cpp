@@ -1,0 +1,681 @@
+// emu.cpp -- sequential emulation of the CUDA kernels' tile decomposition on the
+// CPU, calling the SAME per-thread functions (shafa-cd_b200/csrc/core.h) the
+// kernels call, checked against the oracle (oracle/liboracle.so).  It cannot
+// prove the kernels right (warp scans, look-back and shared-memory staging only
+// exist on the GPU) but it pins every rule and every boundary case of the
+// decomposition -- halos, carries across tiles, ragged windows, word ownership,
+// sub-sequence synchronisation -- before GPU minutes are spent.
+//
+// Build: g++ -O2 -std=c++17 emu.cpp -I<repo> -L<repo>/oracle -loracle
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <random>
+#include <string>
+#include <vector>
+
+#include "oracle/shafa_oracle.h"
+#include "shafa-cd_b200/csrc/core.h"
+
+using namespace shafa;
+typedef std::vector<uint8_t> Bytes;
+
+static int g_fail = 0;
+#define CHECK(cond, ...)                       \
+    do {                                       \
+        if (!(cond)) {                         \
+            printf("FAIL %s:%d: ", __FILE__, __LINE__); \
+            printf(__VA_ARGS__);               \
+            printf("\n");                      \
+            g_fail++;                          \
+            if (g_fail > 20) exit(1);          \
+        }                                      \
+    } while (0)
+
+// ------------------------------------------------------------------ generators
+static Bytes gen(std::mt19937 &rng, size_t n, int kind)
+{
+    Bytes d(n);
+    switch (kind) {
+    case 0:  // uniform
+        for (auto &b : d) b = rng() & 255;
+        break;
+    case 1: {  // skewed text-like with zeros
+        for (auto &b : d) {
+            int r = rng() % 100;
+            b = r < 40 ? 'e' : r < 60 ? ' ' : r < 70 ? 0 : (uint8_t)('a' + rng() % 20);
+        }
+        break;
+    }
+    case 2: {  // runs, lengths up to 1200, with zeros
+        size_t i = 0;
+        while (i < n) {
+            size_t L = 1 + (rng() % 8 == 0 ? rng() % 1200 : rng() % 6);
+            uint8_t s = rng() % 5 == 0 ? 0 : (uint8_t)(rng() % 7);
+            for (size_t k = 0; k < L && i < n; k++) d[i++] = s;
+        }
+        break;
+    }
+    case 3:  // one giant run with a few interruptions
+        std::fill(d.begin(), d.end(), (uint8_t)(rng() % 3 == 0 ? 0 : 9));
+        for (int k = 0; k < 5 && n; k++) d[rng() % n] = 1;
+        break;
+    default:  // two symbols
+        for (auto &b : d) b = (rng() & 1) ? 0 : 7;
+    }
+    return d;
+}
+
+// ------------------------------------------------------------------ RLE encode emulation (rle_encode.cu)
+static Bytes emu_rle_encode_block(const uint8_t *blk, uint64_t len)
+{
+    Bytes out;
+    const uint64_t ntiles = (len + RLE_TILE - 1) / RLE_TILE;
+    std::vector<uint64_t> run_open(ntiles);  // chain #1: open run length at each tile's end
+    for (uint64_t ti = 0; ti < ntiles; ti++) {
+        const uint64_t tile_lo = ti * RLE_TILE;
+        const uint32_t tile_len = (uint32_t)std::min<uint64_t>(RLE_TILE, len - tile_lo);
+        const uint32_t valid_len = (uint32_t)std::min<uint64_t>(RLE_TILE + RLE_HALO, len - tile_lo);
+        uint32_t heads[RLE_HEAD_WORDS + 2] = {0};
+        for (uint32_t p = 0; p < RLE_TILE + RLE_HALO; p++) {
+            bool head = (p >= valid_len) || (p == 0 && ti == 0) || (blk[tile_lo + p] != blk[tile_lo + p - 1]);
+            if (head) heads[p >> 5] |= 1u << (p & 31);
+        }
+        // last head among valid tile positions
+        int lastv = -1;
+        for (int p = (int)tile_len - 1; p >= 0; p--)
+            if ((heads[p >> 5] >> (p & 31)) & 1) {
+                lastv = p;
+                break;
+            }
+        const bool head0 = heads[0] & 1u;
+        uint64_t run_in = 0;
+        if (lastv >= 0) {
+            run_open[ti] = tile_len - lastv;
+            if (!head0) run_in = run_open[ti - 1];
+        } else {
+            run_in = run_open[ti - 1];
+            run_open[ti] = run_in + tile_len;
+        }
+        // threads
+        Bytes stage(2 * RLE_TILE + 64);
+        uint32_t o = 0;
+        int lh = -1;  // last head before the thread's first position
+        for (uint32_t tid = 0; tid < RLE_TILE / RLE_ITEMS; tid++) {
+            const uint32_t p0 = tid * 16;
+            const int nvalid = p0 >= tile_len ? 0 : (int)std::min<uint32_t>(16, tile_len - p0);
+            uint32_t c0 = 0;
+            if (nvalid) {
+                const uint64_t k = lh >= 0 ? (uint64_t)(p0 - lh) : (uint64_t)p0 + run_in;
+                c0 = (uint32_t)(k % 255);
+            }
+            auto symf = [&](int j) -> uint32_t { return blk[tile_lo + p0 + j]; };
+            RleEmit em = rle_emit_thread(heads, p0, nvalid, c0, symf);
+            uint32_t w = rle_write_thread(em, stage.data() + o, symf);
+            CHECK(w == em.bytes, "rle write/emit mismatch");
+            o += w;
+            // advance lh over this thread's 16 positions (heads beyond tile_len pollute lh only for invalid threads)
+            for (uint32_t p = p0; p < p0 + 16; p++)
+                if ((heads[p >> 5] >> (p & 31)) & 1) lh = (int)p;
+        }
+        out.insert(out.end(), stage.begin(), stage.begin() + o);
+    }
+    return out;
+}
+
+static void test_rle_encode(std::mt19937 &rng)
+{
+    const size_t sizes[] = {1, 2, 15, 16, 17, 254, 255, 256, 4095, 4096, 4097, 4096 + 255, 8192, 8192 + 3, 12289, 40000, 70000};
+    for (int kind = 0; kind < 5; kind++)
+        for (size_t n : sizes) {
+            Bytes d = gen(rng, n + 1, kind);
+            d.insert(d.begin(), 0x55);  // guard byte before the block (blk[-1] is read for ti>0 only)
+            const uint8_t *blk = d.data() + 1;
+            Bytes want(2 * n + 3);
+            want.resize(orc_rle_encode_block(blk, n, want.data()));
+            Bytes got = emu_rle_encode_block(blk, n);
+            CHECK(got == want, "rle_encode kind %d n %zu: got %zu want %zu bytes", kind, n, got.size(), want.size());
+        }
+}
+
+// ------------------------------------------------------------------ RLE decode emulation (rle_decode.cu)
+// stream = concatenated ragged blocks; windows are 4096-aligned in stream space
+static Bytes emu_rle_decode(const Bytes &stream, const std::vector<uint64_t> &off, std::vector<uint64_t> &fin, bool &trunc)
+{
+    Bytes out;
+    trunc = false;
+    const int T = 4096;
+    for (size_t b = 0; b + 1 < off.size(); b++) {
+        const uint64_t lo = off[b], hi = off[b + 1];
+        const uint64_t out_before = out.size();
+        if (hi == lo) {
+            fin.push_back(0);
+            continue;
+        }
+        uint32_t tile_entry = 0;
+        for (uint64_t w = lo / T; w <= (hi - 1) / T; w++) {
+            const uint64_t base = w * T;
+            uint32_t maps[256], st = tile_entry;
+            int J0[256], N[256];
+            for (int tid = 0; tid < 256; tid++) {
+                const uint64_t pos = base + tid * 16;
+                int j0 = 0, j1 = 0;
+                if (pos + 16 > lo && pos < hi) {
+                    j0 = lo > pos ? (int)(lo - pos) : 0;
+                    j1 = hi < pos + 16 ? (int)(hi - pos) : 16;
+                }
+                uint32_t z = 0;
+                for (int j = j0; j < j1; j++)
+                    if (stream[pos + j] == 0) z |= 1u << (j - j0);
+                J0[tid] = j0;
+                N[tid] = j1 - j0;
+                maps[tid] = fsm_thread_map(z, j1 - j0);
+            }
+            uint32_t excl = FSM_IDENTITY;
+            for (int tid = 0; tid < 256; tid++) {
+                const uint64_t pos = base + tid * 16;
+                const uint32_t my_entry = fsm_apply(excl, tile_entry);
+                CHECK(my_entry == st, "fsm map scan disagrees with sequential state (tid %d)", tid);
+                uint32_t prevb = 0;
+                if (N[tid] > 0 && my_entry == 2 && pos + J0[tid] > lo) prevb = stream[pos + J0[tid] - 1];
+                auto bytef = [&](int q) -> uint32_t { return stream[pos + J0[tid] + q]; };
+                st = rle_parse_thread(my_entry, N[tid], prevb, bytef, [&](uint32_t len, uint32_t sym) { out.insert(out.end(), len, (uint8_t)sym); });
+                excl = fsm_compose(excl, maps[tid]);
+            }
+            CHECK(fsm_apply(excl, tile_entry) == st, "tile map exit mismatch");
+            tile_entry = st;
+        }
+        if (tile_entry != 0) trunc = true;
+        fin.push_back(out.size() - out_before);
+    }
+    return out;
+}
+
+static void test_rle_decode(std::mt19937 &rng)
+{
+    for (int rep = 0; rep < 40; rep++) {
+        // several ragged blocks of valid RLE (made by the oracle encoder) at arbitrary offsets
+        Bytes stream, want;
+        std::vector<uint64_t> off{0};
+        const int nblk = 1 + rng() % 4;
+        if (rep % 3 == 0) stream.resize(rng() % 5000, 0xEE), off[0] = stream.size();  // unaligned start
+        for (int b = 0; b < nblk; b++) {
+            Bytes raw = gen(rng, 1 + rng() % 30000, rng() % 5);
+            Bytes r(2 * raw.size() + 3);
+            r.resize(orc_rle_encode_block(raw.data(), raw.size(), r.data()));
+            stream.insert(stream.end(), r.begin(), r.end());
+            want.insert(want.end(), raw.begin(), raw.end());
+            off.push_back(stream.size());
+        }
+        stream.resize(stream.size() + 64, 0xEE);
+        std::vector<uint64_t> fin;
+        bool trunc;
+        Bytes got = emu_rle_decode(stream, off, fin, trunc);
+        CHECK(!trunc, "rle_decode reported truncation on valid data");
+        CHECK(got == want, "rle_decode rep %d: got %zu want %zu", rep, got.size(), want.size());
+    }
+    // arbitrary (not encoder-made) streams incl. count 0 and zero syms: compare with the oracle decoder
+    for (int rep = 0; rep < 60; rep++) {
+        Bytes s(1 + rng() % 9000);
+        for (auto &b : s) b = (rng() % 3 == 0) ? 0 : (uint8_t)(rng() % 4);
+        uint64_t fin_o = 0;
+        int rc = orc_rle_decode_block(s.data(), s.size(), nullptr, 0, &fin_o);
+        Bytes want(fin_o);
+        if (rc == 0) rc = orc_rle_decode_block(s.data(), s.size(), want.data(), want.size(), &fin_o);
+        Bytes st = s;
+        st.resize(st.size() + 64);
+        std::vector<uint64_t> fin;
+        bool trunc;
+        Bytes got = emu_rle_decode(st, {0, s.size()}, fin, trunc);
+        if (rc == 0) {
+            CHECK(!trunc && got == want, "rle_decode arbitrary rep %d", rep);
+        } else {
+            CHECK(trunc, "oracle rejects but emulation did not flag truncation (rep %d)", rep);
+        }
+    }
+}
+
+// ------------------------------------------------------------------ SF build emulation (sf_build.cu)
+static int emu_sf_build(const uint64_t *hist, uint8_t *len, uint64_t *code)
+{
+    uint32_t cnt[256], sorted[256], symr[256], P[257];
+    for (int s = 0; s < 256; s++) cnt[s] = (uint32_t)hist[s];
+    for (int s = 0; s < 256; s++) {
+        uint32_t rank = 0;
+        for (int t = 0; t < 256; t++) rank += (cnt[t] > cnt[s]) || (cnt[t] == cnt[s] && t < s);
+        sorted[rank] = cnt[s];
+        symr[rank] = s;
+    }
+    P[0] = 0;
+    int nz = 0;
+    for (int r = 0; r < 256; r++) {
+        P[r + 1] = P[r] + sorted[r];
+        nz += sorted[r] != 0;
+    }
+    const int nn = nz - 1;
+    int lo[256], hi[256];
+    uint64_t cd[256] = {0};
+    uint32_t ln[256] = {0};
+    for (int r = 0; r < 256; r++) lo[r] = 0, hi[r] = nn;
+    int maxlen = 0;
+    for (;;) {
+        bool any = false;
+        int d[256];
+        for (int r = 0; r <= nn; r++)
+            if (lo[r] != hi[r]) {
+                any = true;
+                d[r] = sf_split(P, lo[r], hi[r]);
+            }
+        if (!any) break;
+        for (int r = 0; r <= nn; r++)
+            if (lo[r] != hi[r]) {
+                if (r <= d[r]) {
+                    hi[r] = d[r];
+                    cd[r] <<= 1;
+                } else {
+                    lo[r] = d[r] + 1;
+                    cd[r] = (cd[r] << 1) | 1;
+                }
+                ln[r]++;
+            }
+    }
+    memset(len, 0, 256);
+    memset(code, 0, 256 * 8);
+    for (int r = 0; r <= nn; r++) {
+        len[symr[r]] = (uint8_t)ln[r];
+        code[symr[r]] = cd[r];
+        maxlen = std::max(maxlen, (int)ln[r]);
+    }
+    return maxlen;
+}
+
+static void test_sf_build(std::mt19937 &rng)
+{
+    for (int rep = 0; rep < 3000; rep++) {
+        uint64_t h[256] = {0};
+        const int kind = rep % 6;
+        const int k = 1 + rng() % 256;
+        for (int i = 0; i < k; i++) {
+            const int s = rng() % 256;
+            switch (kind) {
+            case 0: h[s] = 1 + rng() % 1000000; break;
+            case 1: h[s] = 1 + rng() % 3; break;
+            case 2: h[s] = 5; break;
+            case 3: h[s] = 1ull << (rng() % 20); break;
+            case 4: h[s] = 1 + rng() % 40; break;
+            default: h[s] = 2500 + rng() % 100;
+            }
+        }
+        if (rep == 7) {  // fibonacci chain
+            memset(h, 0, sizeof h);
+            uint64_t a = 1, b = 1;
+            for (int i = 0; i < 38; i++) {
+                h[100 + i] = a;
+                uint64_t c = a + b;
+                a = b;
+                b = c;
+            }
+        }
+        uint8_t l1[256], l2[256];
+        uint64_t c1[256], c2[256];
+        const int m1 = orc_sf_codes_packed(h, l1, c1);
+        const int m2 = emu_sf_build(h, l2, c2);
+        CHECK(m1 == m2 && !memcmp(l1, l2, 256) && !memcmp(c1, c2, sizeof c1), "sf_build rep %d (max %d vs %d)", rep, m1, m2);
+    }
+}
+
+// ------------------------------------------------------------------ SF encode emulation (sf_encode.cu fast path)
+static Bytes emu_sf_encode(const Bytes &stream, uint64_t lo, uint64_t hi, const uint8_t *len, const uint64_t *code)
+{
+    const int T = 4096;
+    uint32_t lut[256];
+    for (int s = 0; s < 256; s++) lut[s] = enc_entry(code[s], len[s]);
+    uint64_t total_bits = 0;
+    for (uint64_t p = lo; p < hi; p++) total_bits += len[stream[p]];
+    std::vector<uint32_t> outw((total_bits + 31) / 32 + 4, 0xdeadbeef);  // detect unwritten / doubly written words
+    std::vector<int> written(outw.size(), 0);
+    uint64_t P = 0;
+    const uint64_t w_first = lo / T, w_last = (hi - 1) / T;
+    for (uint64_t w = w_first; w <= w_last; w++) {
+        const uint64_t base = w * T;
+        const bool is_first = w == w_first, is_last = w == w_last;
+        uint32_t e[256][16], bits[256];
+        uint32_t tile_bits = 0;
+        for (int tid = 0; tid < 256; tid++) {
+            bits[tid] = 0;
+            for (int j = 0; j < 16; j++) {
+                const uint64_t p = base + tid * 16 + j;
+                e[tid][j] = (p >= lo && p < hi) ? lut[stream[p]] : 0;
+                bits[tid] += e[tid][j] & 31;
+            }
+            tile_bits += bits[tid];
+        }
+        const uint64_t E = P + tile_bits, W0 = P >> 5;
+        std::vector<uint32_t> stage(((E + 31) >> 5) - W0 + 1, 0);
+        std::vector<int> plain(stage.size(), 0);
+        uint64_t excl = 0;
+        for (int tid = 0; tid < 256; tid++) {
+            const uint64_t p = P + excl;
+            uint32_t wrel = (uint32_t)((p >> 5) - W0), filled = p & 31;
+            bool shared_first = filled != 0;
+            uint64_t acc = 0;
+            for (int j = 0; j < 16; j++) {
+                const uint32_t l = e[tid][j] & 31;
+                if (l) {
+                    acc |= (uint64_t)(e[tid][j] >> 5) << (64 - filled - l);
+                    filled += l;
+                    if (filled >= 32) {
+                        const uint32_t wv = (uint32_t)(acc >> 32);
+                        if (shared_first)
+                            stage[wrel] |= wv;
+                        else {
+                            CHECK(stage[wrel] == 0 && !plain[wrel], "plain store over a non-empty word");
+                            stage[wrel] = wv;
+                            plain[wrel] = 1;
+                        }
+                        shared_first = false;
+                        wrel++;
+                        acc <<= 32;
+                        filled -= 32;
+                    }
+                }
+            }
+            if (filled && (acc >> 32)) {
+                CHECK(!plain[wrel], "atomicOr onto a plainly stored word");
+                stage[wrel] |= (uint32_t)(acc >> 32);
+            }
+            excl += bits[tid];
+        }
+        if (!is_first && (P & 31)) {  // halo: lanes 0..31 look at the symbols before the tile
+            const uint32_t r = P & 31;
+            uint32_t s_prev = 0, wv = 0;
+            for (int lane = 0; lane < 32; lane++) {
+                uint32_t ee = 0;
+                if (base >= lo + 1 + lane) ee = lut[stream[base - 1 - lane]];
+                const uint32_t l = ee & 31;
+                if (l && s_prev < r) {
+                    const uint32_t room = r - s_prev;
+                    wv |= ((ee >> 5) & ((1u << room) - 1u)) << (32 - r + s_prev);
+                }
+                s_prev += l;
+            }
+            stage[0] |= wv;
+        }
+        const uint64_t wend = is_last ? ((E + 31) >> 5) : (E >> 5);
+        for (uint64_t ww = W0; ww < wend; ww++) {
+            CHECK(!written[ww], "output word %llu written twice", (unsigned long long)ww);
+            written[ww] = 1;
+            outw[ww] = stage[ww - W0];
+        }
+        P = E;
+    }
+    Bytes out((total_bits + 7) / 8);
+    for (size_t i = 0; i < out.size(); i++) {
+        CHECK(written[i / 4], "output word %zu never written", i / 4);
+        out[i] = (uint8_t)(outw[i / 4] >> (24 - 8 * (i & 3)));
+    }
+    return out;
+}
+
+static void codes_to_strings(const uint8_t *len, const uint64_t *code, char (*out)[ORC_MAX_CODE])
+{
+    memset(out, 0, 256 * ORC_MAX_CODE);
+    for (int s = 0; s < 256; s++)
+        for (int i = 0; i < len[s]; i++) out[s][i] = ((code[s] >> (len[s] - 1 - i)) & 1) ? '1' : '0';
+}
+
+// ------------------------------------------------------------------ SF decode emulation (sf_decode.cu)
+struct EmuTables {
+    std::vector<uint16_t> lut;
+    uint64_t sleft[256];
+    uint8_t slen[256], ssym[256];
+    DecTables view() const
+    {
+        DecTables t;
+        t.lut = lut.data();
+        t.sleft = sleft;
+        t.slen = slen;
+        t.ssym = ssym;
+        return t;
+    }
+};
+
+static void emu_dec_tables(const uint8_t *len, const uint64_t *code, EmuTables &T)
+{
+    uint64_t left[256];
+    for (int s = 0; s < 256; s++) left[s] = len[s] ? code[s] << (64 - len[s]) : ~0ull;
+    for (int s = 0; s < 256; s++) {
+        uint32_t rank = 0;
+        for (int t = 0; t < 256; t++) {
+            const bool before = (left[t] < left[s]) ||
+                                (left[t] == left[s] && ((len[t] != 0 && len[s] == 0) || ((len[t] != 0) == (len[s] != 0) && t < s)));
+            rank += before;
+        }
+        T.sleft[rank] = left[s];
+        T.slen[rank] = len[s];
+        T.ssym[rank] = (uint8_t)s;
+    }
+    T.lut.assign(DEC_LUT_SIZE, 0);
+    for (int e = 0; e < DEC_LUT_SIZE; e++) {
+        const uint64_t window = (uint64_t)e << (64 - DEC_LUT_BITS);
+        int lo = 0, hi = 256;
+        while (lo < hi) {
+            const int m = (lo + hi) >> 1;
+            if (T.sleft[m] <= window)
+                lo = m + 1;
+            else
+                hi = m;
+        }
+        uint16_t entry = 0;
+        if (lo > 0) {
+            const int r = lo - 1;
+            const uint32_t rl = T.slen[r];
+            if (rl != 0 && rl <= (uint32_t)DEC_LUT_BITS && (window >> (64 - rl)) == (T.sleft[r] >> (64 - rl)))
+                entry = (uint16_t)((T.ssym[r] << 8) | rl);
+            else
+                entry = DEC_LONG;
+        }
+        T.lut[e] = entry;
+    }
+}
+
+static Bytes emu_sf_decode(const Bytes &payload, uint64_t n, const uint8_t *len, const uint64_t *code, bool &bad, int *stitch_passes)
+{
+    EmuTables T;
+    emu_dec_tables(len, code, T);
+    const DecTables t = T.view();
+    const uint64_t z = payload.size();
+    const uint64_t nseq = (z + DEC_SEQ_BYTES - 1) / DEC_SEQ_BYTES;
+    std::vector<uint16_t> start(nseq * DEC_THREADS), count(nseq * DEC_THREADS);
+    std::vector<uint32_t> seq_end(nseq);
+    auto load_words = [&](uint64_t seq, std::vector<uint32_t> &words) {
+        words.assign(DEC_SEQ_WORDS + DEC_WORDS_PAD, 0);
+        for (int i = 0; i < DEC_SEQ_WORDS + DEC_WORDS_PAD; i++) {
+            uint32_t w = 0;
+            for (int k = 0; k < 4; k++) {
+                const uint64_t bo = seq * DEC_SEQ_BYTES + (uint64_t)i * 4 + k;
+                w = (w << 8) | (bo < z ? payload[bo] : 0);
+            }
+            words[i] = w;
+        }
+    };
+    // phase 1
+    for (uint64_t seq = 0; seq < nseq; seq++) {
+        std::vector<uint32_t> words;
+        load_words(seq, words);
+        const uint64_t bits_left = (z - seq * DEC_SEQ_BYTES) * 8;
+        const uint32_t limit = (uint32_t)std::min<uint64_t>(bits_left, DEC_SEQ_BYTES * 8);
+        uint32_t st[DEC_THREADS] = {0}, en[DEC_THREADS], cn[DEC_THREADS];
+        auto run = [&](int tid) {
+            const uint32_t sub_lo = tid * DEC_SUB_BITS, sub_hi = sub_lo + DEC_SUB_BITS;
+            const uint32_t stop = std::min(sub_hi, limit);
+            DecSub r = dec_subsequence(words.data(), t, sub_lo + st[tid], stop, nullptr, 0);
+            en[tid] = r.end > sub_hi ? r.end - sub_hi : 0;
+            cn[tid] = r.count;
+        };
+        for (int tid = 0; tid < DEC_THREADS; tid++) run(tid);
+        for (int iter = 0;; iter++) {
+            uint32_t want[DEC_THREADS];
+            bool any = false;
+            for (int tid = 0; tid < DEC_THREADS; tid++) want[tid] = tid ? en[tid - 1] : 0;
+            for (int tid = 0; tid < DEC_THREADS; tid++)
+                if (want[tid] != st[tid]) {
+                    any = true;
+                    st[tid] = want[tid];
+                    run(tid);
+                }
+            if (!any) break;
+            CHECK(iter < 300, "phase 1 does not converge");
+        }
+        for (int tid = 0; tid < DEC_THREADS; tid++) {
+            CHECK(st[tid] < 128 && cn[tid] < 512, "sub record overflow");
+            start[seq * DEC_THREADS + tid] = (uint16_t)st[tid];
+            count[seq * DEC_THREADS + tid] = (uint16_t)cn[tid];
+        }
+        seq_end[seq] = en[DEC_THREADS - 1];
+    }
+    // phase 2
+    int passes = 0;
+    for (;; passes++) {
+        bool touched = false;
+        for (uint64_t seq = 1; seq < nseq; seq++) {
+            uint32_t cur = seq_end[seq - 1];
+            std::vector<uint32_t> words;
+            load_words(seq, words);
+            const uint64_t bits_left = (z - seq * DEC_SEQ_BYTES) * 8;
+            const uint32_t limit = (uint32_t)std::min<uint64_t>(bits_left, DEC_SEQ_BYTES * 8);
+            for (int k = 0; k < DEC_THREADS; k++) {
+                const uint64_t gi = seq * DEC_THREADS + k;
+                if (start[gi] == cur) break;
+                const uint32_t sub_lo = k * DEC_SUB_BITS, sub_hi = sub_lo + DEC_SUB_BITS;
+                DecSub r = dec_subsequence(words.data(), t, sub_lo + cur, std::min(sub_hi, limit), nullptr, 0);
+                start[gi] = (uint16_t)cur;
+                count[gi] = (uint16_t)r.count;
+                touched = true;
+                cur = r.end > sub_hi ? r.end - sub_hi : 0;
+                if (k == DEC_THREADS - 1) seq_end[seq] = cur;
+            }
+        }
+        if (!touched) break;
+        CHECK(passes < 1000, "phase 2 does not converge");
+    }
+    if (stitch_passes) *stitch_passes = passes;
+    // phases 3+4
+    Bytes out(n);
+    uint64_t first = 0;
+    bad = false;
+    for (uint64_t seq = 0; seq < nseq; seq++) {
+        std::vector<uint32_t> words;
+        load_words(seq, words);
+        const uint64_t bits_left = (z - seq * DEC_SEQ_BYTES) * 8;
+        const uint32_t limit = (uint32_t)std::min<uint64_t>(bits_left, DEC_SEQ_BYTES * 8);
+        for (int tid = 0; tid < DEC_THREADS; tid++) {
+            const uint64_t gi = seq * DEC_THREADS + tid;
+            if (first < n) {
+                const uint32_t sub_lo = tid * DEC_SUB_BITS, sub_hi = sub_lo + DEC_SUB_BITS;
+                DecSub r = dec_subsequence(words.data(), t, sub_lo + start[gi], std::min(sub_hi, limit), out.data() + first,
+                                           (uint32_t)std::min<uint64_t>(n - first, 0xffffffffu));
+                CHECK(r.count == count[gi], "final decode count differs from the recorded count");
+                if (r.bad) bad = true;
+            }
+            first += count[gi];
+        }
+    }
+    if (first < n) bad = true;
+    return out;
+}
+
+static void test_sf_codec(std::mt19937 &rng)
+{
+    int max_passes = 0;
+    for (int rep = 0; rep < 60; rep++) {
+        const int kind = rep % 5;
+        size_t n = 1 + rng() % 60000;
+        if (rep % 7 == 0) n = 1 + rng() % 40;
+        Bytes raw = gen(rng, n, kind);
+        if (rep % 11 == 3) {  // deep code: fibonacci-weighted symbols -> long codes (fast path needs <= 26 bits)
+            uint64_t a = 1, b = 1;
+            raw.clear();
+            for (int i = 0; i < 22; i++) {
+                raw.insert(raw.end(), (size_t)a, (uint8_t)(10 + i));
+                uint64_t c = a + b;
+                a = b;
+                b = c;
+            }
+            std::shuffle(raw.begin(), raw.end(), rng);
+            n = raw.size();
+        }
+        uint64_t hist[256];
+        orc_histogram(raw.data(), n, hist);
+        int distinct = 0;
+        for (int s = 0; s < 256; s++) distinct += hist[s] != 0;
+        if (distinct < 2) continue;
+        uint8_t len[256];
+        uint64_t code[256];
+        const int maxlen = orc_sf_codes_packed(hist, len, code);
+        CHECK(maxlen > 0 && maxlen <= ENC_SHORT_MAX, "unexpected max code length %d", maxlen);
+        static char codes[256][ORC_MAX_CODE];
+        codes_to_strings(len, code, codes);
+        Bytes want((n * maxlen + 7) / 8 + 8);
+        want.resize(orc_sf_encode_block(raw.data(), n, codes, want.data()));
+        // embed at an unaligned offset inside a larger stream
+        const uint64_t lo = rng() % 9000;
+        Bytes stream(lo, 0xAA);
+        stream.insert(stream.end(), raw.begin(), raw.end());
+        stream.resize(stream.size() + 64, 0xBB);
+        Bytes got = emu_sf_encode(stream, lo, lo + n, len, code);
+        CHECK(got == want, "sf_encode rep %d n %zu maxlen %d", rep, n, maxlen);
+        bool bad;
+        int passes;
+        Bytes dec = emu_sf_decode(want, n, len, code, bad, &passes);
+        max_passes = std::max(max_passes, passes);
+        CHECK(!bad && dec == raw, "sf_decode rep %d n %zu", rep, n);
+    }
+    printf("sf codec: max stitch passes %d\n", max_passes);
+    // long codes (> 12 bits) through the fallback search, decode only
+    {
+        uint64_t hist[256] = {0};
+        uint64_t a = 1, b = 1;
+        for (int i = 0; i < 30; i++) {
+            hist[i * 3] = a;
+            uint64_t c = a + b;
+            a = b;
+            b = c;
+        }
+        uint8_t len[256];
+        uint64_t code[256];
+        const int maxlen = orc_sf_codes_packed(hist, len, code);
+        static char codes[256][ORC_MAX_CODE];
+        codes_to_strings(len, code, codes);
+        Bytes raw;
+        for (int i = 0; i < 30; i++) raw.insert(raw.end(), std::min<uint64_t>(hist[i * 3], 3000), (uint8_t)(i * 3));
+        std::shuffle(raw.begin(), raw.end(), rng);
+        Bytes enc((raw.size() * maxlen + 7) / 8 + 8);
+        enc.resize(orc_sf_encode_block(raw.data(), raw.size(), codes, enc.data()));
+        bool bad;
+        Bytes dec = emu_sf_decode(enc, raw.size(), len, code, bad, nullptr);
+        CHECK(!bad && dec == raw, "sf_decode long codes (max %d)", maxlen);
+    }
+}
+
+int main()
+{
+    std::mt19937 rng(12345);
+    test_rle_encode(rng);
+    printf("rle_encode done (%d failures so far)\n", g_fail);
+    test_rle_decode(rng);
+    printf("rle_decode done (%d failures so far)\n", g_fail);
+    test_sf_build(rng);
+    printf("sf_build done (%d failures so far)\n", g_fail);
+    test_sf_codec(rng);
+    printf("sf_codec done (%d failures so far)\n", g_fail);
+    if (g_fail) {
+        printf("EMU FAILED: %d\n", g_fail);
+        return 1;
+    }
+    printf("EMU OK\n");
+    return 0;
+}
