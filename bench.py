@@ -1,0 +1,417 @@
+#!/usr/bin/env python
+"""bench.py -- F+C encode & D decode throughput of the Shafa block pipeline on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A "step" is one full F -> T -> C -> D round trip over one synthetic file of
+BASELINE.json configs[1]: 1 GiB low-entropy text-like bytes, m = 8 MiB blocks
+(R mode).  For N > 1 (torchrun, one rank per GPU) every rank runs the same step
+on its own 1 GiB shard of blocks -- blocks are independent, there is no
+collective on the data path (weak scaling); timing is the max over ranks.
+
+One JSON line on stdout (rank 0).  `value` is device-resident (input already in
+HBM), `e2e` goes through the host-buffer C-ABI calls with host<->device copies
+inside the timed region, `roofline` is the dominant kernel measured with CUDA
+events on the launch stream, `cpu_baseline` is the unmodified reference binary
+(oracle/_ref/shafa) timed on this box's host cores on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import shutil
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+GIB = 1 << 30
+MIB = 1 << 20
+WORKLOAD = "C2: 1 GiB text-like synthetic (seed 2024), -b m (8 MiB blocks), F->T->C->D round trip"
+METRIC = "F+C encode & D decode round-trip throughput, GB/s of input"
+CPU_SAMPLE_BYTES = 256 * MIB   # bounded sample of the same generator for the reference arm
+
+
+def measured_peak_hbm():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ----------------------------------------------------------------------------------
+# reference arm / cpu baseline: the unmodified reference binary on host cores
+# ----------------------------------------------------------------------------------
+
+def reference_round_trip(sample: np.ndarray, bflag: str, workdir: Path) -> dict:
+    """F, T, C, D with oracle/_ref/shafa on `sample`; wall seconds per module."""
+    from oracle import oracle_py as orc
+
+    x = workdir / "x"
+    x.write_bytes(sample.tobytes())
+    t = {}
+
+    def run(args, key):
+        t0 = time.perf_counter()
+        r = orc.ref_run(args, str(workdir), timeout=3600)
+        t[key] = time.perf_counter() - t0
+        if r.returncode != 0:
+            raise RuntimeError(f"reference failed {args}: {r.stderr.decode(errors='replace')[:300]}")
+
+    run(["x", "-m", "f", "-b", bflag], "F")
+    rle = (workdir / "x.rle").exists()
+    base = "x.rle" if rle else "x"
+    run([base + ".freq", "-m", "t"], "T")
+    run([base, "-m", "c"], "C")
+    x.unlink()
+    run([base + ".shaf", "-m", "d"], "D")
+    ok = x.read_bytes() == sample.tobytes()
+    for p in workdir.iterdir():
+        p.unlink()
+    return {"seconds": t, "ok": ok, "rle_mode": rle}
+
+
+def port_round_trip(sample: np.ndarray, block: int) -> dict:
+    """Fallback when the reference binary is absent: the oracle restatement (1 thread)."""
+    from oracle import oracle_py as orc
+
+    t = {}
+    t0 = time.perf_counter(); f = orc.module_f(sample, block); t["F"] = time.perf_counter() - t0
+    sym = f["rle"] if f["rle_mode"] else sample.tobytes()
+    freq = f["rle_freq"] if f["rle_mode"] else f["freq"]
+    t0 = time.perf_counter(); cod = orc.module_t(freq); t["T"] = time.perf_counter() - t0
+    t0 = time.perf_counter(); shaf = orc.module_c(sym, cod); t["C"] = time.perf_counter() - t0
+    t0 = time.perf_counter(); out = orc.module_d_shaf(shaf, cod, f["rle_mode"]); t["D"] = time.perf_counter() - t0
+    return {"seconds": t, "ok": out == sample.tobytes(), "rle_mode": f["rle_mode"]}
+
+
+def cpu_arm(pkg, steps: int, warmup: int):
+    """Returns (per-step seconds list, description dict)."""
+    from oracle import oracle_py as orc
+
+    sample = pkg.datagen.textlike(CPU_SAMPLE_BYTES, seed=2024)
+    use_ref = orc.ref_available()
+    tmp_root = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else None
+    times, last = [], None
+    with tempfile.TemporaryDirectory(dir=tmp_root) as td:
+        for i in range(warmup + steps):
+            r = reference_round_trip(sample, "m", Path(td)) if use_ref else port_round_trip(sample, pkg.datagen.BLOCK_m)
+            if not r["ok"]:
+                raise RuntimeError("CPU arm round trip mismatch")
+            if i >= warmup:
+                times.append(sum(r["seconds"].values()))
+                last = r
+    desc = {
+        "kind": "reference" if use_ref else "port",
+        "cores": os.cpu_count() if use_ref else 1,
+        "sample": f"{CPU_SAMPLE_BYTES // MIB} MiB of the same text-like generator, -b m ({CPU_SAMPLE_BYTES // pkg.datagen.BLOCK_m} blocks), "
+                  f"files on {'tmpfs' if tmp_root else 'tmp'}; F,T single-threaded, C,D one pthread per block (reference design)",
+        "module_seconds": {k: round(v, 4) for k, v in last["seconds"].items()},
+    }
+    return times, desc
+
+
+# ----------------------------------------------------------------------------------
+# clocks
+# ----------------------------------------------------------------------------------
+
+class ClockSampler:
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.path = tempfile.NamedTemporaryFile(prefix="clocks_", suffix=".csv", delete=False).name
+        self.proc = None
+        if shutil.which("nvidia-smi"):
+            try:
+                self.proc = subprocess.Popen(["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                                              "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+            except Exception:
+                self.proc = None
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in Path(self.path).read_text().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.path)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------
+
+ALGO_BYTES_DOC = {
+    "rle_encode": "N + R", "rle_encode_sizes": "n0 (block-0 probe)", "histogram": "S", "sf_encode": "S + Z",
+    "dec_sync": "Z", "dec_write": "Z + S", "rle_decode": "R + N",
+}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from __graft_entry__ import load_package
+
+    pkg = load_package()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+
+    n = args.bytes
+    bs = pkg.datagen.BLOCK_m
+    data = pkg.datagen.textlike(n, seed=2024 + rank)      # this rank's shard of blocks
+    B = (n + bs - 1) // bs
+
+    sh = pkg.Shafa(device=local_rank)
+    stream = torch.cuda.current_stream(dev)
+    sh.set_stream(stream.cuda_stream)
+
+    # ---- device-resident buffers (torch is only the allocator / stream / event provider) ----
+    def dbuf(nbytes):
+        return torch.empty(int(nbytes + 256), dtype=torch.uint8, device=dev)
+
+    h_in = torch.from_numpy(data)
+    d_in = dbuf(n); d_in[:n].copy_(h_in)
+    rle_cap = 2 * n + 3 * B + 64
+    d_rle = dbuf(rle_cap)
+    d_hist = dbuf(B * 256 * 8); d_len = dbuf(B * 256); d_code = dbuf(B * 256 * 8)
+    pay_cap = n + n // 8 + 32 * B + 4096
+    d_payload = dbuf(pay_cap)
+    d_sym2 = dbuf(rle_cap)
+    d_out = dbuf(n)
+    torch.cuda.synchronize(dev)
+    info = {}
+
+    def step(ev_mid=None):
+        p = lambda t: t.data_ptr()
+        first = min(n, bs)
+        rle0 = int(sh.rle_encode_blocks(p(d_in), first, bs)[0])              # F: block-0 probe (f.c:246-258)
+        rle_mode = sh.rle_gate(first, rle0)
+        if rle_mode:
+            sym_sizes = sh.rle_encode_blocks(p(d_in), n, bs, p(d_rle), rle_cap, p(d_hist))   # F: RLE + fused histogram
+            d_sym = d_rle
+        else:
+            sym_sizes = np.array([min(bs, n - b * bs) for b in range(B)], dtype=np.uint64)
+            d_sym = d_in
+        offs = np.concatenate([[0], np.cumsum(sym_sizes)]).astype(np.uint64)
+        if not rle_mode:
+            sh.histogram_blocks(p(d_in), offs, p(d_hist))                                      # F: histogram
+        sh.sf_build_codes(p(d_hist), B, p(d_len), p(d_code))                                   # T
+        poff, z = sh.sf_encode_blocks(p(d_sym), offs, p(d_len), p(d_code), p(d_hist), p(d_payload), pay_cap)   # C
+        if ev_mid is not None:
+            ev_mid.record(stream)
+        sh.sf_decode_blocks(p(d_payload), poff, z, sym_sizes, p(d_len), p(d_code), p(d_sym2), int(offs[-1]) + 64)  # D (SF)
+        if rle_mode:
+            fin = sh.rle_decode_blocks(p(d_sym2), offs, p(d_out), n)                            # D (RLE)
+            assert int(fin.sum()) == n
+        info.update(rle_mode=rle_mode, S=int(offs[-1]), Z=int(z.sum()), R=int(offs[-1]) if rle_mode else 0)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    # verify once, outside the timed region
+    result = (d_out if info["rle_mode"] else d_sym2)[:n].cpu().numpy()
+    if not np.array_equal(result, data):
+        raise RuntimeError("round trip mismatch on the GPU path")
+
+    sh.profile(True); sh.profile_reset()
+    clocks = ClockSampler(local_rank)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    mids = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    launches0 = sh.launch_count()
+    barrier()
+    ev0.record(stream)
+    for i in range(args.steps):
+        starts[i].record(stream)
+        step(mids[i])
+    ev1.record(stream)
+    barrier()
+    total_ms = ev0.elapsed_time(ev1)
+    launches = sh.launch_count() - launches0
+    kstats = sh.profile_read()
+    sh.profile(False)
+    clk = clocks.stop()
+    enc_ms = sum(starts[i].elapsed_time(mids[i]) for i in range(args.steps)) / args.steps
+    dec_ms = total_ms / args.steps - enc_ms
+
+    # ---- e2e: host buffers through the C-ABI, copies inside the timed region ----
+    e2e_steps = max(1, min(args.steps, 3))
+    lib = sh.lib
+    import ctypes as C
+
+    def pinned(nbytes):
+        ptr = lib.shafa_cuda_host_alloc(int(nbytes))
+        if not ptr:
+            raise MemoryError("pinned allocation failed")
+        return ptr, np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint8)), (int(nbytes),))
+
+    sh.set_stream(None)
+    S, Z = info["S"], info["Z"]
+    pin_in_p, pin_in = pinned(n); pin_in[:] = data
+    pin_rle_p, pin_rle = pinned(S + 4096)
+    pin_pay_p, pin_pay = pinned(Z + 32 * B + 4096)
+    pin_out_p, pin_out = pinned(n + 4096)
+    e2e_times, h2d, d2h = [], 0, 0
+    for i in range(1 + e2e_steps):
+        barrier()
+        t0 = time.perf_counter()
+        c = sh.encode_raw(pin_in, bs, rle_buf=pin_rle, payload_buf=pin_pay)
+        enc_view = pkg.Encoded.__new__(pkg.Encoded)   # no copies: read the struct's arrays in place
+        Bc = int(c.n_blocks)
+        z_arr = np.ctypeslib.as_array(c.z, (Bc,)); po_arr = np.ctypeslib.as_array(c.payload_offsets, (Bc,))
+        ss_arr = np.ctypeslib.as_array(c.sym_sizes, (Bc,))
+        ln_arr = np.ctypeslib.as_array(c.code_len, (Bc * 256,)); cd_arr = np.ctypeslib.as_array(c.code_bits, (Bc * 256,))
+        out, _ = sh.decode_tables(pin_pay[: int(c.payload_total)], po_arr, z_arr, ss_arr, ln_arr, cd_arr, bool(c.rle_mode), n, out=pin_out)
+        t1 = time.perf_counter()
+        if i == 0:
+            if not np.array_equal(out[:n], data):
+                raise RuntimeError("e2e round trip mismatch")
+        else:
+            e2e_times.append(t1 - t0)
+        h2d = n + int(c.payload_total) + Bc * 256 * 9
+        d2h = int(c.rle_total) + int(c.payload_total) + Bc * 256 * (8 + 9) + n
+        sh.encoded_free(c)
+        del enc_view
+    e2e_s = sum(e2e_times) / len(e2e_times)
+
+    # ---- reduce over ranks (max time) ----
+    t = torch.tensor([total_ms, e2e_s * 1e3, enc_ms, dec_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, e2e_ms, enc_ms, dec_ms = [float(x) for x in t.tolist()]
+
+    for ptr in (pin_in_p, pin_rle_p, pin_pay_p, pin_out_p):
+        lib.shafa_cuda_host_free(ptr)
+
+    if rank == 0:
+        peak, peak_src = measured_peak_hbm()
+        R = info["R"]
+        algo = {"rle_encode": n + R, "rle_encode_sizes": min(n, bs), "histogram": S, "sf_encode": S + Z, "dec_sync": Z,
+                "dec_write": Z + S, "rle_decode": R + n}
+        kernels = {}
+        for name, st in kstats.items():
+            per_step_ms = st["ms"] / args.steps
+            ent = {"launches_per_step": st["launches"] / args.steps, "ms_per_step": round(per_step_ms, 4)}
+            if name in algo and st["launches"]:
+                avg_ms = st["ms"] / st["launches"]
+                per_launch_bytes = algo[name]   # one launch per step for these kernels
+                ent["algorithmic_bytes"] = ALGO_BYTES_DOC[name]
+                ent["gbs"] = round(per_launch_bytes / (avg_ms * 1e-3) / 1e9, 1) if avg_ms > 0 else None
+                ent["frac_of_hbm"] = round(ent["gbs"] / peak, 4) if ent["gbs"] else None
+            kernels[name] = ent
+        dom = max((k for k in kernels if k in algo), key=lambda k: kernels[k]["ms_per_step"])
+        ms_per_step = total_ms / args.steps
+        value = world * n / (ms_per_step * 1e-3) / 1e9
+        # pipeline-level roofline: algorithmic bytes of the staged pipeline: F (N+R) + C (S+Z) + D (Z+S [+ R+N])
+        pipe_bytes = (n + R) + (S + Z) + (Z + S) + ((R + n) if info["rle_mode"] else 0)
+        line = {
+            "metric": METRIC, "value": round(value, 3), "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "bytes_per_gpu": n, "block_size": bs, "blocks_per_gpu": B, "mode": "R" if info["rle_mode"] else "N",
+                       "S_rle_bytes": S, "Z_payload_bytes": Z, "l2": "inputs (1 GiB per pass) larger than the 126 MB L2",
+                       "sharding": f"{world} x independent block shards, no collective"},
+            "encode_gbs": round(world * n / (enc_ms * 1e-3) / 1e9, 3), "decode_gbs": round(world * n / (dec_ms * 1e-3) / 1e9, 3),
+            "decode_gbs_compressed_in": round(world * Z / (dec_ms * 1e-3) / 1e9, 3),
+            "pipeline_hbm": {"algorithmic_bytes": pipe_bytes, "formula": "(N+R) + (S+Z) + (Z+S) + (R+N)",
+                             "achieved_gbs": round(pipe_bytes / (ms_per_step * 1e-3) / 1e9, 1),
+                             "frac": round(pipe_bytes / (ms_per_step * 1e-3) / 1e9 / peak, 4)},
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["gbs"], "peak": peak, "unit": "GB/s",
+                         "frac": kernels[dom]["frac_of_hbm"], "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes": ALGO_BYTES_DOC[dom]},
+            "kernels": kernels,
+            "e2e": {"value": round(world * n / (e2e_ms * 1e-3) / 1e9, 3), "unit": "GB/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": e2e_steps, "api": "shafa_cuda_encode_host + shafa_cuda_decode_host on pinned host buffers"},
+            "gpu_launches": int(launches), "clocks": clk,
+        }
+        if world == 1 and not args.no_cpu:
+            times, desc = cpu_arm(pkg, 1, 0)
+            desc["value"] = round(CPU_SAMPLE_BYTES / times[0] / 1e9, 4)
+            desc["unit"] = "GB/s"
+            line["cpu_baseline"] = desc
+        print(json.dumps(line), flush=True)
+    sh.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from __graft_entry__ import load_package
+
+    pkg = load_package()
+    times, desc = cpu_arm(pkg, args.steps, min(args.warmup, 1))
+    sec = sum(times) / len(times)
+    v = round(CPU_SAMPLE_BYTES / sec / 1e9, 4)
+    desc.update(value=v, unit="GB/s")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "GB/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": min(args.warmup, 1), "ms_per_step": round(sec * 1e3, 2), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample_bytes": CPU_SAMPLE_BYTES, "block_size": pkg.datagen.BLOCK_m},
+        "cpu_baseline": desc,
+        "e2e": {"value": v, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--bytes", type=int, default=GIB, help="bytes per GPU (default: the 1 GiB of configs[1])")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        if args.warmup < 3:
+            args.warmup = 3
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()
