@@ -1,0 +1,294 @@
+/*
+ * mod_d.c -- module D: Shannon-Fano decoding and/or RLE expansion.
+ * Interfaces and files: reference d.c:628-834 (shafa_decompress) and d.c:232-388
+ * (rle_decompress).  The reference runs process_shafa_decomp /
+ * rle_block_decompressor in one pthread per block and serialises the writes
+ * (multithread_create, d.c:342,735); here all blocks go through one batched CUDA
+ * call each and the ordered write is a single fwrite of the concatenated output.
+ */
+#include <stdlib.h>
+#include <string.h>
+
+#include "util.h"
+
+/* d.c:129-136: the reference's first guess for an expanded block, by size class */
+static uint64_t rle_guess(uint64_t rle_block)
+{
+    if (rle_block <= KIB_64) return KIB_64 + KIB_1;
+    if (rle_block <= KIB_640) return KIB_640 + KIB_1;
+    if (rle_block <= MIB_8) return MIB_8 + KIB_1;
+    return MIB_64 + KIB_1;
+}
+
+static _modules_error write_all(const char *path, const uint8_t *data, uint64_t n)
+{
+    FILE *f = fopen(path, "wb");
+    if (!f) return _FILE_INACCESSIBLE;
+    const bool ok = fwrite(data, 1, n, f) == n;
+    return (fclose(f) != 0 || !ok) ? _FILE_STREAM_FAILED : _SUCCESS;
+}
+
+static void summary(const char *what, double ms, const uint64_t *before, const uint64_t *after, uint64_t nb, const char *out_path)
+{
+    printf("Module: D (%s decoding) [libshafa_cuda]\n", what);
+    for (uint64_t b = 0; b < nb; b++)
+        printf("Size before/after generating file (block %llu): %llu/%llu\n", (unsigned long long)(b + 1), (unsigned long long)before[b],
+               (unsigned long long)after[b]);
+    printf("Module runtime (in milliseconds): %f\nGenerated file %s\n", ms, out_path);
+}
+
+/* expand nb RLE blocks that already sit on the device; returns pinned host output */
+static _modules_error expand_on_device(shafa_cuda_ctx *g, const void *d_rle, const uint64_t *offsets, uint64_t nb, uint64_t *fin,
+                                       uint8_t **h_out, uint64_t *out_size)
+{
+    uint64_t cap = 0;
+    for (uint64_t b = 0; b < nb; b++) cap += rle_guess(offsets[b + 1] - offsets[b]);
+    _modules_error err = _SUCCESS;
+    void *d_out = NULL;
+    for (int attempt = 0; attempt < 2; attempt++) {
+        d_out = shafa_cuda_dev_alloc(g, cap + 64);
+        if (!d_out) return _LACK_OF_MEMORY;
+        err = gpu_status(shafa_cuda_rle_decode_blocks(g, d_rle, offsets, nb, d_out, cap, fin));
+        if (err != _LACK_OF_MEMORY || attempt) break;
+        /* the guess was too small (d.c:154-170 grows stepwise); sizes are exact now */
+        shafa_cuda_dev_free(g, d_out);
+        d_out = NULL;
+        cap = 0;
+        for (uint64_t b = 0; b < nb; b++) cap += fin[b];
+    }
+    if (!err) {
+        uint64_t tot = 0;
+        for (uint64_t b = 0; b < nb; b++) tot += fin[b];
+        *h_out = shafa_cuda_host_alloc(tot + 16);
+        if (!*h_out)
+            err = _LACK_OF_MEMORY;
+        else if (!(err = gpu_status(shafa_cuda_memcpy_d2h(g, *h_out, d_out, tot))))
+            err = gpu_status(shafa_cuda_synchronize(g));
+        *out_size = tot;
+    }
+    if (d_out) shafa_cuda_dev_free(g, d_out);
+    return err;
+}
+
+_modules_error rle_decompress(char **const path)
+{
+    const double t0 = now_ms();
+    char *p_freq = add_ext(*path, FREQ_EXT), *p_out = rm_ext(*path);
+    if (!p_freq || !p_out) {
+        free(p_freq);
+        free(p_out);
+        return _LACK_OF_MEMORY;
+    }
+    blob rle = {0}, freq = {0};
+    uint64_t nb = 0, *offsets = NULL, *sizes = NULL, *fin = NULL, out_size = 0;
+    uint8_t *h_out = NULL;
+    void *d_rle = NULL;
+    shafa_cuda_ctx *g = NULL;
+    _modules_error err = blob_read(*path, &rle);
+    if (!err) err = blob_read(p_freq, &freq);
+    free(p_freq);
+    if (err) goto out;
+    cursor c = {freq.data, freq.data + freq.size};
+    if (!cur_lit(&c, '@') || c.p >= c.end) {
+        err = _FILE_STREAM_FAILED;
+        goto out;
+    }
+    const char mode = (char)*c.p++;
+    if (!cur_lit(&c, '@') || !cur_u64(&c, &nb)) { /* d.c:268 */
+        err = _FILE_STREAM_FAILED;
+        goto out;
+    }
+    if (mode != 'R') { /* d.c:270 */
+        err = _FILE_UNRECOGNIZABLE;
+        goto out;
+    }
+    offsets = malloc((nb + 1) * sizeof *offsets);
+    sizes = malloc((nb + 1) * sizeof *sizes);
+    fin = malloc((nb + 1) * sizeof *fin);
+    if (!offsets || !sizes || !fin) {
+        err = _LACK_OF_MEMORY;
+        goto out;
+    }
+    offsets[0] = 0;
+    for (uint64_t b = 0; b < nb; b++) { /* d.c:278: sizes only, the counts are skipped */
+        const uint8_t *f;
+        size_t fl;
+        if (!cur_lit(&c, '@') || !cur_u64(&c, &sizes[b]) || !cur_lit(&c, '@')) {
+            err = _FILE_STREAM_FAILED;
+            goto out;
+        }
+        cur_field(&c, &f, &fl);
+        offsets[b + 1] = offsets[b] + sizes[b];
+        if (offsets[b + 1] > rle.size) { /* d.c:84 short read */
+            err = _FILE_STREAM_FAILED;
+            goto out;
+        }
+    }
+    g = gpu();
+    if (!g) {
+        err = _THREAD_CREATION_FAILED;
+        goto out;
+    }
+    if (nb) {
+        d_rle = shafa_cuda_dev_alloc(g, offsets[nb] + 64);
+        if (!d_rle) {
+            err = _LACK_OF_MEMORY;
+            goto out;
+        }
+        if ((err = gpu_status(shafa_cuda_memcpy_h2d(g, d_rle, rle.data, offsets[nb])))) goto out;
+        if ((err = expand_on_device(g, d_rle, offsets, nb, fin, &h_out, &out_size))) goto out;
+    }
+    err = write_all(p_out, h_out, out_size); /* d.c:218 */
+out:
+    if (g && d_rle) shafa_cuda_dev_free(g, d_rle);
+    if (h_out) shafa_cuda_host_free(h_out);
+    if (!err) {
+        summary("RLE", now_ms() - t0, sizes, fin, nb, p_out);
+        free(*path); /* d.c:378-379 */
+        *path = p_out;
+        p_out = NULL;
+    }
+    blob_free(&rle);
+    blob_free(&freq);
+    free(p_out);
+    free(offsets);
+    free(sizes);
+    free(fin);
+    return err;
+}
+
+_modules_error shafa_decompress(char **const path, const bool decompress_rle)
+{
+    const double t0 = now_ms();
+    char *p_base = rm_ext(*path); /* "<x>.shaf" -> "<x>" (d.c:652) */
+    char *p_out = NULL, *p_cod = NULL;
+    if (p_base) {
+        p_out = decompress_rle ? rm_ext(p_base) : add_ext(p_base, ""); /* d.c:655-661 */
+        p_cod = add_ext(p_base, CODES_EXT);
+    }
+    free(p_base);
+    if (!p_out || !p_cod) {
+        free(p_out);
+        free(p_cod);
+        return _LACK_OF_MEMORY;
+    }
+    blob shaf = {0}, cod = {0};
+    uint64_t nb = 0, nb_shaf = 0, *z = NULL, *poff = NULL, *n = NULL, *offsets = NULL, *fin = NULL, *code = NULL, out_size = 0;
+    uint8_t *len = NULL, *h_payload = NULL, *h_out = NULL;
+    void *d_payload = NULL, *d_len = NULL, *d_code = NULL, *d_sym = NULL;
+    shafa_cuda_ctx *g = NULL;
+    _modules_error err = blob_read(*path, &shaf);
+    if (!err) err = blob_read(p_cod, &cod);
+    free(p_cod);
+    if (err) goto out;
+    cursor s = {shaf.data, shaf.data + shaf.size}, c = {cod.data, cod.data + cod.size};
+    if (!cur_lit(&s, '@') || !cur_u64(&s, &nb_shaf)) { /* d.c:673 */
+        err = _FILE_STREAM_FAILED;
+        goto out;
+    }
+    if (!cur_lit(&c, '@') || c.p >= c.end) {
+        err = _FILE_STREAM_FAILED;
+        goto out;
+    }
+    const char mode = (char)*c.p++;
+    if (!cur_lit(&c, '@') || !cur_u64(&c, &nb)) { /* d.c:676: the .cod count wins */
+        err = _FILE_STREAM_FAILED;
+        goto out;
+    }
+    if (!((mode == 'N' && !decompress_rle) || mode == 'R')) { /* d.c:678 */
+        err = _FILE_UNRECOGNIZABLE;
+        goto out;
+    }
+    z = malloc((nb + 1) * sizeof *z);
+    poff = malloc((nb + 1) * sizeof *poff);
+    n = malloc((nb + 1) * sizeof *n);
+    offsets = malloc((nb + 1) * sizeof *offsets);
+    fin = malloc((nb + 1) * sizeof *fin);
+    code = malloc((nb * 256 + 1) * sizeof *code);
+    len = malloc(nb * 256 + 1);
+    h_payload = shafa_cuda_host_alloc(shaf.size + 16 * nb + 64);
+    if (!z || !poff || !n || !offsets || !fin || !code || !len || !h_payload) {
+        err = _LACK_OF_MEMORY;
+        goto out;
+    }
+    uint64_t ptotal = 0;
+    offsets[0] = 0;
+    for (uint64_t b = 0; b < nb; b++) {
+        const uint8_t *f;
+        size_t fl;
+        if (!cur_lit(&s, '@') || !cur_u64(&s, &z[b]) || !cur_lit(&s, '@') || (uint64_t)(s.end - s.p) < z[b]) { /* d.c:697,706 */
+            err = _FILE_STREAM_FAILED;
+            goto out;
+        }
+        poff[b] = ptotal; /* payload slots start 16-byte aligned on the device */
+        memcpy(h_payload + ptotal, s.p, z[b]);
+        s.p += z[b];
+        ptotal += (z[b] + 15) & ~15ull;
+        if (!cur_lit(&c, '@') || !cur_u64(&c, &n[b]) || !cur_lit(&c, '@') || !cur_field(&c, &f, &fl)) { /* d.c:709,716 */
+            err = _FILE_STREAM_FAILED;
+            goto out;
+        }
+        if ((err = cod_parse_fields(f, fl, len + b * 256, code + b * 256))) goto out;
+        offsets[b + 1] = offsets[b] + n[b];
+    }
+    g = gpu();
+    if (!g) {
+        err = _THREAD_CREATION_FAILED;
+        goto out;
+    }
+    if (nb) {
+        const uint64_t stotal = offsets[nb];
+        d_payload = shafa_cuda_dev_alloc(g, ptotal + 64);
+        d_len = shafa_cuda_dev_alloc(g, nb * 256);
+        d_code = shafa_cuda_dev_alloc(g, nb * 256 * 8);
+        d_sym = shafa_cuda_dev_alloc(g, stotal + 64);
+        if (!d_payload || !d_len || !d_code || !d_sym) {
+            err = _LACK_OF_MEMORY;
+            goto out;
+        }
+        if ((err = gpu_status(shafa_cuda_memcpy_h2d(g, d_payload, h_payload, ptotal)))) goto out;
+        if ((err = gpu_status(shafa_cuda_memcpy_h2d(g, d_len, len, nb * 256)))) goto out;
+        if ((err = gpu_status(shafa_cuda_memcpy_h2d(g, d_code, code, nb * 256 * 8)))) goto out;
+        if ((err = gpu_status(shafa_cuda_sf_decode_blocks(g, d_payload, poff, z, n, nb, d_len, d_code, d_sym, stotal + 64)))) goto out;
+        if (decompress_rle) { /* d.c:574-586 */
+            if ((err = expand_on_device(g, d_sym, offsets, nb, fin, &h_out, &out_size))) goto out;
+        } else {
+            h_out = shafa_cuda_host_alloc(stotal + 16);
+            if (!h_out) {
+                err = _LACK_OF_MEMORY;
+                goto out;
+            }
+            if ((err = gpu_status(shafa_cuda_memcpy_d2h(g, h_out, d_sym, stotal)))) goto out;
+            if ((err = gpu_status(shafa_cuda_synchronize(g)))) goto out;
+            out_size = stotal;
+            memcpy(fin, n, nb * sizeof *fin);
+        }
+    }
+    err = write_all(p_out, h_out, out_size); /* d.c:613 */
+out:
+    if (g) {
+        if (d_payload) shafa_cuda_dev_free(g, d_payload);
+        if (d_len) shafa_cuda_dev_free(g, d_len);
+        if (d_code) shafa_cuda_dev_free(g, d_code);
+        if (d_sym) shafa_cuda_dev_free(g, d_sym);
+    }
+    if (h_payload) shafa_cuda_host_free(h_payload);
+    if (h_out) shafa_cuda_host_free(h_out);
+    if (!err) {
+        summary(decompress_rle ? "SHAFA & RLE" : "SHAFA", now_ms() - t0, z, fin, nb, p_out);
+        free(*path); /* d.c:814-815 */
+        *path = p_out;
+        p_out = NULL;
+    }
+    blob_free(&shaf);
+    blob_free(&cod);
+    free(p_out);
+    free(z);
+    free(poff);
+    free(n);
+    free(offsets);
+    free(fin);
+    free(code);
+    free(len);
+    return err;
+}

@@ -1,0 +1,182 @@
+#include "util.h"
+
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+
+/* ---- extensions ---------------------------------------------------------------- */
+
+bool check_ext(const char *path, const char *ext)
+{
+    if (!path) return false;
+    const size_t lp = strlen(path), le = strlen(ext);
+    return lp >= le && strcmp(path + (lp - le), ext) == 0;
+}
+
+char *add_ext(const char *path, const char *ext)
+{
+    const size_t lp = strlen(path), le = strlen(ext);
+    char *out = malloc(lp + le + 1);
+    if (out) {
+        memcpy(out, path, lp);
+        memcpy(out + lp, ext, le + 1);
+    }
+    return out;
+}
+
+char *rm_ext(const char *path)
+{
+    const char *dot = strrchr(path, '.');
+    const size_t keep = dot ? (size_t)(dot - path) : strlen(path);
+    char *out = malloc(keep + 1);
+    if (out) {
+        memcpy(out, path, keep);
+        out[keep] = '\0';
+    }
+    return out;
+}
+
+/* ---- errors ------------------------------------------------------------------------ */
+
+const char *error_msg(int num)
+{
+    switch (num) {
+    case _SUCCESS: return "No error\n";
+    case _LACK_OF_MEMORY: return "Not enough memory for allocation\n";
+    case _FILE_INACCESSIBLE: return "File can't be accessed. Either lack of permissions or file doesn't exist\n";
+    case _FILE_UNRECOGNIZABLE: return "File not recognized\n";
+    case _FILE_STREAM_FAILED: return "Can't communicate properly with file's stream\n";
+    case _FILE_TOO_SMALL: return "File too small for decompression\n";
+    case _THREAD_CREATION_FAILED: return "Thread couldn't be created\n";
+    case _THREAD_TERMINATION_FAILED: return "Thread didn't terminate properly\n";
+    default: return "Unknown error";
+    }
+}
+
+/* ---- GPU context ------------------------------------------------------------------- */
+
+static shafa_cuda_ctx *g_ctx;
+
+shafa_cuda_ctx *gpu(void)
+{
+    if (!g_ctx) {
+        const char *dev = getenv("SHAFA_DEVICE");
+        if (shafa_cuda_create(dev ? atoi(dev) : 0, &g_ctx) != SHAFA_SUCCESS) g_ctx = NULL;
+    }
+    return g_ctx;
+}
+
+void gpu_release(void)
+{
+    if (g_ctx) shafa_cuda_destroy(g_ctx);
+    g_ctx = NULL;
+}
+
+_modules_error gpu_status(int rc)
+{
+    if (rc != SHAFA_SUCCESS && g_ctx && getenv("SHAFA_VERBOSE")) fprintf(stderr, "libshafa_cuda: %s\n", shafa_cuda_last_error(g_ctx));
+    return (_modules_error)rc;
+}
+
+/* ---- files ----------------------------------------------------------------------------- */
+
+_modules_error blob_read(const char *path, blob *b)
+{
+    b->data = NULL;
+    b->size = 0;
+    b->pinned = false;
+    FILE *f = fopen(path, "rb");
+    if (!f) return _FILE_INACCESSIBLE;
+    if (fseeko(f, 0, SEEK_END) != 0) {
+        fclose(f);
+        return _FILE_STREAM_FAILED;
+    }
+    const off_t sz = ftello(f);
+    if (sz < 0 || fseeko(f, 0, SEEK_SET) != 0) {
+        fclose(f);
+        return _FILE_STREAM_FAILED;
+    }
+    b->data = shafa_cuda_host_alloc((size_t)sz + 64);
+    b->pinned = b->data != NULL;
+    if (!b->data) b->data = malloc((size_t)sz + 64);
+    if (!b->data) {
+        fclose(f);
+        return _LACK_OF_MEMORY;
+    }
+    if (fread(b->data, 1, (size_t)sz, f) != (size_t)sz) {
+        fclose(f);
+        blob_free(b);
+        return _FILE_STREAM_FAILED;
+    }
+    memset(b->data + sz, 0, 64);
+    b->size = (uint64_t)sz;
+    fclose(f);
+    return _SUCCESS;
+}
+
+void blob_free(blob *b)
+{
+    if (b->data) {
+        if (b->pinned)
+            shafa_cuda_host_free(b->data);
+        else
+            free(b->data);
+    }
+    b->data = NULL;
+    b->size = 0;
+}
+
+/* ---- cursor -------------------------------------------------------------------------------- */
+
+bool cur_lit(cursor *c, char ch)
+{
+    if (c->p < c->end && *c->p == (uint8_t)ch) {
+        c->p++;
+        return true;
+    }
+    return false;
+}
+
+bool cur_u64(cursor *c, uint64_t *v)
+{
+    if (c->p >= c->end || *c->p < '0' || *c->p > '9') return false;
+    uint64_t x = 0;
+    while (c->p < c->end && *c->p >= '0' && *c->p <= '9') x = x * 10 + (uint64_t)(*c->p++ - '0');
+    *v = x;
+    return true;
+}
+
+bool cur_field(cursor *c, const uint8_t **start, size_t *len)
+{
+    *start = c->p;
+    while (c->p < c->end && *c->p != '@') c->p++;
+    *len = (size_t)(c->p - *start);
+    return *len > 0;
+}
+
+_modules_error cod_parse_fields(const uint8_t *p, size_t n, uint8_t *len, uint64_t *code)
+{
+    const uint8_t *end = p + n;
+    for (int s = 0; s < 256; s++) {
+        unsigned l = 0;
+        uint64_t v = 0;
+        while (p < end && (*p == '0' || *p == '1')) {
+            if (++l > 64) return _FILE_UNRECOGNIZABLE;
+            v = (v << 1) | (uint64_t)(*p++ == '1');
+        }
+        len[s] = (uint8_t)l;
+        code[s] = v;
+        if (s != 255) {
+            if (p >= end || *p != ';') return _FILE_UNRECOGNIZABLE; /* c.c:127-131,165-169 */
+            p++;
+        }
+    }
+    return p == end ? _SUCCESS : _FILE_UNRECOGNIZABLE; /* c.c:174-177 */
+}
+
+double now_ms(void)
+{
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e3 + ts.tv_nsec / 1e6;
+}

@@ -1,0 +1,56 @@
+/* util.h -- host-side helpers of the `shafa` program: paths, whole-file I/O into
+ * pinned memory, a cursor over the text containers, the shared GPU context. */
+#ifndef SHAFA_HOST_UTIL_H
+#define SHAFA_HOST_UTIL_H
+
+#include <stdbool.h>
+#include <stddef.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "modules.h"
+#include "shafa_cuda.h"
+
+#define RLE_EXT ".rle"
+#define FREQ_EXT ".freq"
+#define CODES_EXT ".cod"
+#define SHAFA_EXT ".shaf"
+
+enum { KIB_1 = 1024, KIB_64 = 65536, KIB_640 = 655360, MIB_8 = 8388608, MIB_64 = 67108864 };
+
+/* extension helpers (same contracts as utils/extensions.h:19-35) */
+bool check_ext(const char *path, const char *ext);
+char *add_ext(const char *path, const char *ext);
+char *rm_ext(const char *path);
+
+/* the process-wide GPU context (device from $SHAFA_DEVICE, default 0); NULL if no GPU */
+shafa_cuda_ctx *gpu(void);
+void gpu_release(void);
+/* libshafa_cuda status -> _modules_error (same numbering) */
+_modules_error gpu_status(int rc);
+
+/* whole file -> pinned host buffer (16 spare bytes after the end). */
+typedef struct {
+    uint8_t *data;
+    uint64_t size;
+    bool pinned; /* false: plain malloc (no CUDA device to pin against; the module will fail later) */
+} blob;
+_modules_error blob_read(const char *path, blob *b);
+void blob_free(blob *b);
+
+/* cursor over "@...@..." text */
+typedef struct {
+    const uint8_t *p, *end;
+} cursor;
+bool cur_lit(cursor *c, char ch);
+bool cur_u64(cursor *c, uint64_t *v);
+/* span of bytes up to the next '@' (not copied); false if empty */
+bool cur_field(cursor *c, const uint8_t **start, size_t *len);
+
+/* one .cod block: 256 ';'-separated '0'/'1' strings (c.c:115-177, d.c:479-495) -> length + right-aligned bits.
+ * Codes longer than 64 bits are legal in the format but not supported: _FILE_UNRECOGNIZABLE. */
+_modules_error cod_parse_fields(const uint8_t *p, size_t n, uint8_t *len, uint64_t *code);
+
+double now_ms(void);
+
+#endif

@@ -1,0 +1,131 @@
+"""The `shafa` host binary: option handling on the CPU, and (GPU) file-level parity
+with the reference's artefacts, including cross-decoding of the reference's files."""
+from __future__ import annotations
+
+import json
+import shutil
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, ROOT, small_cases
+
+BIN = ROOT / "shafa-cd_b200" / "shafa"
+
+
+def run(args, cwd):
+    return subprocess.run([str(BIN)] + args, cwd=cwd, capture_output=True, timeout=600)
+
+
+def test_binary_built():
+    assert BIN.exists(), "run `python __graft_entry__.py` (build()) first"
+
+
+def test_option_errors(tmp_path):
+    (tmp_path / "x").write_bytes(b"a" * 2000)
+    for args, msg in [([], b"No file input"), (["-m", "f"], b"No file input"), (["x", "-m", "q"], b"Wrong Options' syntax"),
+                      (["x", "-b", "Z"], b"Wrong Options' syntax"), (["x", "y"], b"Wrong Options' syntax"),
+                      (["x", "-m"], b"Wrong Options' syntax"), (["x", "-m", "ff"], b"Wrong Options' syntax")]:
+        r = run(args, tmp_path)
+        assert r.returncode == 1 and msg in r.stderr, (args, r.stderr)
+    # extension / ordering checks happen before any module runs (shafa.c:165-257)
+    for args, msg in [(["x", "-m", "t"], b"Module t: Wrong extension"), (["x", "-m", "d", "-d", "s"], b"Module d: Wrong extension"),
+                      (["x", "-m", "d", "-d", "r"], b"Module d: Wrong extension"), (["x", "-m", "d"], b"Module d: Wrong extension")]:
+        r = run(args, tmp_path)
+        assert r.returncode == 1 and msg in r.stderr, (args, r.stderr)
+
+
+def test_missing_file_and_small_file(tmp_path):
+    r = run(["nope", "-m", "f"], tmp_path)
+    assert r.returncode == 1 and b"File can't be accessed" in r.stderr
+    (tmp_path / "tiny").write_bytes(b"a" * 100)
+    r = run(["tiny", "-m", "f"], tmp_path)
+    assert r.returncode == 1 and b"File too small" in r.stderr   # f.c:220,366
+
+
+def _has_gpu(pkg):
+    return pkg.load_library().shafa_cuda_device_count() > 0
+
+
+def test_no_gpu_is_an_error_not_a_fallback(pkg, tmp_path):
+    if _has_gpu(pkg):
+        pytest.skip("a GPU is present")
+    (tmp_path / "x").write_bytes(bytes(range(256)) * 8)
+    r = run(["x", "-m", "f"], tmp_path)
+    assert r.returncode == 1 and not (tmp_path / "x.freq").exists()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", small_cases())
+def test_cli_matches_reference_files(case, tmp_path):
+    d = GOLDEN / case
+    flags = json.loads((d / "flags.json").read_text())
+    original = (d / "input.bin").read_bytes()
+    (tmp_path / "input.bin").write_bytes(original)
+    assert run(["input.bin", "-m", "f"] + flags["fflags"], tmp_path).returncode == 0
+    rle = (tmp_path / "input.bin.rle").exists()
+    base = "input.bin.rle" if rle else "input.bin"
+    assert run([base + ".freq", "-m", "t"], tmp_path).returncode == 0
+    assert run([base, "-m", "c"], tmp_path).returncode == 0
+    if rle and (tmp_path / "input.bin.freq").exists():
+        assert run(["input.bin.freq", "-m", "t"], tmp_path).returncode == 0
+    produced = sorted(p.name for p in tmp_path.iterdir())
+    expected = sorted(p.name for p in d.iterdir() if p.name != "flags.json")
+    assert produced == expected
+    for name in expected:
+        assert (tmp_path / name).read_bytes() == (d / name).read_bytes(), name
+    # decoding (the decoder overwrites its targets, like the reference)
+    if rle:
+        (tmp_path / "input.bin.rle").unlink()
+        assert run(["input.bin.rle.shaf", "-m", "d", "-d", "s"], tmp_path).returncode == 0
+        assert (tmp_path / "input.bin.rle").read_bytes() == (d / "input.bin.rle").read_bytes()
+        (tmp_path / "input.bin").unlink()
+        assert run(["input.bin.rle", "-m", "d", "-d", "r"], tmp_path).returncode == 0
+        assert (tmp_path / "input.bin").read_bytes() == original
+        (tmp_path / "input.bin").unlink()
+        assert run(["input.bin.rle.shaf"], tmp_path).returncode == 0          # default: -m d on *.shaf (shafa.c:293-295)
+        assert (tmp_path / "input.bin").read_bytes() == original
+    else:
+        (tmp_path / "input.bin").unlink()
+        assert run(["input.bin.shaf", "-m", "d"], tmp_path).returncode == 0
+        assert (tmp_path / "input.bin").read_bytes() == original
+
+
+@pytest.mark.gpu
+def test_cli_default_pipeline_and_block_flags(pkg, orc, tmp_path):
+    """`shafa file -b K` = F,T,C in one invocation (shafa.c:293-298); compared with the oracle."""
+    data = pkg.datagen.mixed4m(9 * 1024 * 1024 + 333, seed=5)
+    (tmp_path / "f").write_bytes(data.tobytes())
+    assert run(["f", "-b", "K"], tmp_path).returncode == 0
+    f = orc.module_f(data, 655360)
+    assert f["rle_mode"] and (tmp_path / "f.rle").read_bytes() == f["rle"]
+    assert (tmp_path / "f.rle.freq").read_bytes() == f["rle_freq"]
+    cod = orc.module_t(f["rle_freq"])
+    assert (tmp_path / "f.rle.cod").read_bytes() == cod
+    assert (tmp_path / "f.rle.shaf").read_bytes() == orc.module_c(f["rle"], cod)
+    (tmp_path / "f").unlink()
+    assert run(["f.rle.shaf", "-m", "d"], tmp_path).returncode == 0
+    assert (tmp_path / "f").read_bytes() == data.tobytes()
+
+
+@pytest.mark.gpu
+def test_cross_decode_with_reference_binary(pkg, orc, tmp_path):
+    """Our encoder -> reference decoder and reference encoder -> our decoder (where oracle/_ref exists)."""
+    if not orc.ref_available():
+        pytest.skip("oracle/_ref/shafa not present on this box")
+    data = pkg.datagen.textlike(1_500_000, seed=77)
+    ours, theirs = tmp_path / "ours", tmp_path / "theirs"
+    ours.mkdir(); theirs.mkdir()
+    (ours / "x").write_bytes(data.tobytes()); (theirs / "x").write_bytes(data.tobytes())
+    assert run(["x", "-b", "K"], ours).returncode == 0
+    for step in (["x", "-m", "f", "-b", "K"], ["x.rle.freq", "-m", "t"], ["x.rle", "-m", "c"]):
+        assert orc.ref_run(step, str(theirs)).returncode == 0
+    for name in ("x.rle", "x.rle.freq", "x.rle.cod", "x.rle.shaf"):
+        assert (ours / name).read_bytes() == (theirs / name).read_bytes(), name
+    (ours / "x").unlink(); (theirs / "x").unlink()
+    assert orc.ref_run(["x.rle.shaf", "-m", "d"], str(ours)).returncode == 0     # reference decodes our files
+    assert run(["x.rle.shaf", "-m", "d"], theirs).returncode == 0                 # we decode the reference's files
+    assert (ours / "x").read_bytes() == data.tobytes() and (theirs / "x").read_bytes() == data.tobytes()
+    _ = shutil
