@@ -124,6 +124,34 @@ SHAFA_HD RleEmit rle_emit_thread(const uint32_t *heads, uint32_t p0, int nvalid,
     return e;
 }
 
+// Bit-parallel form of the same rule for the common case k < 255 at all 16
+// positions of a thread (k = offset inside the run).  E[p] = 1 iff byte p equals
+// byte p-1 ("continuation"; 0 at the block start and at/after the block end).
+//   ewin   bit i = E[p0 - 8 + i]   (needs to be exact for positions p0-2 .. p0+18)
+//   z16    bit j = byte p0+j is 0x00
+//   valid  low nvalid bits set
+// A run has length >= 4 iff it has >= 3 consecutive continuation bits:
+//   T  = E & E>>1 & E>>2           first of three consecutive continuations
+//   Lc = T | T<<1 | T<<2           every continuation position of a long run
+//   LH = ~E & Lc>>1                heads of long runs
+// triple at heads of long runs and at heads of zero runs; literal at every
+// position of a short non-zero run; nothing elsewhere.
+struct RleMasks {
+    uint32_t lit, tri;
+};
+SHAFA_HD RleMasks rle_fast_masks(uint32_t ewin, uint32_t z16, uint32_t valid16)
+{
+    const uint32_t T = ewin & (ewin >> 1) & (ewin >> 2);
+    const uint32_t Lc = T | (T << 1) | (T << 2);
+    const uint32_t H = ~ewin;
+    const uint32_t LH = H & (Lc >> 1);
+    const uint32_t lc16 = (Lc >> 8) & 0xffffu, lh16 = (LH >> 8) & 0xffffu, h16 = (H >> 8) & 0xffffu;
+    RleMasks m;
+    m.tri = h16 & (lh16 | z16) & valid16;
+    m.lit = ~z16 & ~lc16 & ~lh16 & valid16 & 0xffffu;
+    return m;
+}
+
 // Write this thread's emitted bytes to dst (dst points at the thread's first
 // output byte).  Returns bytes written (== e.bytes).
 template <typename SymFn>
@@ -184,6 +212,14 @@ SHAFA_HD uint32_t fsm_thread_map(uint32_t zmask, int n)
     // entry 0: state 0 at position 0 -> ex[0]; entry 1: sym at 0, count at 1 -> ex[2];
     // entry 2: count at 0 -> ex[1]
     return a | (c << 2) | (b << 4);
+}
+
+// Shortcut used by the kernel: >= 2 valid bytes and none of them zero means every
+// entry state is back in state 0 within two bytes and stays there (constant map 0).
+SHAFA_HD uint32_t fsm_thread_map_fast(uint32_t zmask, int n)
+{
+    if (zmask == 0 && n >= 2) return 0u;
+    return fsm_thread_map(zmask, n);
 }
 
 // Walk the thread's n valid bytes from entry state `state`; `byte(q)` returns
@@ -316,28 +352,55 @@ struct DecSub {
 };
 
 // Decode from bit `start` until reaching `stop` (both relative to the sequence
-// words).  If out != nullptr the symbols are stored to out[0..] while fewer
-// than `max_out` have been written.
-SHAFA_HD DecSub dec_subsequence(const uint32_t *words, const DecTables &t, uint32_t start, uint32_t stop,
-                                uint8_t *out, uint32_t max_out)
+// words); emit(i, sym) is called for the i-th symbol.  The next >= 32 bits are
+// kept left-aligned in a 64-bit register and topped up one word at a time, so a
+// symbol costs one table lookup and a shift; codes longer than the first-level
+// table re-read an exact 64-bit window.
+template <typename Emit>
+SHAFA_HD DecSub dec_subsequence(const uint32_t *words, const DecTables &t, uint32_t start, uint32_t stop, Emit emit)
 {
     DecSub r;
     r.count = 0;
     r.bad = 0;
     uint32_t q = start;
-    while (q < stop) {
-        uint32_t sym = 0;
-        uint32_t l = dec_symbol(t, bit_window(words, q), &sym);
-        if (l == 0) {
-            r.bad = 1;
-            l = 1;
+    if (q < stop) {
+        uint32_t wi = q >> 5;
+        uint64_t buf = (((uint64_t)words[wi] << 32) | (uint64_t)words[wi + 1]) << (q & 31u);
+        uint32_t avail = 64u - (q & 31u);
+        wi += 2;
+        while (q < stop) {
+            if (avail < 32u) {
+                buf |= (uint64_t)words[wi++] << (32u - avail);
+                avail += 32u;
+            }
+            const uint32_t e = t.lut[buf >> (64 - DEC_LUT_BITS)];
+            uint32_t l = e & 0xFFu, sym = e >> 8;
+            if (l - 1u < (uint32_t)DEC_LUT_BITS) {
+                buf <<= l;
+                avail -= l;
+            } else {  // long code or no code: exact window, then rebuild the buffer
+                l = dec_symbol(t, bit_window(words, q), &sym);
+                if (l == 0) {
+                    r.bad = 1;
+                    l = 1;
+                }
+                const uint32_t nq = q + l;
+                wi = nq >> 5;
+                buf = (((uint64_t)words[wi] << 32) | (uint64_t)words[wi + 1]) << (nq & 31u);
+                avail = 64u - (nq & 31u);
+                wi += 2;
+            }
+            emit(r.count, sym);
+            r.count++;
+            q += l;
         }
-        if (out && r.count < max_out) out[r.count] = (uint8_t)sym;
-        r.count++;
-        q += l;
     }
     r.end = q;
     return r;
 }
+
+struct DecNoEmit {
+    SHAFA_HD void operator()(uint32_t, uint32_t) const {}
+};
 
 }  // namespace shafa

@@ -5,13 +5,19 @@
 //
 // The byte-serial parser of the reference becomes a 3-state automaton
 // (core.h): each thread summarises its 16 bytes as an entry->exit state map,
-// maps are composed by a CTA scan, and chain #1 (decoupled look-back inside the
-// block) carries the state across tiles -- tiles whose map is constant (almost
-// all) publish their exit state without waiting.  With the entry state known
-// every thread lists its records {length, byte}; a CTA scan plus chain #2 (over
-// all tiles of the file) places the tile in the output; the tile's record list
-// is then expanded cooperatively, 16 output bytes per thread per step, so long
-// runs become full-width stores and no thread ever owns a 255-byte memset.
+// maps are composed by a CTA scan (composition = one lookup in a 4 KiB table),
+// and chain #1 (decoupled look-back inside the block) carries the state across
+// tiles -- tiles whose map is constant (almost all) publish their exit state
+// without waiting.  With the entry state known every thread knows its records
+// {length, byte}; a CTA scan plus chain #2 (over all tiles of the file) places
+// the tile in the output.  Two ways to materialise a tile:
+//   * small expansion (<= 16 KiB, the literal-heavy case): every thread writes
+//     its own bytes into a staging buffer that is co-aligned with the
+//     destination, then the CTA copies it out with 16-byte stores;
+//   * large expansion (long runs): the records go to a list in shared memory and
+//     the CTA expands it cooperatively, one aligned 16-byte chunk per thread per
+//     step (binary search for the chunk's first record), so long runs become
+//     full-width stores and no thread ever owns a 255-byte memset.
 #include "common.cuh"
 #include "core.h"
 #include "internal.h"
@@ -19,15 +25,25 @@
 namespace shafa {
 
 constexpr int RLD_THREADS = 256;
-constexpr int RLD_TILE = RLD_THREADS * RLE_ITEMS;  // 4096 RLE bytes
+constexpr int RLD_WARPS = RLD_THREADS / 32;
+constexpr int RLD_TILE = RLD_THREADS * RLE_ITEMS;          // 4096 RLE bytes
+constexpr int RLD_STAGE = 16384;                           // staged expansion limit (bytes)
 constexpr uint64_t RLE_BLOCK_CAP = 67108864ull + 1024ull;  // d.c:135,163
 
 struct RleDecShared {
-    uint32_t rec_start[RLD_TILE + 1];
-    uint8_t rec_sym[RLD_TILE];
-    uint32_t scan[RLD_THREADS / 32 + 1];
-    uint32_t wmap[RLD_THREADS / 32];
+    union {
+        struct {
+            uint32_t rec_start[RLD_TILE + 1];
+            uint8_t rec_sym[RLD_TILE];
+        } list;
+        alignas(16) uint8_t stage[RLD_STAGE + 32];
+    } u;
+    uint8_t compose[64 * 64];  // compose[a*64+b] = first a, then b
+    uint32_t scan[RLD_WARPS + 1];
+    uint32_t wmap[RLD_WARPS];
+    uint32_t wexcl[RLD_WARPS];
     uint64_t out_prefix;
+    uint32_t tile_map;
     uint32_t entry;
     uint32_t ticket;
     uint32_t block;
@@ -42,6 +58,7 @@ k_rle_decode(const uint8_t *__restrict__ in, const uint64_t *__restrict__ off, c
     __shared__ RleDecShared sh;
     const unsigned tid = threadIdx.x, lane = lane_id(), warp = warp_id();
     const uint64_t total_tiles = tile0[nb];
+    for (int i = tid; i < 64 * 64; i += RLD_THREADS) sh.compose[i] = (uint8_t)fsm_compose((uint32_t)i >> 6, (uint32_t)i & 63u);
 
     for (;;) {
         __syncthreads();
@@ -70,30 +87,33 @@ k_rle_decode(const uint8_t *__restrict__ in, const uint64_t *__restrict__ off, c
             j1 = (hi < pos + 16) ? (int)(hi - pos) : 16;
         }
         const int n = j1 - j0;
-        const uint32_t zmask = zero_mask16(v) >> j0;
+        const uint32_t zmask = (zero_mask16(v) >> j0) & ((n >= 16) ? 0xffffu : ((1u << n) - 1u));
 
-        // ---- state maps: thread -> warp -> CTA ----
-        const uint32_t my_map = fsm_thread_map(zmask, n);
-        uint32_t incl = my_map;
+        // ---- state maps: thread -> warp -> CTA (composition through the table) ----
+        uint32_t incl = fsm_thread_map_fast(zmask, n);
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             const uint32_t o = __shfl_up_sync(FULL, incl, d);
-            if (lane >= (unsigned)d) incl = fsm_compose(o, incl);
+            if (lane >= (unsigned)d) incl = sh.compose[o * 64 + incl];
         }
         if (lane == 31) sh.wmap[warp] = incl;
         uint32_t excl_map = __shfl_up_sync(FULL, incl, 1);
         if (lane == 0) excl_map = FSM_IDENTITY;
         __syncthreads();
-        uint32_t before = FSM_IDENTITY, tile_map = FSM_IDENTITY;
-        for (unsigned w = 0; w < RLD_THREADS / 32; w++) {
-            const uint32_t m = sh.wmap[w];
-            if (w < warp) before = fsm_compose(before, m);
-            tile_map = fsm_compose(tile_map, m);
-        }
-        excl_map = fsm_compose(before, excl_map);  // everything of this tile before this thread
 
-        // ---- chain #1: automaton state at the tile start ----
+        // ---- warp 0: scan of the warp maps, then chain #1 (automaton state at the tile start) ----
         if (warp == 0) {
+            uint32_t wm = (lane < RLD_WARPS) ? sh.wmap[lane] : FSM_IDENTITY;
+            uint32_t wi = wm;
+#pragma unroll
+            for (int d = 1; d < RLD_WARPS; d <<= 1) {
+                const uint32_t o = __shfl_up_sync(FULL, wi, d);
+                if (lane >= (unsigned)d) wi = sh.compose[o * 64 + wi];
+            }
+            uint32_t we = __shfl_up_sync(FULL, wi, 1);
+            if (lane == 0) we = FSM_IDENTITY;
+            if (lane < RLD_WARPS) sh.wexcl[lane] = we;
+            const uint32_t tile_map = __shfl_sync(FULL, wi, RLD_WARPS - 1);
             uint32_t entry = 0;
             if (is_first) {
                 if (lane == 0) desc_store(desc_state_chain + t, desc_pack(DESC_PREFIX, fsm_apply(tile_map, 0)));
@@ -114,9 +134,8 @@ k_rle_decode(const uint8_t *__restrict__ in, const uint64_t *__restrict__ off, c
                     }
                     const unsigned pm = __ballot_sync(FULL, desc_state(d) == DESC_PREFIX);
                     const int upto = pm ? (__ffs(pm) - 1) : 32;  // lanes 0..upto-1 hold maps, lane upto the state
-                    // compose maps of lanes upto-1 .. 0 (oldest first) in front of `pending`
                     uint32_t win = FSM_IDENTITY;
-                    for (int i = upto - 1; i >= 0; i--) {
+                    for (int i = upto - 1; i >= 0; i--) {  // oldest first
                         const uint32_t m = (uint32_t)desc_value(__shfl_sync(FULL, d, i));
                         win = fsm_compose(win, m);
                     }
@@ -131,22 +150,29 @@ k_rle_decode(const uint8_t *__restrict__ in, const uint64_t *__restrict__ off, c
                 if (!cst && lane == 0)
                     desc_store(desc_state_chain + t, desc_pack(DESC_PREFIX, fsm_apply(tile_map, entry)));
             }
-            if (lane == 0) sh.entry = entry;
+            if (lane == 0) {
+                sh.entry = entry;
+                sh.tile_map = tile_map;
+            }
         }
         __syncthreads();
         const uint32_t tile_entry = sh.entry;
-        const uint32_t my_entry = fsm_apply(excl_map, tile_entry);
+        const uint32_t my_entry = fsm_apply(excl_map, fsm_apply(sh.wexcl[warp], tile_entry));
 
         // ---- records of this thread: count + output bytes ----
+        const bool all_literal = (n == 16) && (zmask == 0) && (my_entry == 0);
         uint32_t prevb = 0;
         if (n > 0 && my_entry == 2 && pos + j0 > lo) prevb = in[pos + j0 - 1];
         auto bytef = [&](int q) -> uint32_t { return byte_of(v, j0 + q); };
-        uint32_t recs = 0, obytes = 0;
-        const uint32_t exit_state = rle_parse_thread(my_entry, n, prevb, bytef, [&](uint32_t len, uint32_t) {
-            recs++;
-            obytes += len;
-        });
-        (void)exit_state;
+        uint32_t recs = 16, obytes = 16;
+        if (!all_literal) {
+            recs = 0;
+            obytes = 0;
+            rle_parse_thread(my_entry, n, prevb, bytef, [&](uint32_t len, uint32_t) {
+                recs++;
+                obytes += len;
+            });
+        }
         uint32_t packed_total;
         const uint32_t packed_excl = block_excl_scan<RLD_THREADS>(obytes | (recs << 19), sh.scan, &packed_total);
         const uint32_t tile_out = packed_total & ((1u << 19) - 1u);
@@ -155,48 +181,81 @@ k_rle_decode(const uint8_t *__restrict__ in, const uint64_t *__restrict__ off, c
             const uint64_t pfx = lookback_sum(desc_out, (int64_t)t, 0, tile_out);
             if (lane == 0) sh.out_prefix = pfx;
         }
-        // ---- record list in shared memory ----
-        {
-            uint32_t o = packed_excl & ((1u << 19) - 1u);
-            uint32_t r = packed_excl >> 19;
-            rle_parse_thread(my_entry, n, prevb, bytef, [&](uint32_t len, uint32_t sym) {
-                sh.rec_start[r] = o;
-                sh.rec_sym[r] = (uint8_t)sym;
-                r++;
-                o += len;
-            });
-            if (tid == RLD_THREADS - 1) sh.rec_start[tile_recs] = tile_out;
-        }
         __syncthreads();
         const uint64_t out0 = sh.out_prefix;
         if (is_last && tid == 0) {
             blk_end[b] = out0 + tile_out;
-            if (fsm_apply(tile_map, tile_entry) != 0) atomicOr(err, 64u);  // block ends inside a triple
+            if (fsm_apply(sh.tile_map, tile_entry) != 0) atomicOr(err, (uint32_t)ERR_RLE_TRUNCATED);  // block ends inside a triple
         }
         if (out0 + tile_out > out_capacity) {
-            if (tid == 0) atomicOr(err, 32u);
+            if (tid == 0) atomicOr(err, (uint32_t)ERR_CAPACITY);
             continue;
         }
-        // ---- cooperative expansion: one aligned 16-byte chunk per thread per step ----
-        if (tile_out) {
+        if (tile_out == 0) continue;
+        const uint32_t my_out = packed_excl & ((1u << 19) - 1u);
+
+        if (tile_out <= (uint32_t)RLD_STAGE) {
+            // ---- staged expansion: every thread writes its own bytes ----
+            const uint32_t shift = (uint32_t)(out0 & 15u);
+            uint8_t *dst = sh.u.stage + shift + my_out;
+            if (all_literal) {
+#pragma unroll
+                for (int j = 0; j < 16; j++) dst[j] = (uint8_t)byte_of(v, j);
+            } else {
+                rle_parse_thread(my_entry, n, prevb, bytef, [&](uint32_t len, uint32_t sym) {
+                    for (uint32_t k = 0; k < len; k++) dst[k] = (uint8_t)sym;
+                    dst += len;
+                });
+            }
+            __syncthreads();
+            uint8_t *g = out + (out0 - shift);  // 16-byte aligned
+            const uint32_t end = shift + tile_out;
+            for (uint32_t c = tid * 16; c < end; c += RLD_THREADS * 16) {
+                if (c >= shift && c + 16 <= end) {
+                    st_stream16(g + c, *reinterpret_cast<const uint4 *>(sh.u.stage + c));
+                } else {
+                    for (uint32_t k = (c > shift ? c : shift); k < c + 16 && k < end; k++) g[k] = sh.u.stage[k];
+                }
+            }
+        } else {
+            // ---- large expansion: record list + cooperative fill ----
+            {
+                uint32_t o = my_out;
+                uint32_t r = packed_excl >> 19;
+                if (all_literal) {
+#pragma unroll
+                    for (int j = 0; j < 16; j++) {
+                        sh.u.list.rec_start[r + j] = o + j;
+                        sh.u.list.rec_sym[r + j] = (uint8_t)byte_of(v, j);
+                    }
+                } else {
+                    rle_parse_thread(my_entry, n, prevb, bytef, [&](uint32_t len, uint32_t sym) {
+                        sh.u.list.rec_start[r] = o;
+                        sh.u.list.rec_sym[r] = (uint8_t)sym;
+                        r++;
+                        o += len;
+                    });
+                }
+                if (tid == RLD_THREADS - 1) sh.u.list.rec_start[tile_recs] = tile_out;
+            }
+            __syncthreads();
             const uint64_t a0 = out0 & ~15ull;
             const uint64_t a1 = out0 + tile_out;
             for (uint64_t g = a0 + (uint64_t)tid * 16; g < a1; g += (uint64_t)RLD_THREADS * 16) {
                 const int64_t r0 = (int64_t)g - (int64_t)out0;  // tile-relative offset of the chunk (may be < 0)
                 const uint32_t first = r0 < 0 ? 0u : (uint32_t)r0;
-                // record containing `first`: largest ri with rec_start[ri] <= first
-                uint32_t lo_i = 0, hi_i = tile_recs;
+                uint32_t lo_i = 0, hi_i = tile_recs;  // largest ri with rec_start[ri] <= first
                 while (hi_i - lo_i > 1) {
                     const uint32_t mid = (lo_i + hi_i) >> 1;
-                    if (sh.rec_start[mid] <= first)
+                    if (sh.u.list.rec_start[mid] <= first)
                         lo_i = mid;
                     else
                         hi_i = mid;
                 }
                 uint32_t ri = lo_i;
                 const bool full = (r0 >= 0) && (r0 + 16 <= (int64_t)tile_out);
-                if (full && sh.rec_start[ri + 1] >= first + 16) {
-                    const uint32_t w = (uint32_t)sh.rec_sym[ri] * 0x01010101u;
+                if (full && sh.u.list.rec_start[ri + 1] >= first + 16) {
+                    const uint32_t w = (uint32_t)sh.u.list.rec_sym[ri] * 0x01010101u;
                     st_stream16(out + g, make_uint4(w, w, w, w));
                 } else {
                     uint32_t w[4] = {0, 0, 0, 0};
@@ -204,8 +263,8 @@ k_rle_decode(const uint8_t *__restrict__ in, const uint64_t *__restrict__ off, c
                     for (int k = 0; k < 16; k++) {
                         const int64_t r = r0 + k;
                         if (r >= 0 && r < (int64_t)tile_out) {
-                            while (sh.rec_start[ri + 1] <= (uint32_t)r) ri++;
-                            w[k >> 2] |= (uint32_t)sh.rec_sym[ri] << (8 * (k & 3));
+                            while (sh.u.list.rec_start[ri + 1] <= (uint32_t)r) ri++;
+                            w[k >> 2] |= (uint32_t)sh.u.list.rec_sym[ri] << (8 * (k & 3));
                         }
                     }
                     if (full) {
@@ -254,7 +313,7 @@ int launch_rle_decode(shafa_cuda_ctx *ctx, const uint8_t *d_rle, const uint64_t 
     if (!desc || !blk_end || !counter) return SHAFA_LACK_OF_MEMORY;
     SHAFA_CUDA_TRY(ctx, cudaMemsetAsync(desc, 0, 2 * (tiles + 1) * sizeof(uint64_t), ctx->stream));
     SHAFA_CUDA_TRY(ctx, cudaMemsetAsync(counter, 0, 4, ctx->stream));
-    // empty blocks never run a tile: pre-fill their ends on the host side below
+    // empty blocks never run a tile: their ends are filled in on the host side below
     SHAFA_CUDA_TRY(ctx, cudaMemsetAsync(blk_end, 0xff, nb * sizeof(uint64_t), ctx->stream));
     if (tiles) {
         uint64_t grid = (uint64_t)ctx->sm_count * occ;

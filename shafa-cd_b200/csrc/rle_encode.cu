@@ -4,33 +4,39 @@
 // file, f.c:307).  Algorithmic bytes: N read + R written.
 //
 // Tile = 4096 bytes of one block (tiles never straddle a block), 256 threads x
-// 16 bytes.  Per tile:
-//   1. 16-byte loads; run-head bitmask of the tile plus a 288-position look-ahead
-//      halo (positions at/after the block end count as heads);
-//   2. chain #1 (decoupled look-back inside the block): length of the equal-byte
-//      run that is still open at the tile start, needed for k mod 255;
-//   3. shafa::rle_emit_thread decides what each position emits (core.h);
+// 16 bytes held in registers.  Per tile:
+//   1. 16-byte loads; "continuation" bits E (byte equals its predecessor) by
+//      SIMD byte compares; neighbours' bits arrive by warp shuffles, the warp
+//      edges read one extra word.  ~E is the run-head bitmask, kept in shared
+//      memory together with a 288-position look-ahead halo (positions at/after
+//      the block end count as heads).
+//   2. chain #1 (decoupled look-back inside the block): length of the run that
+//      is still open at the tile start (needed for k mod 255).
+//   3. what every position emits: threads whose positions all have k < 255 use
+//      the bit-parallel rule shafa::rle_fast_masks (core.h); threads deep inside
+//      a >= 255-byte run use the general per-position walk rle_emit_thread.
 //   4. CTA scan of emitted bytes, chain #2 (look-back over ALL tiles of the
-//      file) gives the tile's offset in the compacted output;
+//      file) gives the tile's offset in the compacted output.
 //   5. bytes are staged in shared memory co-aligned with the destination and
 //      copied out with 16-byte stores; the same staging buffer feeds the fused
-//      256-bin histogram.
+//      256-bin histogram (8 striped sub-histograms to spread equal-byte hits).
 #include "common.cuh"
 #include "core.h"
 #include "internal.h"
 
 namespace shafa {
 
-constexpr int RLE_THREADS = RLE_TILE / RLE_ITEMS;  // 256
-constexpr int RLE_STAGE = 2 * RLE_TILE + 3 + 16 + 13;  // worst case 2n+3 (f.c:244) + alignment slack, multiple of 16
+constexpr int RLE_THREADS = RLE_TILE / RLE_ITEMS;        // 256
+constexpr int RLE_WARPS = RLE_THREADS / 32;
+constexpr int RLE_STAGE = 2 * RLE_TILE + 3 + 16 + 13;    // worst case 2n+3 (f.c:244) + alignment slack, multiple of 16
+constexpr int RLE_HIST_COPIES = 8;
 
 struct RleEncShared {
-    alignas(16) uint8_t bytes[16 + RLE_TILE + RLE_HALO + 16];  // [16 back halo][tile][look-ahead]
     alignas(16) uint8_t stage[RLE_STAGE];
     uint32_t heads[RLE_HEAD_WORDS + 2];
-    uint32_t hist[RLE_THREADS / 32][256];
-    uint32_t scan[RLE_THREADS / 32 + 1];
-    int32_t lasthead[RLE_THREADS / 32];
+    uint32_t hist[256 * RLE_HIST_COPIES];
+    uint32_t scan[RLE_WARPS + 1];
+    int32_t lasthead[RLE_WARPS];
     uint64_t out_prefix;
     uint64_t run_in;
     uint32_t ticket;
@@ -43,14 +49,15 @@ k_rle_encode(const uint8_t *__restrict__ in, uint64_t n, uint64_t block_size, ui
              unsigned long long *__restrict__ hist, uint64_t *__restrict__ blk_end, uint64_t *__restrict__ desc_run,
              uint64_t *__restrict__ desc_out, uint32_t *__restrict__ counter, uint32_t *__restrict__ err)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    RleEncShared &sh = *reinterpret_cast<RleEncShared *>(smem_raw);
+    __shared__ RleEncShared sh;
     const unsigned tid = threadIdx.x, lane = lane_id(), warp = warp_id();
-    uint8_t *tileb = sh.bytes + 16;  // tileb[p] = byte at tile position p; tileb[-1] = byte before the tile
 
     for (;;) {
         __syncthreads();
         if (tid == 0) sh.ticket = atomicAdd(counter, 1u);
+        if (HIST) {
+            for (int i = tid; i < 256 * RLE_HIST_COPIES; i += RLE_THREADS) sh.hist[i] = 0;
+        }
         __syncthreads();
         const uint64_t t = sh.ticket;
         if (t >= total_tiles) break;
@@ -62,43 +69,57 @@ k_rle_encode(const uint8_t *__restrict__ in, uint64_t n, uint64_t block_size, ui
         const uint32_t tile_len = (uint32_t)((blk_hi - tile_lo < RLE_TILE) ? (blk_hi - tile_lo) : RLE_TILE);
         const bool last_tile = (tile_lo + tile_len == blk_hi);
         const uint64_t first_tile_of_block = b * tiles_per_block;
-
-        // ---- 1. load tile + halo (16-byte vectors; the block start is 16-byte aligned) ----
-        uint4 v = make_uint4(0, 0, 0, 0);
-        {
-            const uint64_t pos = tile_lo + (uint64_t)tid * 16;
-            if (pos < blk_hi) v = ld_stream16(in + pos);
-            *reinterpret_cast<uint4 *>(tileb + tid * 16) = v;
-            if (tid < RLE_HALO / 16) {  // look-ahead halo
-                uint4 h = make_uint4(0, 0, 0, 0);
-                const uint64_t hp = tile_lo + RLE_TILE + (uint64_t)tid * 16;
-                if (hp < blk_hi) h = ld_stream16(in + hp);
-                *reinterpret_cast<uint4 *>(tileb + RLE_TILE + tid * 16) = h;
-            }
-            if (tid == RLE_THREADS - 1) tileb[-1] = (ti != 0) ? in[tile_lo - 1] : 0;
-        }
-        __syncthreads();
-        // ---- heads: bit p set iff position p starts a run (or lies at/after the block end) ----
         const uint32_t valid_len = (uint32_t)((blk_hi - tile_lo < (uint64_t)(RLE_TILE + RLE_HALO)) ? (blk_hi - tile_lo)
                                                                                                   : (RLE_TILE + RLE_HALO));
-        uint32_t my_heads;
+        // ---- 1. load; continuation bits of my 16 positions and of my neighbours ----
+        const uint32_t p0 = tid * 16;
+        const uint64_t pos = tile_lo + p0;
+        const int nvalid = (p0 >= tile_len) ? 0 : (int)((tile_len - p0 < 16) ? (tile_len - p0) : 16);
+        const uint32_t valid16 = (nvalid >= 16) ? 0xffffu : ((1u << nvalid) - 1u);
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (nvalid) v = ld_stream16(in + pos);
+        uint32_t prevb = __shfl_up_sync(FULL, v.w >> 24, 1);
+        uint32_t e_before = 0;  // E of the 8 positions before mine (only the top 2 bits matter)
+        if (lane == 0 && pos > blk_lo && nvalid) {
+            const uint32_t w = *reinterpret_cast<const uint32_t *>(in + pos - 4);  // bytes pos-4 .. pos-1, inside the block
+            prevb = w >> 24;
+            const uint32_t b1 = (w >> 8) & 0xffu, b2 = (w >> 16) & 0xffu;
+            e_before = ((b2 == b1) ? 0x40u : 0u) | ((prevb == b2) ? 0x80u : 0u);
+        }
+        uint32_t e16 = eq_prev_mask16(v, prevb) & valid16;   // positions at/after the block end: E = 0
+        if (pos == blk_lo) e16 &= ~1u;                        // the block start is a head
         {
-            const uint32_t p0h = tid * 16;
-            uint32_t m = ~eq_prev_mask16(v, tileb[(int)p0h - 1]) & 0xffffu;
-            if (p0h + 16 > valid_len) m |= (p0h >= valid_len) ? 0xffffu : (0xffffu << (valid_len - p0h)) & 0xffffu;
-            if (tid == 0 && ti == 0) m |= 1u;
-            my_heads = m;
-            reinterpret_cast<uint16_t *>(sh.heads)[tid] = (uint16_t)m;
-            if (tid < RLE_HALO / 16) {  // halo chunks, from shared memory
-                const uint32_t q0 = RLE_TILE + tid * 16;
-                const uint4 hv = *reinterpret_cast<const uint4 *>(tileb + q0);
-                uint32_t hm = ~eq_prev_mask16(hv, tileb[q0 - 1]) & 0xffffu;
-                if (q0 + 16 > valid_len) hm |= (q0 >= valid_len) ? 0xffffu : (0xffffu << (valid_len - q0)) & 0xffffu;
-                reinterpret_cast<uint16_t *>(sh.heads)[RLE_TILE / 16 + tid] = (uint16_t)hm;
+            const uint32_t up = __shfl_up_sync(FULL, e16, 1);
+            if (lane != 0) e_before = up >> 8;
+        }
+        uint32_t e_after = __shfl_down_sync(FULL, e16, 1) & 0xffu;
+        if (lane == 31) {
+            e_after = 0;
+            if (nvalid == 16 && pos + 16 < blk_hi) {
+                const uint32_t w = *reinterpret_cast<const uint32_t *>(in + pos + 16);  // bytes pos+16 .. pos+19
+                const uint32_t c0 = w & 0xffu, c1 = (w >> 8) & 0xffu, c2 = (w >> 16) & 0xffu;
+                const uint64_t left = blk_hi - (pos + 16);  // valid bytes from pos+16 on
+                e_after = (c0 == (v.w >> 24)) ? 1u : 0u;
+                if (left > 1 && c1 == c0) e_after |= 2u;
+                if (left > 2 && c2 == c1) e_after |= 4u;
             }
         }
-        // ---- last head at or before each thread's first position ----
-        int32_t lh = my_heads ? (int32_t)(tid * 16 + 31 - clz32(my_heads)) : -1;  // highest head inside my 16
+        const uint32_t ewin = (e_before & 0xffu) | (e16 << 8) | (e_after << 24);
+        const uint32_t my_heads = ~e16 & 0xffffu;  // includes every position >= valid
+        reinterpret_cast<uint16_t *>(sh.heads)[tid] = (uint16_t)my_heads;
+        if (tid < RLE_HALO / 16) {  // look-ahead halo heads, straight from global memory
+            const uint32_t q0 = RLE_TILE + tid * 16;
+            uint32_t hm = 0xffffu;
+            if (q0 < valid_len) {
+                const uint4 hv = ld_stream16(in + tile_lo + q0);
+                const uint32_t pb = in[tile_lo + q0 - 1];
+                hm = ~eq_prev_mask16(hv, pb) & 0xffffu;
+                if (q0 + 16 > valid_len) hm |= (0xffffu << (valid_len - q0)) & 0xffffu;
+            }
+            reinterpret_cast<uint16_t *>(sh.heads)[RLE_TILE / 16 + tid] = (uint16_t)hm;
+        }
+        // ---- last head strictly before each thread's first position ----
+        int32_t lh = my_heads ? (int32_t)(p0 + 31 - clz32(my_heads)) : -1;  // highest head inside my 16
         {
             int32_t incl = lh;
 #pragma unroll
@@ -109,7 +130,7 @@ k_rle_encode(const uint8_t *__restrict__ in, uint64_t n, uint64_t block_size, ui
             if (lane == 31) sh.lasthead[warp] = incl;
             int32_t prev = __shfl_up_sync(FULL, incl, 1);
             if (lane == 0) prev = -1;
-            lh = prev;  // exclusive within the warp
+            lh = prev;
         }
         __syncthreads();  // heads[] and lasthead[] complete
         {
@@ -123,12 +144,10 @@ k_rle_encode(const uint8_t *__restrict__ in, uint64_t n, uint64_t block_size, ui
 
         // ---- 2. chain #1: equal-byte run still open at the tile start ----
         if (warp == 0) {
-            // run length that is open at the END of this tile, if it can be known locally
-            // last head among valid positions:
-            int32_t lastv = -1;
+            int32_t lastv = -1;  // last head among the tile's valid positions
             for (int w = (int)((tile_len + 31) / 32) - 1 - (int)lane; w >= 0; w -= 32) {
                 uint32_t word = sh.heads[w];
-                const uint32_t lim = tile_len - (uint32_t)w * 32;  // valid bits in this word
+                const uint32_t lim = tile_len - (uint32_t)w * 32;
                 if (lim < 32) word &= (1u << lim) - 1u;
                 if (word) {
                     lastv = w * 32 + 31 - clz32(word);
@@ -143,7 +162,7 @@ k_rle_encode(const uint8_t *__restrict__ in, uint64_t n, uint64_t block_size, ui
             const bool head0 = (sh.heads[0] & 1u) != 0;
             uint64_t run_in = 0;
             if (lastv >= 0) {
-                // the open run at the tile end starts inside this tile: publish it right away
+                // the run open at the tile end starts inside this tile: publish it right away
                 if (lane == 0) desc_store(desc_run + t, desc_pack(DESC_PREFIX, (uint64_t)(tile_len - (uint32_t)lastv)));
                 if (!head0) run_in = lookback_read(desc_run, (int64_t)t, (int64_t)first_tile_of_block);
             } else {
@@ -156,15 +175,32 @@ k_rle_encode(const uint8_t *__restrict__ in, uint64_t n, uint64_t block_size, ui
         const uint64_t run_in = sh.run_in;
 
         // ---- 3. what does each position emit ----
-        const uint32_t p0 = tid * 16;
-        const int nvalid = (p0 >= tile_len) ? 0 : (int)((tile_len - p0 < 16) ? (tile_len - p0) : 16);
-        uint32_t c0 = 0;
-        if (nvalid) {
-            const uint64_t k = (lh >= 0) ? (uint64_t)(p0 - (uint32_t)lh) : (uint64_t)p0 + run_in;
-            c0 = (uint32_t)(k % 255);
-        }
         auto symf = [&](int j) -> uint32_t { return byte_of(v, j); };
-        const RleEmit em = rle_emit_thread(sh.heads, p0, nvalid, c0, symf);
+        RleEmit em;
+        em.lit = em.tri = em.bytes = 0;
+        em.cnt[0] = em.cnt[1] = em.cnt[2] = em.cnt[3] = 0;
+        if (nvalid) {
+            const uint64_t k0 = (lh >= 0) ? (uint64_t)(p0 - (uint32_t)lh) : (uint64_t)p0 + run_in;  // k at p0 if p0 is no head
+            if ((e16 & 1u) && k0 + 15 >= 255) {
+                em = rle_emit_thread(sh.heads, p0, nvalid, (uint32_t)(k0 % 255), symf);  // deep inside a long run
+            } else {
+                const RleMasks m = rle_fast_masks(ewin, zero_mask16(v), valid16);
+                em.lit = m.lit;
+                em.tri = m.tri;
+                uint32_t tb = m.tri;
+                while (tb) {
+                    const int j = ctz32(tb);
+                    tb &= tb - 1;
+                    const uint32_t val = rle_run_remaining(sh.heads, p0 + (uint32_t)j) << (8 * (j & 3));
+                    const int q = j >> 2;  // constant indices keep cnt[] in registers
+                    if (q == 0) em.cnt[0] |= val;
+                    else if (q == 1) em.cnt[1] |= val;
+                    else if (q == 2) em.cnt[2] |= val;
+                    else em.cnt[3] |= val;
+                }
+                em.bytes = (uint32_t)__popc(m.lit) + 3u * (uint32_t)__popc(m.tri);
+            }
+        }
 
         // ---- 4. offsets ----
         uint32_t tile_bytes;
@@ -173,20 +209,26 @@ k_rle_encode(const uint8_t *__restrict__ in, uint64_t n, uint64_t block_size, ui
             const uint64_t pfx = lookback_sum(desc_out, (int64_t)t, 0, tile_bytes);
             if (lane == 0) sh.out_prefix = pfx;
         }
-        if (HIST) {
-            for (int i = tid; i < (RLE_THREADS / 32) * 256; i += RLE_THREADS) (&sh.hist[0][0])[i] = 0;
-        }
         __syncthreads();
         const uint64_t out0 = sh.out_prefix;
         if (last_tile && tid == 0) blk_end[b] = out0 + tile_bytes;
+        if (!WRITE && !HIST) continue;
 
         // ---- 5. stage + copy out + fused histogram ----
         const uint32_t shift = (uint32_t)(out0 & 15u);  // co-align staging with the destination
-        rle_write_thread(em, sh.stage + shift + excl, symf);
+        {
+            uint8_t *dst = sh.stage + shift + excl;
+            if (em.tri == 0 && em.lit == 0xffffu) {
+#pragma unroll
+                for (int j = 0; j < 16; j++) dst[j] = (uint8_t)byte_of(v, j);
+            } else if (em.tri | em.lit) {
+                rle_write_thread(em, dst, symf);
+            }
+        }
         __syncthreads();
         if (WRITE) {
             if (out0 + tile_bytes > out_capacity) {
-                if (tid == 0) atomicOr(err, 32u);
+                if (tid == 0) atomicOr(err, (uint32_t)ERR_CAPACITY);
             } else {
                 uint8_t *dst = out + (out0 - shift);  // 16-byte aligned
                 const uint32_t end = shift + tile_bytes;
@@ -200,12 +242,27 @@ k_rle_encode(const uint8_t *__restrict__ in, uint64_t n, uint64_t block_size, ui
             }
         }
         if (HIST) {
-            uint32_t *mine = sh.hist[warp];
-            for (uint32_t k = shift + tid; k < shift + tile_bytes; k += RLE_THREADS) atomicAdd(&mine[sh.stage[k]], 1u);
+            uint32_t *mine = sh.hist + (lane & (RLE_HIST_COPIES - 1));
+            const uint32_t end = shift + tile_bytes;
+            const uint32_t *stage32 = reinterpret_cast<const uint32_t *>(sh.stage);
+            for (uint32_t w = tid; w * 4 < end; w += RLE_THREADS) {
+                const uint32_t word = stage32[w];
+                const uint32_t c = w * 4;
+                if (c >= shift && c + 4 <= end) {
+                    atomicAdd(&mine[(word & 0xffu) * RLE_HIST_COPIES], 1u);
+                    atomicAdd(&mine[((word >> 8) & 0xffu) * RLE_HIST_COPIES], 1u);
+                    atomicAdd(&mine[((word >> 16) & 0xffu) * RLE_HIST_COPIES], 1u);
+                    atomicAdd(&mine[(word >> 24) * RLE_HIST_COPIES], 1u);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 4; k++)
+                        if (c + k >= shift && c + k < end) atomicAdd(&mine[((word >> (8 * k)) & 0xffu) * RLE_HIST_COPIES], 1u);
+                }
+            }
             __syncthreads();
             uint32_t sum = 0;
 #pragma unroll
-            for (int w = 0; w < RLE_THREADS / 32; w++) sum += sh.hist[w][tid];
+            for (int c = 0; c < RLE_HIST_COPIES; c++) sum += sh.hist[tid * RLE_HIST_COPIES + c];
             if (sum) atomicAdd(hist + b * 256 + tid, (unsigned long long)sum);
         }
     }
@@ -224,7 +281,6 @@ int launch_rle_encode(shafa_cuda_ctx *ctx, const uint8_t *d_in, uint64_t n, uint
     if (tpb > 0xffffffffull || total_tiles > 0xfffffff0ull) return set_error(ctx, SHAFA_LACK_OF_MEMORY, "rle_encode: too many tiles");
 
     static int occ[4] = {0, 0, 0, 0};
-    const size_t smem = sizeof(RleEncShared);
     const int variant = (d_rle ? 2 : 0) | (d_hist ? 1 : 0);
     void (*kern)(const uint8_t *, uint64_t, uint64_t, uint32_t, uint64_t, uint8_t *, uint64_t, unsigned long long *,
                  uint64_t *, uint64_t *, uint64_t *, uint32_t *, uint32_t *) =
@@ -233,8 +289,7 @@ int launch_rle_encode(shafa_cuda_ctx *ctx, const uint8_t *d_in, uint64_t n, uint
         : variant == 1 ? k_rle_encode<false, true>
                        : k_rle_encode<false, false>;
     if (!occ[variant]) {
-        SHAFA_CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        SHAFA_CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[variant], kern, RLE_THREADS, smem));
+        SHAFA_CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[variant], kern, RLE_THREADS, 0));
         if (occ[variant] < 1) occ[variant] = 1;
     }
     uint64_t *desc = (uint64_t *)scratch_get(ctx, SCR_DESC, 2 * (total_tiles + 1) * sizeof(uint64_t));
@@ -246,7 +301,7 @@ int launch_rle_encode(shafa_cuda_ctx *ctx, const uint8_t *d_in, uint64_t n, uint
     if (d_hist) SHAFA_CUDA_TRY(ctx, cudaMemsetAsync(d_hist, 0, nb * 256 * sizeof(uint64_t), ctx->stream));
     uint64_t grid = (uint64_t)ctx->sm_count * occ[variant];
     if (grid > total_tiles) grid = total_tiles;
-    SHAFA_LAUNCH(ctx, d_rle ? "rle_encode" : "rle_encode_sizes", kern, dim3((unsigned)grid), dim3(RLE_THREADS), smem,
+    SHAFA_LAUNCH(ctx, d_rle ? "rle_encode" : "rle_encode_sizes", kern, dim3((unsigned)grid), dim3(RLE_THREADS), 0,
                  d_in, n, block_size, (uint32_t)tpb, total_tiles, d_rle, rle_capacity, (unsigned long long *)d_hist,
                  blk_end, desc, desc + total_tiles + 1, counter, d_err);
     SHAFA_CHECK_LAUNCH(ctx);

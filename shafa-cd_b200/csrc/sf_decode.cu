@@ -93,6 +93,8 @@ struct DecPlan {
     uint32_t nb;
 };
 
+constexpr int DEC_STAGE = 16384;  // symbols of one sequence staged in shared memory before the coalesced copy-out
+
 struct DecShared {
     uint32_t words[DEC_SEQ_WORDS + DEC_WORDS_PAD];
     uint16_t lut[DEC_LUT_SIZE];
@@ -102,6 +104,11 @@ struct DecShared {
     uint32_t ends[DEC_THREADS];
     uint32_t scan[DEC_THREADS / 32 + 1];
     uint32_t block;
+};
+
+struct DecWriteShared {
+    DecShared d;
+    alignas(16) uint8_t stage[DEC_STAGE + 32];
 };
 
 // load tables + the sequence's payload words (big-endian) into shared memory
@@ -178,10 +185,9 @@ k_dec_sync(const uint8_t *__restrict__ payload, DecPlan plan, DecTablesGlobal g,
     const uint32_t sub_hi = sub_lo + DEC_SUB_BITS;
     const uint32_t stop = sub_hi < limit ? sub_hi : limit;
 
-    uint32_t start = 0, bad = 0;
-    DecSub r = dec_subsequence(sh.words, t, sub_lo + start, stop, nullptr, 0);
+    uint32_t start = 0;
+    DecSub r = dec_subsequence(sh.words, t, sub_lo + start, stop, DecNoEmit());
     uint32_t my_end = r.end > sub_hi ? r.end - sub_hi : 0;  // overshoot into the next sub-sequence
-    bad = r.bad;
     for (;;) {
         sh.ends[tid] = my_end;
         __syncthreads();
@@ -190,15 +196,13 @@ k_dec_sync(const uint8_t *__restrict__ payload, DecPlan plan, DecTablesGlobal g,
         if (!__syncthreads_or(changed)) break;
         if (changed) {
             start = want;
-            r = dec_subsequence(sh.words, t, sub_lo + start, stop, nullptr, 0);
+            r = dec_subsequence(sh.words, t, sub_lo + start, stop, DecNoEmit());
             my_end = r.end > sub_hi ? r.end - sub_hi : 0;
-            bad = r.bad;
         }
     }
     sub_info[seq * DEC_THREADS + tid] = sub_pack(start, r.count);
     if (tid == DEC_THREADS - 1) seq_end[seq] = my_end;
-    (void)bad;  // a speculative start may hit garbage; errors are judged in k_dec_write
-    (void)err;
+    (void)err;  // a speculative start may hit garbage; errors are judged in k_dec_write
 }
 
 // ---- phase 2: stitch sequences together -------------------------------------------------------
@@ -296,13 +300,17 @@ k_dec_scan(DecPlan plan, const uint32_t *__restrict__ seq_count, uint64_t *__res
 }
 
 // ---- phase 4: final decode + write --------------------------------------------------------------
+// Symbols of a sequence are staged in shared memory (co-aligned with their destination) and
+// copied out with 16-byte stores; a sequence that decodes to more than DEC_STAGE symbols
+// (codes of 1-2 bits) writes straight to global memory instead.
 __global__ void __launch_bounds__(DEC_THREADS)
 k_dec_write(const uint8_t *__restrict__ payload, DecPlan plan, DecTablesGlobal g,
             const uint16_t *__restrict__ sub_info, const uint64_t *__restrict__ seq_excl, uint8_t *__restrict__ out,
             uint32_t *__restrict__ err)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    DecShared &sh = *reinterpret_cast<DecShared *>(smem_raw);
+    DecWriteShared &ws = *reinterpret_cast<DecWriteShared *>(smem_raw);
+    DecShared &sh = ws.d;
     const unsigned tid = threadIdx.x;
     const uint64_t seq = blockIdx.x;
     if (tid == 0) sh.block = find_block(plan.seq0, plan.nb, seq);
@@ -321,14 +329,40 @@ k_dec_write(const uint8_t *__restrict__ payload, DecPlan plan, DecTablesGlobal g
     const uint32_t sub_hi = sub_lo + DEC_SUB_BITS;
     const uint32_t stop = sub_hi < limit ? sub_hi : limit;
     const uint64_t n = plan.n[b];
-    const uint64_t first = seq_excl[seq] + excl;  // index of this thread's first symbol inside the block
-    if (first >= n) return;                        // only padding garbage from here on
-    const uint64_t room = n - first;
-    uint8_t *dst = out + plan.out_off[b] + first;
-    const DecSub r = dec_subsequence(sh.words, t, sub_lo + sub_start(rec), stop, dst,
-                                     room > 0xffffffffull ? 0xffffffffu : (uint32_t)room);
+    const uint64_t seq_first = seq_excl[seq];  // index of this sequence's first symbol inside the block
+    if (seq_first >= n) return;                // only padding garbage from here on (uniform for the CTA)
+    const uint64_t seq_room = n - seq_first;   // symbols of this sequence that are real
+    const uint32_t seq_syms = seq_room < total ? (uint32_t)seq_room : total;
+    uint8_t *gdst = out + plan.out_off[b] + seq_first;
+    uint32_t bad = 0;
+    if (seq_syms <= (uint32_t)DEC_STAGE) {
+        const uint32_t shift = (uint32_t)((uintptr_t)gdst & 15u);
+        uint8_t *dst = ws.stage + shift + excl;
+        const uint32_t room = excl < seq_syms ? seq_syms - excl : 0u;
+        const DecSub r = dec_subsequence(sh.words, t, sub_lo + sub_start(rec), stop, [&](uint32_t i, uint32_t sym) {
+            if (i < room) dst[i] = (uint8_t)sym;
+        });
+        bad = r.bad && room;
+        __syncthreads();
+        uint8_t *ga = gdst - shift;  // 16-byte aligned
+        const uint32_t end = shift + seq_syms;
+        for (uint32_t c = tid * 16; c < end; c += DEC_THREADS * 16) {
+            if (c >= shift && c + 16 <= end) {
+                st_stream16(ga + c, *reinterpret_cast<const uint4 *>(ws.stage + c));
+            } else {
+                for (uint32_t k = (c > shift ? c : shift); k < c + 16 && k < end; k++) ga[k] = ws.stage[k];
+            }
+        }
+    } else {
+        uint8_t *dst = gdst + excl;
+        const uint32_t room = excl < seq_syms ? seq_syms - excl : 0u;
+        const DecSub r = dec_subsequence(sh.words, t, sub_lo + sub_start(rec), stop, [&](uint32_t i, uint32_t sym) {
+            if (i < room) dst[i] = (uint8_t)sym;
+        });
+        bad = r.bad && room;
+    }
     // a bad window only matters if it produced one of the n real symbols
-    if (r.bad) atomicOr(err, 16u);
+    if (bad) atomicOr(err, (uint32_t)ERR_BAD_WINDOW);
 }
 
 // ---- launcher -------------------------------------------------------------------------------------
@@ -387,10 +421,10 @@ int launch_sf_decode(shafa_cuda_ctx *ctx, const uint8_t *d_payload, const uint64
     uint32_t *seq_count = seq_end + nseq;
 
     static bool attr_done = false;
-    const size_t smem = sizeof(DecShared);
+    const size_t smem = sizeof(DecShared), smem_w = sizeof(DecWriteShared);
     if (!attr_done) {
         SHAFA_CUDA_TRY(ctx, cudaFuncSetAttribute(k_dec_sync, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        SHAFA_CUDA_TRY(ctx, cudaFuncSetAttribute(k_dec_write, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SHAFA_CUDA_TRY(ctx, cudaFuncSetAttribute(k_dec_write, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w));
         attr_done = true;
     }
     SHAFA_LAUNCH(ctx, "dec_tables", k_dec_tables, dim3((unsigned)nb), dim3(256), 0, d_len, d_code, g);
@@ -412,7 +446,7 @@ int launch_sf_decode(shafa_cuda_ctx *ctx, const uint8_t *d_payload, const uint64
     }
     SHAFA_LAUNCH(ctx, "dec_count", k_dec_count, dim3((unsigned)nseq), dim3(DEC_THREADS), 0, sub_info, seq_count);
     SHAFA_LAUNCH(ctx, "dec_scan", k_dec_scan, dim3((unsigned)nb), dim3(256), 0, plan, seq_count, seq_excl, d_err);
-    SHAFA_LAUNCH(ctx, "dec_write", k_dec_write, dim3((unsigned)nseq), dim3(DEC_THREADS), smem, d_payload, plan, g,
+    SHAFA_LAUNCH(ctx, "dec_write", k_dec_write, dim3((unsigned)nseq), dim3(DEC_THREADS), smem_w, d_payload, plan, g,
                  sub_info, seq_excl, d_sym, d_err);
     SHAFA_CHECK_LAUNCH(ctx);
     return SHAFA_SUCCESS;

@@ -70,6 +70,7 @@ static Bytes gen(std::mt19937 &rng, size_t n, int kind)
 }
 
 // ------------------------------------------------------------------ RLE encode emulation (rle_encode.cu)
+static uint32_t rng_noise = 0xa5a5a5a5u;
 static Bytes emu_rle_encode_block(const uint8_t *blk, uint64_t len)
 {
     Bytes out;
@@ -113,7 +114,34 @@ static Bytes emu_rle_encode_block(const uint8_t *blk, uint64_t len)
                 c0 = (uint32_t)(k % 255);
             }
             auto symf = [&](int j) -> uint32_t { return blk[tile_lo + p0 + j]; };
-            RleEmit em = rle_emit_thread(heads, p0, nvalid, c0, symf);
+            RleEmit em;
+            em.lit = em.tri = em.bytes = 0;
+            em.cnt[0] = em.cnt[1] = em.cnt[2] = em.cnt[3] = 0;
+            if (nvalid) {
+                // E bit of an absolute block position (0 at the block start and at/after the block end)
+                auto Ebit = [&](int64_t a) -> uint32_t { return (a > 0 && a < (int64_t)len && blk[a] == blk[a - 1]) ? 1u : 0u; };
+                uint32_t ewin = 0, z16 = 0;
+                for (int i = 6; i <= 26; i++) ewin |= Ebit((int64_t)tile_lo + p0 - 8 + i) << i;  // only bits 6..26 are specified
+                ewin |= 0xf800003fu & (rng_noise = rng_noise * 1664525u + 1013904223u);                                              // unspecified bits may hold anything
+                for (int j = 0; j < nvalid; j++) z16 |= (blk[tile_lo + p0 + j] == 0 ? 1u : 0u) << j;
+                const uint32_t valid16 = nvalid >= 16 ? 0xffffu : ((1u << nvalid) - 1u);
+                const uint64_t k0 = lh >= 0 ? (uint64_t)(p0 - lh) : (uint64_t)p0 + run_in;
+                const uint32_t e0 = (ewin >> 8) & 1u;
+                if (e0 && k0 + 15 >= 255) {
+                    em = rle_emit_thread(heads, p0, nvalid, (uint32_t)(k0 % 255), symf);
+                } else {
+                    const RleMasks m = rle_fast_masks(ewin, z16, valid16);
+                    em.lit = m.lit;
+                    em.tri = m.tri;
+                    for (int j = 0; j < 16; j++)
+                        if ((m.tri >> j) & 1) em.cnt[j >> 2] |= rle_run_remaining(heads, p0 + j) << (8 * (j & 3));
+                    em.bytes = __builtin_popcount(m.lit) + 3 * __builtin_popcount(m.tri);
+                    // the general rule must agree wherever the fast rule is used
+                    RleEmit ref = rle_emit_thread(heads, p0, nvalid, c0, symf);
+                    CHECK(ref.lit == em.lit && ref.tri == em.tri && ref.bytes == em.bytes && !memcmp(ref.cnt, em.cnt, sizeof ref.cnt),
+                          "fast masks differ from the general rule (tile %llu tid %u)", (unsigned long long)ti, tid);
+                }
+            }
             uint32_t w = rle_write_thread(em, stage.data() + o, symf);
             CHECK(w == em.bytes, "rle write/emit mismatch");
             o += w;
@@ -172,7 +200,7 @@ static Bytes emu_rle_decode(const Bytes &stream, const std::vector<uint64_t> &of
                     if (stream[pos + j] == 0) z |= 1u << (j - j0);
                 J0[tid] = j0;
                 N[tid] = j1 - j0;
-                maps[tid] = fsm_thread_map(z, j1 - j0);
+                maps[tid] = fsm_thread_map_fast(z, j1 - j0);
             }
             uint32_t excl = FSM_IDENTITY;
             for (int tid = 0; tid < 256; tid++) {
@@ -364,28 +392,28 @@ static Bytes emu_sf_encode(const Bytes &stream, uint64_t lo, uint64_t hi, const 
             uint64_t acc = 0;
             for (int j = 0; j < 16; j++) {
                 const uint32_t l = e[tid][j] & 31;
-                if (l) {
-                    acc |= (uint64_t)(e[tid][j] >> 5) << (64 - filled - l);
-                    filled += l;
-                    if (filled >= 32) {
-                        const uint32_t wv = (uint32_t)(acc >> 32);
-                        if (shared_first)
-                            stage[wrel] |= wv;
-                        else {
-                            CHECK(stage[wrel] == 0 && !plain[wrel], "plain store over a non-empty word");
-                            stage[wrel] = wv;
-                            plain[wrel] = 1;
-                        }
-                        shared_first = false;
-                        wrel++;
-                        acc <<= 32;
-                        filled -= 32;
+                acc = (acc << l) | (uint64_t)(e[tid][j] >> 5);
+                filled += l;
+                if (filled >= 32) {
+                    const uint32_t wv = (uint32_t)(acc >> (filled - 32));
+                    if (shared_first)
+                        stage[wrel] |= wv;
+                    else {
+                        CHECK(stage[wrel] == 0 && !plain[wrel], "plain store over a non-empty word");
+                        stage[wrel] = wv;
+                        plain[wrel] = 1;
                     }
+                    shared_first = false;
+                    wrel++;
+                    filled -= 32;
                 }
             }
-            if (filled && (acc >> 32)) {
-                CHECK(!plain[wrel], "atomicOr onto a plainly stored word");
-                stage[wrel] |= (uint32_t)(acc >> 32);
+            if (filled) {
+                const uint32_t wv = (uint32_t)acc << (32 - filled);
+                if (wv) {
+                    CHECK(!plain[wrel], "atomicOr onto a plainly stored word");
+                    stage[wrel] |= wv;
+                }
             }
             excl += bits[tid];
         }
@@ -512,7 +540,7 @@ static Bytes emu_sf_decode(const Bytes &payload, uint64_t n, const uint8_t *len,
         auto run = [&](int tid) {
             const uint32_t sub_lo = tid * DEC_SUB_BITS, sub_hi = sub_lo + DEC_SUB_BITS;
             const uint32_t stop = std::min(sub_hi, limit);
-            DecSub r = dec_subsequence(words.data(), t, sub_lo + st[tid], stop, nullptr, 0);
+            DecSub r = dec_subsequence(words.data(), t, sub_lo + st[tid], stop, DecNoEmit());
             en[tid] = r.end > sub_hi ? r.end - sub_hi : 0;
             cn[tid] = r.count;
         };
@@ -551,7 +579,7 @@ static Bytes emu_sf_decode(const Bytes &payload, uint64_t n, const uint8_t *len,
                 const uint64_t gi = seq * DEC_THREADS + k;
                 if (start[gi] == cur) break;
                 const uint32_t sub_lo = k * DEC_SUB_BITS, sub_hi = sub_lo + DEC_SUB_BITS;
-                DecSub r = dec_subsequence(words.data(), t, sub_lo + cur, std::min(sub_hi, limit), nullptr, 0);
+                DecSub r = dec_subsequence(words.data(), t, sub_lo + cur, std::min(sub_hi, limit), DecNoEmit());
                 start[gi] = (uint16_t)cur;
                 count[gi] = (uint16_t)r.count;
                 touched = true;
@@ -576,8 +604,10 @@ static Bytes emu_sf_decode(const Bytes &payload, uint64_t n, const uint8_t *len,
             const uint64_t gi = seq * DEC_THREADS + tid;
             if (first < n) {
                 const uint32_t sub_lo = tid * DEC_SUB_BITS, sub_hi = sub_lo + DEC_SUB_BITS;
-                DecSub r = dec_subsequence(words.data(), t, sub_lo + start[gi], std::min(sub_hi, limit), out.data() + first,
-                                           (uint32_t)std::min<uint64_t>(n - first, 0xffffffffu));
+                const uint64_t room = n - first;
+                uint8_t *dst = out.data() + first;
+                DecSub r = dec_subsequence(words.data(), t, sub_lo + start[gi], std::min(sub_hi, limit),
+                                           [&](uint32_t i, uint32_t sym) { if (i < room) dst[i] = (uint8_t)sym; });
                 CHECK(r.count == count[gi], "final decode count differs from the recorded count");
                 if (r.bad) bad = true;
             }
