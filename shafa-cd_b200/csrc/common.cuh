@@ -105,23 +105,59 @@ __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t *smem, 
 // the nearest one that has published an inclusive prefix and returns the sum of
 // everything in between (= the exclusive prefix of `tile`).  Tiles before
 // `first` count as an inclusive prefix of 0.
+//
+// The prefix frontier of a chain advances by at most one look-back window per L2
+// round trip, so the window is LB_WINDOW = 128 descriptors (4 per lane), not 32:
+// with 4 KiB tiles a 32-wide window capped a file-wide chain at ~250 GB/s.
+constexpr int LB_PER_LANE = 4;
+constexpr int LB_WINDOW = 32 * LB_PER_LANE;
+
 __device__ __forceinline__ uint64_t lookback_read(const uint64_t *desc, int64_t tile, int64_t first)
 {
     const unsigned lane = lane_id();
     uint64_t excl = 0;
     int64_t pos = tile - 1;
     for (;;) {
-        const int64_t idx = pos - (int64_t)lane;
-        uint64_t d = desc_pack(DESC_PREFIX, 0);
-        if (idx >= first) d = desc_load(desc + idx);
-        while (__any_sync(FULL, desc_state(d) == DESC_INVALID)) {
-            if (idx >= first && desc_state(d) == DESC_INVALID) d = desc_load(desc + idx);
+        // lane l looks at pos - l - 32*j: j = 0 is the nearest group of 32 predecessors
+        uint64_t d[LB_PER_LANE];
+        bool pending;
+        unsigned spins = 0;
+        do {
+            pending = false;
+#pragma unroll
+            for (int j = 0; j < LB_PER_LANE; j++) {
+                const int64_t idx = pos - (int64_t)lane - 32 * j;
+                d[j] = (idx >= first) ? desc_load(desc + idx) : desc_pack(DESC_PREFIX, 0);
+            }
+            // only descriptors nearer than the first published prefix have to be valid
+#pragma unroll
+            for (int j = 0; j < LB_PER_LANE; j++) {
+                const unsigned inv = __ballot_sync(FULL, desc_state(d[j]) == DESC_INVALID);
+                const unsigned pfx = __ballot_sync(FULL, desc_state(d[j]) == DESC_PREFIX);
+                if (pfx) {
+                    const unsigned nearer = (1u << (__ffs(pfx) - 1)) - 1u;  // lanes before the first prefix
+                    if (inv & nearer) pending = true;
+                    break;
+                }
+                if (inv) {
+                    pending = true;
+                    break;
+                }
+            }
+            if (pending && ++spins > 2) __nanosleep(40);
+        } while (pending);
+        bool done = false;
+#pragma unroll
+        for (int j = 0; j < LB_PER_LANE; j++) {
+            if (!done) {
+                const unsigned pm = __ballot_sync(FULL, desc_state(d[j]) == DESC_PREFIX);
+                const unsigned upto = pm ? (unsigned)(__ffs(pm) - 1) : 31u;  // lanes 0..upto contribute
+                excl += warp_sum64(lane <= upto ? desc_value(d[j]) : 0ull);
+                if (pm) done = true;
+            }
         }
-        const unsigned pm = __ballot_sync(FULL, desc_state(d) == DESC_PREFIX);
-        const unsigned upto = pm ? (unsigned)(__ffs(pm) - 1) : 31u;  // lanes 0..upto contribute
-        excl += warp_sum64(lane <= upto ? desc_value(d) : 0ull);
-        if (pm) break;
-        pos -= 32;
+        if (done) break;
+        pos -= LB_WINDOW;
     }
     return excl;
 }

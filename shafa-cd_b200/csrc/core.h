@@ -58,8 +58,10 @@ SHAFA_HD uint32_t bswap32(uint32_t x)
 // block end set, and must be readable up to bit p+255 for any queried p.
 // =============================================================================
 
-constexpr int RLE_TILE = 4096;          // bytes per tile
-constexpr int RLE_ITEMS = 16;           // bytes per thread
+constexpr int RLE_ITEMS = 16;           // bytes per 16-byte group (one vector load)
+constexpr int RLE_VECS = 4;             // groups per thread of the encoder: 64 contiguous bytes
+constexpr int RLE_THREADS = 256;
+constexpr int RLE_TILE = RLE_THREADS * RLE_ITEMS * RLE_VECS;  // 16 KiB per tile
 constexpr int RLE_HALO = 288;           // look-ahead positions kept after the tile
 constexpr int RLE_HEAD_WORDS = (RLE_TILE + RLE_HALO) / 32;
 
@@ -152,6 +154,33 @@ SHAFA_HD RleMasks rle_fast_masks(uint32_t ewin, uint32_t z16, uint32_t valid16)
     return m;
 }
 
+// The same rule on 64 positions at once (one thread of the 16 KiB-tile kernel).
+//   E      bit p = E[p0 + p]
+//   before bit 0 = E[p0 - 2], bit 1 = E[p0 - 1]
+//   after  bit 0 = E[p0 + 64], bit 1 = E[p0 + 65], bit 2 = E[p0 + 66]
+struct RleMasks64 {
+    uint64_t lit, tri;
+};
+SHAFA_HD RleMasks64 rle_fast_masks64(uint64_t E, uint32_t before, uint32_t after, uint64_t Z, uint64_t valid)
+{
+    const uint64_t a0 = after & 1u, a1 = (after >> 1) & 1u, a2 = (after >> 2) & 1u;
+    const uint64_t m2 = before & 1u, m1 = (before >> 1) & 1u;
+    const uint64_t E1 = (E >> 1) | (a0 << 63);               // E[p+1]
+    const uint64_t E2 = (E >> 2) | (a0 << 62) | (a1 << 63);  // E[p+2]
+    const uint64_t T = E & E1 & E2;                          // first of three consecutive continuations
+    const uint64_t Tm1 = m1 & E & (E >> 1) & 1ull;           // T[-1]
+    const uint64_t Tm2 = m2 & m1 & E & 1ull;                 // T[-2]
+    const uint64_t T64 = a0 & a1 & a2;                       // T[64]
+    const uint64_t Lc = T | (T << 1) | Tm1 | (T << 2) | (Tm1 << 1) | Tm2;
+    const uint64_t Lc64 = T64 | (T >> 63) | ((T >> 62) & 1ull);
+    const uint64_t H = ~E;
+    const uint64_t LH = H & ((Lc >> 1) | (Lc64 << 63));
+    RleMasks64 m;
+    m.tri = (LH | (H & Z)) & valid;
+    m.lit = ~Z & ~Lc & ~LH & valid;
+    return m;
+}
+
 // Write this thread's emitted bytes to dst (dst points at the thread's first
 // output byte).  Returns bytes written (== e.bytes).
 template <typename SymFn>
@@ -222,6 +251,64 @@ SHAFA_HD uint32_t fsm_thread_map_fast(uint32_t zmask, int n)
     return fsm_thread_map(zmask, n);
 }
 
+// 64-byte form used by the 16 KiB-tile decoder.  Only the escape bytes matter: from a
+// position in state 0 every non-zero byte is a literal and the next zero byte is an escape
+// that swallows the two bytes after it.  Z bit q = (byte q == 0), bits >= n clear.
+SHAFA_HD int ctz64(uint64_t x)
+{
+#if defined(__CUDA_ARCH__)
+    return __ffsll((long long)x) - 1;
+#else
+    return __builtin_ctzll(x);
+#endif
+}
+struct FsmWalk {
+    uint64_t esc;   // positions of the escape bytes met in state 0
+    uint32_t exit;  // state after the n bytes
+};
+SHAFA_HD FsmWalk fsm_walk64(uint64_t Z, int n, uint32_t entry)
+{
+    FsmWalk w;
+    w.esc = 0;
+    const int cur = entry == 0 ? 0 : (entry == 1 ? 2 : 1);  // first position in state 0
+    if (cur > n) {  // the pending triple is not even finished inside these n bytes
+        w.exit = (entry == 1 && n == 0) ? 1u : 2u;
+        return w;
+    }
+    w.exit = 0;
+    uint64_t zz = (cur >= 64) ? 0ull : ((Z >> cur) << cur);
+    while (zz) {
+        const int zp = ctz64(zz);
+        w.esc |= 1ull << zp;
+        const int nxt = zp + 3;
+        if (nxt > n) {
+            w.exit = (nxt - n == 2) ? 1u : 2u;  // escape was the last byte: sym pending; second to last: count pending
+            break;
+        }
+        zz = (nxt >= 64) ? 0ull : ((zz >> nxt) << nxt);
+    }
+    return w;
+}
+SHAFA_HD uint32_t fsm_map64(uint64_t Z, int n)
+{
+    if (Z == 0 && n >= 2) return 0u;  // no escape at all: every entry state is back in state 0 and stays there
+    return fsm_walk64(Z, n, 0).exit | (fsm_walk64(Z, n, 1).exit << 2) | (fsm_walk64(Z, n, 2).exit << 4);
+}
+// positions that emit: lit = literal bytes, run = count bytes of triples (the run's byte is the one before)
+struct RleDecMasks {
+    uint64_t lit, run;
+};
+SHAFA_HD RleDecMasks rle_dec_masks64(uint64_t esc, int n, uint32_t entry)
+{
+    const uint64_t maskn = (n >= 64) ? ~0ull : ((1ull << n) - 1ull);
+    const uint64_t pre = entry == 1 ? 3ull : (entry == 2 ? 1ull : 0ull);      // bytes owed to a triple opened earlier
+    const uint64_t prerun = entry == 1 ? 2ull : (entry == 2 ? 1ull : 0ull);   // where that triple's count byte sits
+    RleDecMasks m;
+    m.run = ((esc << 2) | prerun) & maskn;
+    m.lit = ~(esc | (esc << 1) | (esc << 2) | pre) & maskn;
+    return m;
+}
+
 // Walk the thread's n valid bytes from entry state `state`; `byte(q)` returns
 // byte q, prev = the byte just before byte 0 (needed when entering in state 2).
 // emit(len, sym) is called once per record, in order.  Returns the exit state.
@@ -285,6 +372,11 @@ SHAFA_HD int sf_split(const uint32_t *P, int lo, int hi)
 // =============================================================================
 
 constexpr int ENC_SHORT_MAX = 26;                          // fast path: code + 5-bit length in one word
+constexpr int ENC_THREADS = 256;
+constexpr int ENC_VECS = 4;                                // 16-byte vectors per thread, contiguous
+constexpr int ENC_ITEMS = 16 * ENC_VECS;                   // 64 symbols per thread
+constexpr int ENC_TILE = ENC_THREADS * ENC_ITEMS;          // 16 KiB of symbols per tile
+constexpr int ENC_STAGE_WORDS = 6144;                      // staging window: 24 KiB of the tile's bit range
 SHAFA_HD uint32_t enc_entry(uint64_t code, uint32_t len) { return ((uint32_t)code << 5) | len; }
 
 // 64-bit window starting at bit `q` of a big-endian word array
@@ -351,49 +443,98 @@ struct DecSub {
     uint32_t bad;    // a window matched no code
 };
 
-// Decode from bit `start` until reaching `stop` (both relative to the sequence
-// words); emit(i, sym) is called for the i-th symbol.  The next >= 32 bits are
-// kept left-aligned in a 64-bit register and topped up one word at a time, so a
-// symbol costs one table lookup and a shift; codes longer than the first-level
-// table re-read an exact 64-bit window.
-template <typename Emit>
-SHAFA_HD DecSub dec_subsequence(const uint32_t *words, const DecTables &t, uint32_t start, uint32_t stop, Emit emit)
+// ---- sequence-level decoding -------------------------------------------------------------------
+// The sequence's payload is kept as an array of overlapping pairs: pairs[i] = (w[i] << 32) | w[i+1]
+// (big-endian words), so the 32 bits starting at any bit q are one 64-bit load and a funnel shift and
+// there is no refill branch to diverge a warp.
+SHAFA_HD uint32_t dec_window32(const uint64_t *pairs, uint32_t q)
+{
+    const uint64_t pr = pairs[q >> 5];
+    return (uint32_t)((pr << (q & 31u)) >> 32);
+}
+SHAFA_HD uint64_t dec_window64(const uint64_t *pairs, uint32_t q)
+{
+    const uint32_t i = q >> 5, sh = q & 31u;
+    const uint64_t hi = pairs[i];
+    return sh ? ((hi << sh) | ((pairs[i + 1] & 0xffffffffull) >> (32 - sh))) : hi;  // low word of pairs[i+1] is w[i+2]
+}
+
+// Tables of one block as seen by a decoding thread (shared memory on the GPU).
+//   lut1[4096]  (sym << 8) | len, len 1..12; 0 = no code; 0xFF = longer than 12 bits
+//   lut2[4096]  (nsym << 8) | bits: how many whole codes fit in the 12-bit window and their total length; 0 = use lut1
+struct DecView {
+    const uint64_t *pairs;
+    const uint16_t *lut1;
+    const uint16_t *lut2;
+    const uint64_t *sleft;
+    const uint8_t *slen;
+    const uint8_t *ssym;
+};
+
+// one symbol at bit q: returns its length (>= 1), *sym; *bad is set if the bits are no code
+template <typename V>
+SHAFA_HD uint32_t dec_one(const V &t, uint32_t q, uint32_t *sym, uint32_t *bad)
+{
+    const uint32_t e = t.lut1[dec_window32(t.pairs, q) >> (32 - DEC_LUT_BITS)];
+    uint32_t l = e & 0xFFu;
+    *sym = e >> 8;
+    if (l - 1u >= (uint32_t)DEC_LUT_BITS) {  // long code or no code: exact 64-bit window + sorted search
+        DecTables dt;
+        dt.lut = t.lut1;
+        dt.sleft = t.sleft;
+        dt.slen = t.slen;
+        dt.ssym = t.ssym;
+        l = dec_symbol(dt, dec_window64(t.pairs, q), sym);
+        if (l == 0) {
+            *bad = 1;
+            l = 1;
+        }
+    }
+    return l;
+}
+
+// Count the symbols that START in [start, stop) and find where decoding leaves the range.
+// While a whole 12-bit window lies before `stop`, all codes inside it are taken at once (lut2).
+template <typename V>
+SHAFA_HD DecSub dec_count_subsequence(const V &t, uint32_t start, uint32_t stop)
 {
     DecSub r;
     r.count = 0;
     r.bad = 0;
     uint32_t q = start;
-    if (q < stop) {
-        uint32_t wi = q >> 5;
-        uint64_t buf = (((uint64_t)words[wi] << 32) | (uint64_t)words[wi + 1]) << (q & 31u);
-        uint32_t avail = 64u - (q & 31u);
-        wi += 2;
-        while (q < stop) {
-            if (avail < 32u) {
-                buf |= (uint64_t)words[wi++] << (32u - avail);
-                avail += 32u;
-            }
-            const uint32_t e = t.lut[buf >> (64 - DEC_LUT_BITS)];
-            uint32_t l = e & 0xFFu, sym = e >> 8;
-            if (l - 1u < (uint32_t)DEC_LUT_BITS) {
-                buf <<= l;
-                avail -= l;
-            } else {  // long code or no code: exact window, then rebuild the buffer
-                l = dec_symbol(t, bit_window(words, q), &sym);
-                if (l == 0) {
-                    r.bad = 1;
-                    l = 1;
-                }
-                const uint32_t nq = q + l;
-                wi = nq >> 5;
-                buf = (((uint64_t)words[wi] << 32) | (uint64_t)words[wi + 1]) << (nq & 31u);
-                avail = 64u - (nq & 31u);
-                wi += 2;
-            }
-            emit(r.count, sym);
+    while (q + (uint32_t)DEC_LUT_BITS <= stop) {
+        const uint32_t e2 = t.lut2[dec_window32(t.pairs, q) >> (32 - DEC_LUT_BITS)];
+        if (e2) {
+            q += e2 & 0xFFu;
+            r.count += e2 >> 8;
+        } else {
+            uint32_t sym;
+            q += dec_one(t, q, &sym, &r.bad);
             r.count++;
-            q += l;
         }
+    }
+    while (q < stop) {
+        uint32_t sym;
+        q += dec_one(t, q, &sym, &r.bad);
+        r.count++;
+    }
+    r.end = q;
+    return r;
+}
+
+// Decode the symbols that start in [start, stop); emit(i, sym) for the i-th one.
+template <typename V, typename Emit>
+SHAFA_HD DecSub dec_emit_subsequence(const V &t, uint32_t start, uint32_t stop, Emit emit)
+{
+    DecSub r;
+    r.count = 0;
+    r.bad = 0;
+    uint32_t q = start;
+    while (q < stop) {
+        uint32_t sym;
+        q += dec_one(t, q, &sym, &r.bad);
+        emit(r.count, sym);
+        r.count++;
     }
     r.end = q;
     return r;
@@ -402,5 +543,18 @@ SHAFA_HD DecSub dec_subsequence(const uint32_t *words, const DecTables &t, uint3
 struct DecNoEmit {
     SHAFA_HD void operator()(uint32_t, uint32_t) const {}
 };
+
+// lut2 entry for the 12-bit window value e, derived from lut1
+SHAFA_HD uint16_t dec_lut2_entry(const uint16_t *lut1, uint32_t e)
+{
+    uint32_t pos = 0, n = 0;
+    while (pos < (uint32_t)DEC_LUT_BITS) {
+        const uint32_t l = lut1[(e << pos) & (DEC_LUT_SIZE - 1)] & 0xFFu;  // remaining bits, zero padded
+        if (l - 1u >= (uint32_t)DEC_LUT_BITS || pos + l > (uint32_t)DEC_LUT_BITS) break;  // must fit entirely
+        pos += l;
+        n++;
+    }
+    return (uint16_t)(n ? ((n << 8) | pos) : 0);
+}
 
 }  // namespace shafa

@@ -3,21 +3,18 @@
 // compacted back to back (= the decoded file, d.c:218,613).  Algorithmic bytes:
 // R read + N written.
 //
-// The byte-serial parser of the reference becomes a 3-state automaton
-// (core.h): each thread summarises its 16 bytes as an entry->exit state map,
-// maps are composed by a CTA scan (composition = one lookup in a 4 KiB table),
-// and chain #1 (decoupled look-back inside the block) carries the state across
-// tiles -- tiles whose map is constant (almost all) publish their exit state
-// without waiting.  With the entry state known every thread knows its records
-// {length, byte}; a CTA scan plus chain #2 (over all tiles of the file) places
-// the tile in the output.  Two ways to materialise a tile:
-//   * small expansion (<= 16 KiB, the literal-heavy case): every thread writes
-//     its own bytes into a staging buffer that is co-aligned with the
-//     destination, then the CTA copies it out with 16-byte stores;
-//   * large expansion (long runs): the records go to a list in shared memory and
-//     the CTA expands it cooperatively, one aligned 16-byte chunk per thread per
-//     step (binary search for the chunk's first record), so long runs become
-//     full-width stores and no thread ever owns a 255-byte memset.
+// The byte-serial parser of the reference is a 3-state automaton (core.h).  A
+// thread owns 64 contiguous RLE bytes; only escape bytes (0x00 met in state 0)
+// change the state, so its entry->exit map and its emission masks come from
+// walking the zero-byte bitmask, not the bytes.  Maps are composed by a CTA scan
+// (composition = one lookup in a 4 KiB table) and chain #1 (decoupled look-back
+// inside the block) carries the state across 16 KiB tiles -- tiles whose map is
+// constant (almost all) publish their exit state without waiting.  A CTA scan of
+// output sizes plus chain #2 (over all tiles of the file) places the tile in the
+// output.  The tile's output is materialised in a 32 KiB staging buffer that is
+// co-aligned with the destination and copied out with 16-byte stores; a tile
+// that expands to more than one buffer (long runs) goes through it window by
+// window, every thread writing only the part of its output inside the window.
 #include "common.cuh"
 #include "core.h"
 #include "internal.h"
@@ -26,18 +23,14 @@ namespace shafa {
 
 constexpr int RLD_THREADS = 256;
 constexpr int RLD_WARPS = RLD_THREADS / 32;
-constexpr int RLD_TILE = RLD_THREADS * RLE_ITEMS;          // 4096 RLE bytes
-constexpr int RLD_STAGE = 16384;                           // staged expansion limit (bytes)
+constexpr int RLD_VECS = 4;
+constexpr int RLD_PER_THREAD = 16 * RLD_VECS;             // 64 RLE bytes per thread
+constexpr int RLD_TILE = RLD_THREADS * RLD_PER_THREAD;    // 16 KiB of RLE bytes per tile
+constexpr int RLD_STAGE = 32768;                          // staging window (bytes of output)
 constexpr uint64_t RLE_BLOCK_CAP = 67108864ull + 1024ull;  // d.c:135,163
 
 struct RleDecShared {
-    union {
-        struct {
-            uint32_t rec_start[RLD_TILE + 1];
-            uint8_t rec_sym[RLD_TILE];
-        } list;
-        alignas(16) uint8_t stage[RLD_STAGE + 32];
-    } u;
+    alignas(16) uint8_t stage[RLD_STAGE + 16];
     uint8_t compose[64 * 64];  // compose[a*64+b] = first a, then b
     uint32_t scan[RLD_WARPS + 1];
     uint32_t wmap[RLD_WARPS];
@@ -49,7 +42,48 @@ struct RleDecShared {
     uint32_t block;
 };
 
-__global__ void __launch_bounds__(RLD_THREADS)
+__device__ __forceinline__ uint4 rld_ld16(const void *p)
+{
+    uint4 v;  // default L1 policy: the four vectors of a thread share sectors
+    asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+
+// `len` copies of `sym` at dst (shared memory): bytes up to a 4-byte boundary, words, tail bytes
+__device__ __noinline__ void rld_fill(uint8_t *dst, uint32_t sym, uint32_t len)
+{
+    if (len < 8) {
+        for (uint32_t k = 0; k < len; k++) dst[k] = (uint8_t)sym;
+        return;
+    }
+    const uint32_t head = (4u - ((uint32_t)(uintptr_t)dst & 3u)) & 3u;
+    for (uint32_t k = 0; k < head; k++) dst[k] = (uint8_t)sym;
+    dst += head;
+    len -= head;
+    const uint32_t w = sym * 0x01010101u;
+    uint32_t *d32 = reinterpret_cast<uint32_t *>(dst);
+    const uint32_t nw = len >> 2;
+    for (uint32_t k = 0; k < nw; k++) d32[k] = w;
+    for (uint32_t k = nw * 4; k < len; k++) dst[k] = (uint8_t)sym;
+}
+
+// one output piece [o, o+len) of byte `sym` (tile-relative offsets), clipped to the window [wlo, whi)
+template <bool CLIP>
+__device__ __forceinline__ void rld_emit(uint8_t *stage_base, uint32_t wlo, uint32_t whi, uint32_t o, uint32_t len, uint32_t sym)
+{
+    if (!CLIP) {
+        if (len == 1)
+            stage_base[o] = (uint8_t)sym;
+        else
+            rld_fill(stage_base + o, sym, len);
+    } else {
+        const uint32_t lo = o > wlo ? o : wlo;
+        const uint32_t hi = (o + len < whi) ? (o + len) : whi;
+        if (lo < hi) rld_fill(stage_base + lo, sym, hi - lo);
+    }
+}
+
+__global__ void __launch_bounds__(RLD_THREADS, 3)
 k_rle_decode(const uint8_t *__restrict__ in, const uint64_t *__restrict__ off, const uint64_t *__restrict__ tile0,
              uint32_t nb, uint8_t *__restrict__ out, uint64_t out_capacity, uint64_t *__restrict__ blk_end,
              uint64_t *__restrict__ desc_state_chain, uint64_t *__restrict__ desc_out, uint32_t *__restrict__ counter,
@@ -76,21 +110,29 @@ k_rle_decode(const uint8_t *__restrict__ in, const uint64_t *__restrict__ off, c
         const bool is_first = (t == first_tile);
         const bool is_last = (t + 1 == tile0[b + 1]);
         const uint64_t base = (lo / RLD_TILE + (t - first_tile)) * RLD_TILE;
-        const uint64_t pos = base + (uint64_t)tid * 16;
+        const uint64_t pos = base + (uint64_t)tid * RLD_PER_THREAD;
 
-        // ---- load, valid range [j0, j1) of this thread ----
-        uint4 v = make_uint4(0, 0, 0, 0);
+        // ---- load; valid range [j0, j1) of this thread's 64 bytes ----
         int j0 = 0, j1 = 0;
-        if (pos + 16 > lo && pos < hi) {
-            v = ld_stream16(in + pos);
+        if (pos + RLD_PER_THREAD > lo && pos < hi) {
             j0 = (lo > pos) ? (int)(lo - pos) : 0;
-            j1 = (hi < pos + 16) ? (int)(hi - pos) : 16;
+            j1 = (hi < pos + RLD_PER_THREAD) ? (int)(hi - pos) : RLD_PER_THREAD;
         }
         const int n = j1 - j0;
-        const uint32_t zmask = (zero_mask16(v) >> j0) & ((n >= 16) ? 0xffffu : ((1u << n) - 1u));
+        const bool full = (n == RLD_PER_THREAD);
+        uint4 v[RLD_VECS];
+        uint64_t Z = 0;  // bit q = (valid byte q == 0), relative to j0
+#pragma unroll
+        for (int c = 0; c < RLD_VECS; c++) {
+            v[c] = make_uint4(0, 0, 0, 0);
+            if (16 * c < j1 && 16 * c + 16 > j0) v[c] = rld_ld16(in + pos + 16 * c);
+            Z |= (uint64_t)zero_mask16(v[c]) << (16 * c);
+        }
+        Z = (j0 < 64) ? (Z >> j0) : 0ull;
+        Z &= (n >= 64) ? ~0ull : ((1ull << n) - 1ull);
 
         // ---- state maps: thread -> warp -> CTA (composition through the table) ----
-        uint32_t incl = fsm_thread_map_fast(zmask, n);
+        uint32_t incl = fsm_map64(Z, n);
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             const uint32_t o = __shfl_up_sync(FULL, incl, d);
@@ -99,6 +141,9 @@ k_rle_decode(const uint8_t *__restrict__ in, const uint64_t *__restrict__ off, c
         if (lane == 31) sh.wmap[warp] = incl;
         uint32_t excl_map = __shfl_up_sync(FULL, incl, 1);
         if (lane == 0) excl_map = FSM_IDENTITY;
+        // byte just before this thread's first valid byte (needed when a count byte is my first byte)
+        uint32_t prevb = __shfl_up_sync(FULL, v[RLD_VECS - 1].w >> 24, 1);
+        if ((lane == 0 || !full) && n > 0 && pos + j0 > lo) prevb = in[pos + j0 - 1];
         __syncthreads();
 
         // ---- warp 0: scan of the warp maps, then chain #1 (automaton state at the tile start) ----
@@ -159,24 +204,20 @@ k_rle_decode(const uint8_t *__restrict__ in, const uint64_t *__restrict__ off, c
         const uint32_t tile_entry = sh.entry;
         const uint32_t my_entry = fsm_apply(excl_map, fsm_apply(sh.wexcl[warp], tile_entry));
 
-        // ---- records of this thread: count + output bytes ----
-        const bool all_literal = (n == 16) && (zmask == 0) && (my_entry == 0);
-        uint32_t prevb = 0;
-        if (n > 0 && my_entry == 2 && pos + j0 > lo) prevb = in[pos + j0 - 1];
-        auto bytef = [&](int q) -> uint32_t { return byte_of(v, j0 + q); };
-        uint32_t recs = 16, obytes = 16;
-        if (!all_literal) {
-            recs = 0;
-            obytes = 0;
-            rle_parse_thread(my_entry, n, prevb, bytef, [&](uint32_t len, uint32_t) {
-                recs++;
-                obytes += len;
-            });
+        // ---- what do my bytes emit: literal positions, count-byte positions, output size ----
+        const RleDecMasks m = rle_dec_masks64(fsm_walk64(Z, n, my_entry).esc, n, my_entry);
+        uint32_t obytes = (uint32_t)__popcll(m.lit);
+        {
+            uint64_t rb = m.run;
+            while (rb) {  // sparse: one iteration per triple
+                const int q = ctz64(rb);
+                rb &= rb - 1;
+                const uint32_t cnt = in[pos + j0 + q];  // L1 hit: the line was just loaded
+                obytes += cnt ? cnt : 1u;               // d.c:179-184: count 0 -> one copy
+            }
         }
-        uint32_t packed_total;
-        const uint32_t packed_excl = block_excl_scan<RLD_THREADS>(obytes | (recs << 19), sh.scan, &packed_total);
-        const uint32_t tile_out = packed_total & ((1u << 19) - 1u);
-        const uint32_t tile_recs = packed_total >> 19;
+        uint32_t tile_out;
+        const uint32_t my_out = block_excl_scan<RLD_THREADS>(obytes, sh.scan, &tile_out);
         if (warp == 0) {
             const uint64_t pfx = lookback_sum(desc_out, (int64_t)t, 0, tile_out);
             if (lane == 0) sh.out_prefix = pfx;
@@ -192,92 +233,76 @@ k_rle_decode(const uint8_t *__restrict__ in, const uint64_t *__restrict__ off, c
             continue;
         }
         if (tile_out == 0) continue;
-        const uint32_t my_out = packed_excl & ((1u << 19) - 1u);
 
-        if (tile_out <= (uint32_t)RLD_STAGE) {
-            // ---- staged expansion: every thread writes its own bytes ----
-            const uint32_t shift = (uint32_t)(out0 & 15u);
-            uint8_t *dst = sh.u.stage + shift + my_out;
-            if (all_literal) {
+        // ---- materialise the tile's output, one staging window at a time ----
+        const uint32_t shift = (uint32_t)(out0 & 15u);
+        uint8_t *const gbase = out + (out0 - shift);  // 16-byte aligned; stage index s <-> gbase[s] in window 0
+        const uint32_t span = shift + tile_out;       // window k covers stage-space [k*RLD_STAGE, (k+1)*RLD_STAGE) of this span
+        const bool single = span <= (uint32_t)RLD_STAGE;
+        for (uint32_t w0 = 0; w0 < span; w0 += RLD_STAGE) {
+            const uint32_t w1 = (span - w0 < (uint32_t)RLD_STAGE) ? span : (w0 + RLD_STAGE);
+            // my output occupies span-space [a, a+obytes)
+            const uint32_t a = shift + my_out;
+            if (obytes && a < w1 && a + obytes > w0) {
+                uint8_t *sb = sh.stage - w0;  // sb[x] is span-space position x
+                uint32_t o = a;
+                if (full && single) {
 #pragma unroll
-                for (int j = 0; j < 16; j++) dst[j] = (uint8_t)byte_of(v, j);
-            } else {
-                rle_parse_thread(my_entry, n, prevb, bytef, [&](uint32_t len, uint32_t sym) {
-                    for (uint32_t k = 0; k < len; k++) dst[k] = (uint8_t)sym;
-                    dst += len;
-                });
-            }
-            __syncthreads();
-            uint8_t *g = out + (out0 - shift);  // 16-byte aligned
-            const uint32_t end = shift + tile_out;
-            for (uint32_t c = tid * 16; c < end; c += RLD_THREADS * 16) {
-                if (c >= shift && c + 16 <= end) {
-                    st_stream16(g + c, *reinterpret_cast<const uint4 *>(sh.u.stage + c));
-                } else {
-                    for (uint32_t k = (c > shift ? c : shift); k < c + 16 && k < end; k++) g[k] = sh.u.stage[k];
-                }
-            }
-        } else {
-            // ---- large expansion: record list + cooperative fill ----
-            {
-                uint32_t o = my_out;
-                uint32_t r = packed_excl >> 19;
-                if (all_literal) {
+                    for (int c = 0; c < RLD_VECS; c++) {
+                        const uint32_t l16 = (uint32_t)(m.lit >> (16 * c)) & 0xffffu, r16 = (uint32_t)(m.run >> (16 * c)) & 0xffffu;
+                        if (r16 == 0 && l16 == 0xffffu) {  // sixteen literals: straight from registers
 #pragma unroll
-                    for (int j = 0; j < 16; j++) {
-                        sh.u.list.rec_start[r + j] = o + j;
-                        sh.u.list.rec_sym[r + j] = (uint8_t)byte_of(v, j);
-                    }
-                } else {
-                    rle_parse_thread(my_entry, n, prevb, bytef, [&](uint32_t len, uint32_t sym) {
-                        sh.u.list.rec_start[r] = o;
-                        sh.u.list.rec_sym[r] = (uint8_t)sym;
-                        r++;
-                        o += len;
-                    });
-                }
-                if (tid == RLD_THREADS - 1) sh.u.list.rec_start[tile_recs] = tile_out;
-            }
-            __syncthreads();
-            const uint64_t a0 = out0 & ~15ull;
-            const uint64_t a1 = out0 + tile_out;
-            for (uint64_t g = a0 + (uint64_t)tid * 16; g < a1; g += (uint64_t)RLD_THREADS * 16) {
-                const int64_t r0 = (int64_t)g - (int64_t)out0;  // tile-relative offset of the chunk (may be < 0)
-                const uint32_t first = r0 < 0 ? 0u : (uint32_t)r0;
-                uint32_t lo_i = 0, hi_i = tile_recs;  // largest ri with rec_start[ri] <= first
-                while (hi_i - lo_i > 1) {
-                    const uint32_t mid = (lo_i + hi_i) >> 1;
-                    if (sh.u.list.rec_start[mid] <= first)
-                        lo_i = mid;
-                    else
-                        hi_i = mid;
-                }
-                uint32_t ri = lo_i;
-                const bool full = (r0 >= 0) && (r0 + 16 <= (int64_t)tile_out);
-                if (full && sh.u.list.rec_start[ri + 1] >= first + 16) {
-                    const uint32_t w = (uint32_t)sh.u.list.rec_sym[ri] * 0x01010101u;
-                    st_stream16(out + g, make_uint4(w, w, w, w));
-                } else {
-                    uint32_t w[4] = {0, 0, 0, 0};
-#pragma unroll
-                    for (int k = 0; k < 16; k++) {
-                        const int64_t r = r0 + k;
-                        if (r >= 0 && r < (int64_t)tile_out) {
-                            while (sh.u.list.rec_start[ri + 1] <= (uint32_t)r) ri++;
-                            w[k >> 2] |= (uint32_t)sh.u.list.rec_sym[ri] << (8 * (k & 3));
+                            for (int j = 0; j < 16; j++) sb[o + j] = (uint8_t)byte_of(v[c], j);
+                            o += 16;
+                        } else {  // compact loop over the emitting positions (kept small: the I-cache matters here)
+                            uint32_t eb = l16 | r16;
+#pragma unroll 1
+                            while (eb) {
+                                const int j = ctz32(eb);
+                                eb &= eb - 1;
+                                const uint32_t q = 16 * c + j;
+                                const uint32_t cur = in[pos + q];
+                                if ((r16 >> j) & 1u) {
+                                    const uint32_t sym = q ? (uint32_t)in[pos + q - 1] : prevb;
+                                    const uint32_t len = cur ? cur : 1u;
+                                    rld_fill(sb + o, sym, len);
+                                    o += len;
+                                } else {
+                                    sb[o++] = (uint8_t)cur;
+                                }
+                            }
                         }
                     }
-                    if (full) {
-                        st_stream16(out + g, make_uint4(w[0], w[1], w[2], w[3]));
-                    } else {
-#pragma unroll
-                        for (int k = 0; k < 16; k++) {
-                            const int64_t r = r0 + k;
-                            if (r >= 0 && r < (int64_t)tile_out) out[g + k] = (uint8_t)(w[k >> 2] >> (8 * (k & 3)));
+                } else {
+                    // partial threads (block edges) and multi-window tiles: generic walk over the emitting positions
+                    uint64_t eb = m.lit | m.run;
+#pragma unroll 1
+                    while (eb) {
+                        const int q = ctz64(eb);
+                        eb &= eb - 1;
+                        const uint32_t cur = in[pos + j0 + q];
+                        if ((m.run >> q) & 1ull) {
+                            const uint32_t sym = (q > 0) ? (uint32_t)in[pos + j0 + q - 1] : prevb;
+                            const uint32_t len = cur ? cur : 1u;
+                            rld_emit<true>(sb, w0, w1, o, len, sym);
+                            o += len;
+                        } else {
+                            rld_emit<true>(sb, w0, w1, o, 1u, cur);
+                            o += 1;
                         }
                     }
                 }
             }
+            __syncthreads();
+            // copy the window out: stage[s - w0] -> gbase[s] for s in [max(w0, shift), w1)
+            for (uint32_t c = w0 + tid * 16; c < w1; c += RLD_THREADS * 16) {
+                if (c >= shift && c + 16 <= w1) {
+                    st_stream16(gbase + c, *reinterpret_cast<const uint4 *>(sh.stage + (c - w0)));
+                } else {
+                    for (uint32_t k = (c > shift ? c : shift); k < c + 16 && k < w1; k++) gbase[k] = sh.stage[k - w0];
+                }
+            }
+            if (w1 < span) __syncthreads();  // the next window overwrites the stage
         }
     }
 }

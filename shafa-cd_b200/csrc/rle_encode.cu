@@ -3,20 +3,22 @@
 // fused (f.c:310) and the blocks' outputs compacted back to back (= the .rle
 // file, f.c:307).  Algorithmic bytes: N read + R written.
 //
-// Tile = 4096 bytes of one block (tiles never straddle a block), 256 threads x
-// 16 bytes held in registers.  Per tile:
-//   1. 16-byte loads; "continuation" bits E (byte equals its predecessor) by
-//      SIMD byte compares; neighbours' bits arrive by warp shuffles, the warp
-//      edges read one extra word.  ~E is the run-head bitmask, kept in shared
-//      memory together with a 288-position look-ahead halo (positions at/after
-//      the block end count as heads).
+// Tile = 16 KiB of one block (tiles never straddle a block), 256 threads x 64
+// contiguous bytes held in registers (four 16-byte vectors).  Per tile:
+//   1. loads; "continuation" bits E (byte equals its predecessor) as one 64-bit
+//      mask per thread by SIMD byte compares; the neighbours' edge bits arrive by
+//      warp shuffles, the warp edges read one extra word.  ~E is the run-head
+//      bitmask, kept in shared memory together with a 288-position look-ahead
+//      halo (positions at/after the block end count as heads).
 //   2. chain #1 (decoupled look-back inside the block): length of the run that
 //      is still open at the tile start (needed for k mod 255).
 //   3. what every position emits: threads whose positions all have k < 255 use
-//      the bit-parallel rule shafa::rle_fast_masks (core.h); threads deep inside
-//      a >= 255-byte run use the general per-position walk rle_emit_thread.
+//      the bit-parallel rule shafa::rle_fast_masks64 (core.h); threads deep
+//      inside a >= 255-byte run use the general per-position walk.
 //   4. CTA scan of emitted bytes, chain #2 (look-back over ALL tiles of the
-//      file) gives the tile's offset in the compacted output.
+//      file) gives the tile's offset in the compacted output.  The chain's
+//      prefix frontier moves one look-back window per L2 round trip, which is
+//      why tiles are 16 KiB and the window 128 descriptors.
 //   5. bytes are staged in shared memory co-aligned with the destination and
 //      copied out with 16-byte stores; the same staging buffer feeds the fused
 //      256-bin histogram (8 striped sub-histograms to spread equal-byte hits).
@@ -26,8 +28,8 @@
 
 namespace shafa {
 
-constexpr int RLE_THREADS = RLE_TILE / RLE_ITEMS;        // 256
 constexpr int RLE_WARPS = RLE_THREADS / 32;
+constexpr int RLE_PER_THREAD = RLE_ITEMS * RLE_VECS;     // 64
 constexpr int RLE_STAGE = 2 * RLE_TILE + 3 + 16 + 13;    // worst case 2n+3 (f.c:244) + alignment slack, multiple of 16
 constexpr int RLE_HIST_COPIES = 8;
 
@@ -42,14 +44,22 @@ struct RleEncShared {
     uint32_t ticket;
 };
 
+__device__ __forceinline__ uint4 rle_ld16(const void *p)
+{
+    uint4 v;  // default L1 policy: the four vectors of a thread share sectors
+    asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+
 template <bool WRITE, bool HIST>
-__global__ void __launch_bounds__(RLE_THREADS)
+__global__ void __launch_bounds__(RLE_THREADS, 3)
 k_rle_encode(const uint8_t *__restrict__ in, uint64_t n, uint64_t block_size, uint32_t tiles_per_block,
              uint64_t total_tiles, uint8_t *__restrict__ out, uint64_t out_capacity,
              unsigned long long *__restrict__ hist, uint64_t *__restrict__ blk_end, uint64_t *__restrict__ desc_run,
              uint64_t *__restrict__ desc_out, uint32_t *__restrict__ counter, uint32_t *__restrict__ err)
 {
-    __shared__ RleEncShared sh;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    RleEncShared &sh = *reinterpret_cast<RleEncShared *>(smem_raw);
     const unsigned tid = threadIdx.x, lane = lane_id(), warp = warp_id();
 
     for (;;) {
@@ -71,47 +81,58 @@ k_rle_encode(const uint8_t *__restrict__ in, uint64_t n, uint64_t block_size, ui
         const uint64_t first_tile_of_block = b * tiles_per_block;
         const uint32_t valid_len = (uint32_t)((blk_hi - tile_lo < (uint64_t)(RLE_TILE + RLE_HALO)) ? (blk_hi - tile_lo)
                                                                                                   : (RLE_TILE + RLE_HALO));
-        // ---- 1. load; continuation bits of my 16 positions and of my neighbours ----
-        const uint32_t p0 = tid * 16;
+        // ---- 1. load 64 bytes; continuation bits of my positions and of my neighbours' edges ----
+        const uint32_t p0 = tid * RLE_PER_THREAD;
         const uint64_t pos = tile_lo + p0;
-        const int nvalid = (p0 >= tile_len) ? 0 : (int)((tile_len - p0 < 16) ? (tile_len - p0) : 16);
-        const uint32_t valid16 = (nvalid >= 16) ? 0xffffu : ((1u << nvalid) - 1u);
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (nvalid) v = ld_stream16(in + pos);
-        uint32_t prevb = __shfl_up_sync(FULL, v.w >> 24, 1);
-        uint32_t e_before = 0;  // E of the 8 positions before mine (only the top 2 bits matter)
+        const int nvalid = (p0 >= tile_len) ? 0 : (int)((tile_len - p0 < (uint32_t)RLE_PER_THREAD) ? (tile_len - p0) : RLE_PER_THREAD);
+        const uint64_t valid64 = (nvalid >= 64) ? ~0ull : ((1ull << nvalid) - 1ull);
+        uint4 v[RLE_VECS];
+#pragma unroll
+        for (int c = 0; c < RLE_VECS; c++) {
+            v[c] = make_uint4(0, 0, 0, 0);
+            if ((int)(16 * c) < nvalid) v[c] = rle_ld16(in + pos + 16 * c);
+        }
+        uint32_t prevb = __shfl_up_sync(FULL, v[RLE_VECS - 1].w >> 24, 1);
+        uint32_t e_before = 0;  // bit 0 = E[p0-2], bit 1 = E[p0-1]
         if (lane == 0 && pos > blk_lo && nvalid) {
             const uint32_t w = *reinterpret_cast<const uint32_t *>(in + pos - 4);  // bytes pos-4 .. pos-1, inside the block
             prevb = w >> 24;
             const uint32_t b1 = (w >> 8) & 0xffu, b2 = (w >> 16) & 0xffu;
-            e_before = ((b2 == b1) ? 0x40u : 0u) | ((prevb == b2) ? 0x80u : 0u);
+            e_before = ((b2 == b1) ? 1u : 0u) | ((prevb == b2) ? 2u : 0u);
         }
-        uint32_t e16 = eq_prev_mask16(v, prevb) & valid16;   // positions at/after the block end: E = 0
-        if (pos == blk_lo) e16 &= ~1u;                        // the block start is a head
+        uint64_t E = 0, Z = 0;
+#pragma unroll
+        for (int c = 0; c < RLE_VECS; c++) {
+            const uint32_t pb = (c == 0) ? prevb : (v[c - 1].w >> 24);
+            E |= (uint64_t)eq_prev_mask16(v[c], pb) << (16 * c);
+            Z |= (uint64_t)zero_mask16(v[c]) << (16 * c);
+        }
+        E &= valid64;                   // positions at/after the block end: E = 0
+        if (pos == blk_lo) E &= ~1ull;  // the block start is a head
         {
-            const uint32_t up = __shfl_up_sync(FULL, e16, 1);
-            if (lane != 0) e_before = up >> 8;
+            const uint32_t up = __shfl_up_sync(FULL, (uint32_t)(E >> 62), 1);
+            if (lane != 0) e_before = up;
         }
-        uint32_t e_after = __shfl_down_sync(FULL, e16, 1) & 0xffu;
+        uint32_t e_after = __shfl_down_sync(FULL, (uint32_t)E & 7u, 1);  // bit i = E[p0+64+i]
         if (lane == 31) {
             e_after = 0;
-            if (nvalid == 16 && pos + 16 < blk_hi) {
-                const uint32_t w = *reinterpret_cast<const uint32_t *>(in + pos + 16);  // bytes pos+16 .. pos+19
+            if (nvalid == RLE_PER_THREAD && pos + RLE_PER_THREAD < blk_hi) {
+                const uint32_t w = *reinterpret_cast<const uint32_t *>(in + pos + RLE_PER_THREAD);  // next 4 bytes
                 const uint32_t c0 = w & 0xffu, c1 = (w >> 8) & 0xffu, c2 = (w >> 16) & 0xffu;
-                const uint64_t left = blk_hi - (pos + 16);  // valid bytes from pos+16 on
-                e_after = (c0 == (v.w >> 24)) ? 1u : 0u;
+                const uint64_t left = blk_hi - (pos + RLE_PER_THREAD);  // valid bytes from there on
+                e_after = (c0 == (v[RLE_VECS - 1].w >> 24)) ? 1u : 0u;
                 if (left > 1 && c1 == c0) e_after |= 2u;
                 if (left > 2 && c2 == c1) e_after |= 4u;
             }
         }
-        const uint32_t ewin = (e_before & 0xffu) | (e16 << 8) | (e_after << 24);
-        const uint32_t my_heads = ~e16 & 0xffffu;  // includes every position >= valid
-        reinterpret_cast<uint16_t *>(sh.heads)[tid] = (uint16_t)my_heads;
+        const uint64_t my_heads = ~E;  // includes every position >= valid
+        sh.heads[2 * tid] = (uint32_t)my_heads;
+        sh.heads[2 * tid + 1] = (uint32_t)(my_heads >> 32);
         if (tid < RLE_HALO / 16) {  // look-ahead halo heads, straight from global memory
             const uint32_t q0 = RLE_TILE + tid * 16;
             uint32_t hm = 0xffffu;
             if (q0 < valid_len) {
-                const uint4 hv = ld_stream16(in + tile_lo + q0);
+                const uint4 hv = rle_ld16(in + tile_lo + q0);
                 const uint32_t pb = in[tile_lo + q0 - 1];
                 hm = ~eq_prev_mask16(hv, pb) & 0xffffu;
                 if (q0 + 16 > valid_len) hm |= (0xffffu << (valid_len - q0)) & 0xffffu;
@@ -119,7 +140,7 @@ k_rle_encode(const uint8_t *__restrict__ in, uint64_t n, uint64_t block_size, ui
             reinterpret_cast<uint16_t *>(sh.heads)[RLE_TILE / 16 + tid] = (uint16_t)hm;
         }
         // ---- last head strictly before each thread's first position ----
-        int32_t lh = my_heads ? (int32_t)(p0 + 31 - clz32(my_heads)) : -1;  // highest head inside my 16
+        int32_t lh = my_heads ? (int32_t)(p0 + 63 - __clzll((long long)my_heads)) : -1;  // highest head inside my 64
         {
             int32_t incl = lh;
 #pragma unroll
@@ -175,36 +196,35 @@ k_rle_encode(const uint8_t *__restrict__ in, uint64_t n, uint64_t block_size, ui
         const uint64_t run_in = sh.run_in;
 
         // ---- 3. what does each position emit ----
-        auto symf = [&](int j) -> uint32_t { return byte_of(v, j); };
-        RleEmit em;
-        em.lit = em.tri = em.bytes = 0;
-        em.cnt[0] = em.cnt[1] = em.cnt[2] = em.cnt[3] = 0;
+        uint64_t lit = 0, tri = 0;
         if (nvalid) {
             const uint64_t k0 = (lh >= 0) ? (uint64_t)(p0 - (uint32_t)lh) : (uint64_t)p0 + run_in;  // k at p0 if p0 is no head
-            if ((e16 & 1u) && k0 + 15 >= 255) {
-                em = rle_emit_thread(sh.heads, p0, nvalid, (uint32_t)(k0 % 255), symf);  // deep inside a long run
-            } else {
-                const RleMasks m = rle_fast_masks(ewin, zero_mask16(v), valid16);
-                em.lit = m.lit;
-                em.tri = m.tri;
-                uint32_t tb = m.tri;
-                while (tb) {
-                    const int j = ctz32(tb);
-                    tb &= tb - 1;
-                    const uint32_t val = rle_run_remaining(sh.heads, p0 + (uint32_t)j) << (8 * (j & 3));
-                    const int q = j >> 2;  // constant indices keep cnt[] in registers
-                    if (q == 0) em.cnt[0] |= val;
-                    else if (q == 1) em.cnt[1] |= val;
-                    else if (q == 2) em.cnt[2] |= val;
-                    else em.cnt[3] |= val;
+            if ((E & 1ull) && k0 + (RLE_PER_THREAD - 1) >= 255) {
+                // deep inside a long run: general per-position walk, one 16-byte group at a time
+#pragma unroll
+                for (int c = 0; c < RLE_VECS; c++) {
+                    const int nv = nvalid - 16 * c;
+                    if (nv > 0) {
+                        // k at the group's first position: distance to the last head before it
+                        const uint64_t hb = (c == 0) ? 0ull : (my_heads & ((1ull << (16 * c)) - 1ull));
+                        const uint64_t kc = hb ? (uint64_t)(16 * c - (63 - __clzll((long long)hb))) : k0 + 16 * c;
+                        auto symc = [&](int j) -> uint32_t { return byte_of(v[c], j); };
+                        const RleEmit em = rle_emit_thread(sh.heads, p0 + 16 * c, nv > 16 ? 16 : nv, (uint32_t)(kc % 255), symc);
+                        lit |= (uint64_t)em.lit << (16 * c);
+                        tri |= (uint64_t)em.tri << (16 * c);
+                    }
                 }
-                em.bytes = (uint32_t)__popc(m.lit) + 3u * (uint32_t)__popc(m.tri);
+            } else {
+                const RleMasks64 m = rle_fast_masks64(E, e_before, e_after, Z & valid64, valid64);
+                lit = m.lit;
+                tri = m.tri;
             }
         }
+        const uint32_t my_bytes = (uint32_t)__popcll(lit) + 3u * (uint32_t)__popcll(tri);
 
         // ---- 4. offsets ----
         uint32_t tile_bytes;
-        const uint32_t excl = block_excl_scan<RLE_THREADS>(em.bytes, sh.scan, &tile_bytes);
+        const uint32_t excl = block_excl_scan<RLE_THREADS>(my_bytes, sh.scan, &tile_bytes);
         if (warp == 0) {
             const uint64_t pfx = lookback_sum(desc_out, (int64_t)t, 0, tile_bytes);
             if (lane == 0) sh.out_prefix = pfx;
@@ -218,11 +238,30 @@ k_rle_encode(const uint8_t *__restrict__ in, uint64_t n, uint64_t block_size, ui
         const uint32_t shift = (uint32_t)(out0 & 15u);  // co-align staging with the destination
         {
             uint8_t *dst = sh.stage + shift + excl;
-            if (em.tri == 0 && em.lit == 0xffffu) {
 #pragma unroll
-                for (int j = 0; j < 16; j++) dst[j] = (uint8_t)byte_of(v, j);
-            } else if (em.tri | em.lit) {
-                rle_write_thread(em, dst, symf);
+            for (int c = 0; c < RLE_VECS; c++) {
+                const uint32_t l16 = (uint32_t)(lit >> (16 * c)) & 0xffffu, t16 = (uint32_t)(tri >> (16 * c)) & 0xffffu;
+                if (t16 == 0 && l16 == 0xffffu) {  // sixteen literals: straight from registers
+#pragma unroll
+                    for (int j = 0; j < 16; j++) dst[j] = (uint8_t)byte_of(v[c], j);
+                    dst += 16;
+                } else {  // compact loop over the emitting positions (kept small: the I-cache matters here)
+                    uint32_t eb = l16 | t16;
+#pragma unroll 1
+                    while (eb) {
+                        const int j = ctz32(eb);
+                        eb &= eb - 1;
+                        const uint32_t s = in[pos + 16 * c + j];  // L1 hit: the line was just loaded
+                        if ((t16 >> j) & 1u) {
+                            dst[0] = 0;
+                            dst[1] = (uint8_t)s;
+                            dst[2] = (uint8_t)rle_run_remaining(sh.heads, p0 + 16 * c + j);
+                            dst += 3;
+                        } else {
+                            *dst++ = (uint8_t)s;
+                        }
+                    }
+                }
             }
         }
         __syncthreads();
@@ -281,6 +320,7 @@ int launch_rle_encode(shafa_cuda_ctx *ctx, const uint8_t *d_in, uint64_t n, uint
     if (tpb > 0xffffffffull || total_tiles > 0xfffffff0ull) return set_error(ctx, SHAFA_LACK_OF_MEMORY, "rle_encode: too many tiles");
 
     static int occ[4] = {0, 0, 0, 0};
+    const size_t smem = sizeof(RleEncShared);
     const int variant = (d_rle ? 2 : 0) | (d_hist ? 1 : 0);
     void (*kern)(const uint8_t *, uint64_t, uint64_t, uint32_t, uint64_t, uint8_t *, uint64_t, unsigned long long *,
                  uint64_t *, uint64_t *, uint64_t *, uint32_t *, uint32_t *) =
@@ -289,7 +329,8 @@ int launch_rle_encode(shafa_cuda_ctx *ctx, const uint8_t *d_in, uint64_t n, uint
         : variant == 1 ? k_rle_encode<false, true>
                        : k_rle_encode<false, false>;
     if (!occ[variant]) {
-        SHAFA_CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[variant], kern, RLE_THREADS, 0));
+        SHAFA_CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SHAFA_CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[variant], kern, RLE_THREADS, smem));
         if (occ[variant] < 1) occ[variant] = 1;
     }
     uint64_t *desc = (uint64_t *)scratch_get(ctx, SCR_DESC, 2 * (total_tiles + 1) * sizeof(uint64_t));
@@ -301,7 +342,7 @@ int launch_rle_encode(shafa_cuda_ctx *ctx, const uint8_t *d_in, uint64_t n, uint
     if (d_hist) SHAFA_CUDA_TRY(ctx, cudaMemsetAsync(d_hist, 0, nb * 256 * sizeof(uint64_t), ctx->stream));
     uint64_t grid = (uint64_t)ctx->sm_count * occ[variant];
     if (grid > total_tiles) grid = total_tiles;
-    SHAFA_LAUNCH(ctx, d_rle ? "rle_encode" : "rle_encode_sizes", kern, dim3((unsigned)grid), dim3(RLE_THREADS), 0,
+    SHAFA_LAUNCH(ctx, d_rle ? "rle_encode" : "rle_encode_sizes", kern, dim3((unsigned)grid), dim3(RLE_THREADS), smem,
                  d_in, n, block_size, (uint32_t)tpb, total_tiles, d_rle, rle_capacity, (unsigned long long *)d_hist,
                  blk_end, desc, desc + total_tiles + 1, counter, d_err);
     SHAFA_CHECK_LAUNCH(ctx);

@@ -23,7 +23,8 @@ namespace shafa {
 
 // ---- tables -----------------------------------------------------------------------------
 struct DecTablesGlobal {
-    uint16_t *lut;    // [nb][4096]
+    uint16_t *lut;    // [nb][4096]  first-level: (sym << 8) | len
+    uint16_t *lut2;   // [nb][4096]  (nsym << 8) | bits of all whole codes in the window
     uint64_t *sleft;  // [nb][256]
     uint8_t *slen;    // [nb][256]
     uint8_t *ssym;    // [nb][256]
@@ -37,6 +38,7 @@ k_dec_tables(const uint8_t *__restrict__ lens, const uint64_t *__restrict__ code
     __shared__ uint64_t sl[256];
     __shared__ uint8_t sn[256];
     __shared__ uint8_t ss[256];
+    __shared__ uint16_t lut1[DEC_LUT_SIZE];
     const unsigned s = threadIdx.x;
     const uint64_t b = blockIdx.x;
     const uint32_t l = lens[b * 256 + s];
@@ -79,8 +81,11 @@ k_dec_tables(const uint8_t *__restrict__ lens, const uint64_t *__restrict__ code
             else
                 entry = (uint16_t)DEC_LONG;
         }
+        lut1[e] = entry;
         g.lut[b * DEC_LUT_SIZE + e] = entry;
     }
+    __syncthreads();
+    for (int e = s; e < DEC_LUT_SIZE; e += 256) g.lut2[b * DEC_LUT_SIZE + e] = dec_lut2_entry(lut1, (uint32_t)e);
 }
 
 // ---- shared helpers -----------------------------------------------------------------------
@@ -96,8 +101,10 @@ struct DecPlan {
 constexpr int DEC_STAGE = 16384;  // symbols of one sequence staged in shared memory before the coalesced copy-out
 
 struct DecShared {
-    uint32_t words[DEC_SEQ_WORDS + DEC_WORDS_PAD];
-    uint16_t lut[DEC_LUT_SIZE];
+    uint64_t pairs[DEC_SEQ_WORDS + DEC_WORDS_PAD];  // pairs[i] = (w[i] << 32) | w[i+1], big-endian words
+    uint32_t words[DEC_SEQ_WORDS + DEC_WORDS_PAD + 4];
+    uint16_t lut1[DEC_LUT_SIZE];
+    uint16_t lut2[DEC_LUT_SIZE];
     uint64_t sleft[256];
     uint8_t slen[256];
     uint8_t ssym[256];
@@ -106,28 +113,31 @@ struct DecShared {
     uint32_t block;
 };
 
-struct DecWriteShared {
-    DecShared d;
-    alignas(16) uint8_t stage[DEC_STAGE + 32];
-};
-
-// load tables + the sequence's payload words (big-endian) into shared memory
-__device__ __forceinline__ void dec_load_sequence(DecShared &sh, const DecTablesGlobal &g, const uint8_t *payload,
-                                                  uint64_t pay_off, uint64_t z, uint64_t seq_in_block, uint32_t b)
+__device__ __forceinline__ void dec_load_tables(DecShared &sh, const DecTablesGlobal &g, uint32_t b, bool want_lut2)
 {
     const unsigned tid = threadIdx.x;
-    {
-        const uint4 *src = reinterpret_cast<const uint4 *>(g.lut + (uint64_t)b * DEC_LUT_SIZE);
-        uint4 *dst = reinterpret_cast<uint4 *>(sh.lut);
-        for (int i = tid; i < DEC_LUT_SIZE * 2 / 16; i += DEC_THREADS) dst[i] = src[i];
-        sh.sleft[tid] = g.sleft[(uint64_t)b * 256 + tid];
-        sh.slen[tid] = g.slen[(uint64_t)b * 256 + tid];
-        sh.ssym[tid] = g.ssym[(uint64_t)b * 256 + tid];
+    const uint4 *src1 = reinterpret_cast<const uint4 *>(g.lut + (uint64_t)b * DEC_LUT_SIZE);
+    const uint4 *src2 = reinterpret_cast<const uint4 *>(g.lut2 + (uint64_t)b * DEC_LUT_SIZE);
+    uint4 *dst1 = reinterpret_cast<uint4 *>(sh.lut1);
+    uint4 *dst2 = reinterpret_cast<uint4 *>(sh.lut2);
+    for (int i = tid; i < DEC_LUT_SIZE * 2 / 16; i += DEC_THREADS) {
+        dst1[i] = src1[i];
+        if (want_lut2) dst2[i] = src2[i];
     }
+    sh.sleft[tid] = g.sleft[(uint64_t)b * 256 + tid];
+    sh.slen[tid] = g.slen[(uint64_t)b * 256 + tid];
+    sh.ssym[tid] = g.ssym[(uint64_t)b * 256 + tid];
+}
+
+// load the sequence's payload as big-endian words, then as overlapping pairs (call between barriers)
+__device__ __forceinline__ void dec_load_words(DecShared &sh, const uint8_t *payload, uint64_t pay_off, uint64_t z,
+                                               uint64_t seq_in_block)
+{
+    const unsigned tid = threadIdx.x;
     const uint64_t byte0 = seq_in_block * DEC_SEQ_BYTES;  // offset of this sequence in the block's payload
     const uint64_t slot = (z + 15) & ~15ull;              // readable bytes of the block's slot
     const uint8_t *base = payload + pay_off;
-    for (int i = tid; i < (DEC_SEQ_WORDS + DEC_WORDS_PAD) / 4; i += DEC_THREADS) {
+    for (int i = tid; i < (DEC_SEQ_WORDS + DEC_WORDS_PAD + 4) / 4; i += DEC_THREADS) {
         const uint64_t o = byte0 + (uint64_t)i * 16;
         uint4 v = make_uint4(0, 0, 0, 0);
         if (o < slot) v = ld_stream16(base + o);
@@ -144,65 +154,90 @@ __device__ __forceinline__ void dec_load_sequence(DecShared &sh, const DecTables
         }
     }
 }
-
-__device__ __forceinline__ DecTables dec_tables_of(const DecShared &sh)
+__device__ __forceinline__ void dec_build_pairs(DecShared &sh)
 {
-    DecTables t;
-    t.lut = sh.lut;
+    for (int i = threadIdx.x; i < DEC_SEQ_WORDS + DEC_WORDS_PAD; i += DEC_THREADS)
+        sh.pairs[i] = ((uint64_t)sh.words[i] << 32) | (uint64_t)sh.words[i + 1];
+}
+
+__device__ __forceinline__ DecView dec_view_of(const DecShared &sh)
+{
+    DecView t;
+    t.pairs = sh.pairs;
+    t.lut1 = sh.lut1;
+    t.lut2 = sh.lut2;
     t.sleft = sh.sleft;
     t.slen = sh.slen;
     t.ssym = sh.ssym;
     return t;
 }
 
-// sub-sequence record: low 8 bits = start offset inside the sub-sequence (< 64),
-// high 8 bits... counts can reach 128, so: bits [6:0] start, bits [15:7] count
+// sub-sequence record: bits [6:0] start offset inside the sub-sequence (< 64), bits [15:7] symbol count (<= 128)
 __device__ __forceinline__ uint16_t sub_pack(uint32_t start, uint32_t count) { return (uint16_t)(start | (count << 7)); }
 __device__ __forceinline__ uint32_t sub_start(uint16_t v) { return v & 127u; }
 __device__ __forceinline__ uint32_t sub_count(uint16_t v) { return v >> 7; }
 
+// contiguous chunk of sequences owned by this CTA (tables are reloaded only when the block changes)
+__device__ __forceinline__ void dec_chunk(uint64_t nseq, uint64_t *first, uint64_t *last)
+{
+    const uint64_t per = (nseq + gridDim.x - 1) / gridDim.x;
+    *first = (uint64_t)blockIdx.x * per;
+    const uint64_t e = *first + per;
+    *last = e < nseq ? e : nseq;
+}
+
 // ---- phase 1: synchronise inside each sequence ----------------------------------------------
 __global__ void __launch_bounds__(DEC_THREADS)
 k_dec_sync(const uint8_t *__restrict__ payload, DecPlan plan, DecTablesGlobal g, uint16_t *__restrict__ sub_info,
-           uint32_t *__restrict__ seq_end, uint32_t *__restrict__ err)
+           uint32_t *__restrict__ seq_end, uint64_t nseq)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    DecShared &sh = *reinterpret_cast<DecShared *>(smem_raw);
+    __shared__ DecShared sh;
     const unsigned tid = threadIdx.x;
-    const uint64_t seq = blockIdx.x;
-    if (tid == 0) sh.block = find_block(plan.seq0, plan.nb, seq);
-    __syncthreads();
-    const uint32_t b = sh.block;
-    const uint64_t sib = seq - plan.seq0[b];
-    const uint64_t z = plan.z[b];
-    dec_load_sequence(sh, g, payload, plan.pay_off[b], z, sib, b);
-    __syncthreads();
-    const DecTables t = dec_tables_of(sh);
-    // bits of this sequence that exist in the payload
-    const uint64_t bits_left = (z - sib * DEC_SEQ_BYTES) * 8;
-    const uint32_t limit = bits_left < (uint64_t)DEC_SEQ_BYTES * 8 ? (uint32_t)bits_left : DEC_SEQ_BYTES * 8;
-    const uint32_t sub_lo = tid * DEC_SUB_BITS;
-    const uint32_t sub_hi = sub_lo + DEC_SUB_BITS;
-    const uint32_t stop = sub_hi < limit ? sub_hi : limit;
-
-    uint32_t start = 0;
-    DecSub r = dec_subsequence(sh.words, t, sub_lo + start, stop, DecNoEmit());
-    uint32_t my_end = r.end > sub_hi ? r.end - sub_hi : 0;  // overshoot into the next sub-sequence
-    for (;;) {
-        sh.ends[tid] = my_end;
+    uint64_t seq_first, seq_last;
+    dec_chunk(nseq, &seq_first, &seq_last);
+    uint32_t cur_block = 0xffffffffu;
+    for (uint64_t seq = seq_first; seq < seq_last; seq++) {
+        __syncthreads();  // previous sequence fully consumed
+        if (tid == 0) sh.block = find_block(plan.seq0, plan.nb, seq);
         __syncthreads();
-        const uint32_t want = tid ? sh.ends[tid - 1] : 0u;
-        const int changed = (want != start);
-        if (!__syncthreads_or(changed)) break;
-        if (changed) {
-            start = want;
-            r = dec_subsequence(sh.words, t, sub_lo + start, stop, DecNoEmit());
-            my_end = r.end > sub_hi ? r.end - sub_hi : 0;
+        const uint32_t b = sh.block;
+        const uint64_t sib = seq - plan.seq0[b];
+        const uint64_t z = plan.z[b];
+        if (b != cur_block) {
+            cur_block = b;
+            dec_load_tables(sh, g, b, true);
         }
+        dec_load_words(sh, payload, plan.pay_off[b], z, sib);
+        __syncthreads();
+        dec_build_pairs(sh);
+        __syncthreads();
+        const DecView t = dec_view_of(sh);
+        // bits of this sequence that exist in the payload
+        const uint64_t bits_left = (z - sib * DEC_SEQ_BYTES) * 8;
+        const uint32_t limit = bits_left < (uint64_t)DEC_SEQ_BYTES * 8 ? (uint32_t)bits_left : DEC_SEQ_BYTES * 8;
+        const uint32_t sub_lo = tid * DEC_SUB_BITS;
+        const uint32_t sub_hi = sub_lo + DEC_SUB_BITS;
+        const uint32_t stop = sub_hi < limit ? sub_hi : limit;
+
+        uint32_t start = 0;
+        DecSub r = dec_count_subsequence(t, sub_lo + start, stop);
+        uint32_t my_end = r.end > sub_hi ? r.end - sub_hi : 0;  // overshoot into the next sub-sequence
+        for (;;) {
+            sh.ends[tid] = my_end;
+            __syncthreads();
+            const uint32_t want = tid ? sh.ends[tid - 1] : 0u;
+            const int changed = (want != start);
+            if (!__syncthreads_or(changed)) break;
+            if (changed) {
+                start = want;
+                r = dec_count_subsequence(t, sub_lo + start, stop);
+                my_end = r.end > sub_hi ? r.end - sub_hi : 0;
+            }
+        }
+        sub_info[seq * DEC_THREADS + tid] = sub_pack(start, r.count);
+        if (tid == DEC_THREADS - 1) seq_end[seq] = my_end;
+        // a speculative start may hit garbage; errors are judged in k_dec_write
     }
-    sub_info[seq * DEC_THREADS + tid] = sub_pack(start, r.count);
-    if (tid == DEC_THREADS - 1) seq_end[seq] = my_end;
-    (void)err;  // a speculative start may hit garbage; errors are judged in k_dec_write
 }
 
 // ---- phase 2: stitch sequences together -------------------------------------------------------
@@ -303,63 +338,78 @@ k_dec_scan(DecPlan plan, const uint32_t *__restrict__ seq_count, uint64_t *__res
 // Symbols of a sequence are staged in shared memory (co-aligned with their destination) and
 // copied out with 16-byte stores; a sequence that decodes to more than DEC_STAGE symbols
 // (codes of 1-2 bits) writes straight to global memory instead.
+struct DecWriteShared {
+    DecShared d;
+    alignas(16) uint8_t stage[DEC_STAGE + 32];
+};
+
 __global__ void __launch_bounds__(DEC_THREADS)
 k_dec_write(const uint8_t *__restrict__ payload, DecPlan plan, DecTablesGlobal g,
             const uint16_t *__restrict__ sub_info, const uint64_t *__restrict__ seq_excl, uint8_t *__restrict__ out,
-            uint32_t *__restrict__ err)
+            uint64_t nseq, uint32_t *__restrict__ err)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     DecWriteShared &ws = *reinterpret_cast<DecWriteShared *>(smem_raw);
     DecShared &sh = ws.d;
     const unsigned tid = threadIdx.x;
-    const uint64_t seq = blockIdx.x;
-    if (tid == 0) sh.block = find_block(plan.seq0, plan.nb, seq);
-    __syncthreads();
-    const uint32_t b = sh.block;
-    const uint64_t sib = seq - plan.seq0[b];
-    const uint64_t z = plan.z[b];
-    dec_load_sequence(sh, g, payload, plan.pay_off[b], z, sib, b);
-    const uint16_t rec = sub_info[seq * DEC_THREADS + tid];
-    uint32_t total;
-    const uint32_t excl = block_excl_scan<DEC_THREADS>(sub_count(rec), sh.scan, &total);  // also fences the loads above
-    const DecTables t = dec_tables_of(sh);
-    const uint64_t bits_left = (z - sib * DEC_SEQ_BYTES) * 8;
-    const uint32_t limit = bits_left < (uint64_t)DEC_SEQ_BYTES * 8 ? (uint32_t)bits_left : DEC_SEQ_BYTES * 8;
-    const uint32_t sub_lo = tid * DEC_SUB_BITS;
-    const uint32_t sub_hi = sub_lo + DEC_SUB_BITS;
-    const uint32_t stop = sub_hi < limit ? sub_hi : limit;
-    const uint64_t n = plan.n[b];
-    const uint64_t seq_first = seq_excl[seq];  // index of this sequence's first symbol inside the block
-    if (seq_first >= n) return;                // only padding garbage from here on (uniform for the CTA)
-    const uint64_t seq_room = n - seq_first;   // symbols of this sequence that are real
-    const uint32_t seq_syms = seq_room < total ? (uint32_t)seq_room : total;
-    uint8_t *gdst = out + plan.out_off[b] + seq_first;
+    uint64_t seq_first, seq_last;
+    dec_chunk(nseq, &seq_first, &seq_last);
+    uint32_t cur_block = 0xffffffffu;
     uint32_t bad = 0;
-    if (seq_syms <= (uint32_t)DEC_STAGE) {
-        const uint32_t shift = (uint32_t)((uintptr_t)gdst & 15u);
-        uint8_t *dst = ws.stage + shift + excl;
-        const uint32_t room = excl < seq_syms ? seq_syms - excl : 0u;
-        const DecSub r = dec_subsequence(sh.words, t, sub_lo + sub_start(rec), stop, [&](uint32_t i, uint32_t sym) {
-            if (i < room) dst[i] = (uint8_t)sym;
-        });
-        bad = r.bad && room;
+    for (uint64_t seq = seq_first; seq < seq_last; seq++) {
         __syncthreads();
-        uint8_t *ga = gdst - shift;  // 16-byte aligned
-        const uint32_t end = shift + seq_syms;
-        for (uint32_t c = tid * 16; c < end; c += DEC_THREADS * 16) {
-            if (c >= shift && c + 16 <= end) {
-                st_stream16(ga + c, *reinterpret_cast<const uint4 *>(ws.stage + c));
-            } else {
-                for (uint32_t k = (c > shift ? c : shift); k < c + 16 && k < end; k++) ga[k] = ws.stage[k];
-            }
+        if (tid == 0) sh.block = find_block(plan.seq0, plan.nb, seq);
+        __syncthreads();
+        const uint32_t b = sh.block;
+        const uint64_t sib = seq - plan.seq0[b];
+        const uint64_t z = plan.z[b];
+        if (b != cur_block) {
+            cur_block = b;
+            dec_load_tables(sh, g, b, false);
         }
-    } else {
-        uint8_t *dst = gdst + excl;
+        dec_load_words(sh, payload, plan.pay_off[b], z, sib);
+        const uint16_t rec = sub_info[seq * DEC_THREADS + tid];
+        uint32_t total;
+        const uint32_t excl = block_excl_scan<DEC_THREADS>(sub_count(rec), sh.scan, &total);  // also fences the loads above
+        dec_build_pairs(sh);
+        __syncthreads();
+        const DecView t = dec_view_of(sh);
+        const uint64_t bits_left = (z - sib * DEC_SEQ_BYTES) * 8;
+        const uint32_t limit = bits_left < (uint64_t)DEC_SEQ_BYTES * 8 ? (uint32_t)bits_left : DEC_SEQ_BYTES * 8;
+        const uint32_t sub_lo = tid * DEC_SUB_BITS;
+        const uint32_t sub_hi = sub_lo + DEC_SUB_BITS;
+        const uint32_t stop = sub_hi < limit ? sub_hi : limit;
+        const uint64_t n = plan.n[b];
+        const uint64_t sfirst = seq_excl[seq];   // index of this sequence's first symbol inside the block
+        if (sfirst >= n) continue;               // only padding garbage from here on (uniform for the CTA)
+        const uint64_t seq_room = n - sfirst;    // symbols of this sequence that are real
+        const uint32_t seq_syms = seq_room < total ? (uint32_t)seq_room : total;
+        uint8_t *gdst = out + plan.out_off[b] + sfirst;
         const uint32_t room = excl < seq_syms ? seq_syms - excl : 0u;
-        const DecSub r = dec_subsequence(sh.words, t, sub_lo + sub_start(rec), stop, [&](uint32_t i, uint32_t sym) {
-            if (i < room) dst[i] = (uint8_t)sym;
-        });
-        bad = r.bad && room;
+        if (seq_syms <= (uint32_t)DEC_STAGE) {
+            const uint32_t shift = (uint32_t)((uintptr_t)gdst & 15u);
+            uint8_t *dst = ws.stage + shift + excl;
+            const DecSub r = dec_emit_subsequence(t, sub_lo + sub_start(rec), stop, [&](uint32_t i, uint32_t sym) {
+                if (i < room) dst[i] = (uint8_t)sym;
+            });
+            bad |= r.bad && room;
+            __syncthreads();
+            uint8_t *ga = gdst - shift;  // 16-byte aligned
+            const uint32_t end = shift + seq_syms;
+            for (uint32_t c = tid * 16; c < end; c += DEC_THREADS * 16) {
+                if (c >= shift && c + 16 <= end) {
+                    st_stream16(ga + c, *reinterpret_cast<const uint4 *>(ws.stage + c));
+                } else {
+                    for (uint32_t k = (c > shift ? c : shift); k < c + 16 && k < end; k++) ga[k] = ws.stage[k];
+                }
+            }
+        } else {
+            uint8_t *dst = gdst + excl;
+            const DecSub r = dec_emit_subsequence(t, sub_lo + sub_start(rec), stop, [&](uint32_t i, uint32_t sym) {
+                if (i < room) dst[i] = (uint8_t)sym;
+            });
+            bad |= r.bad && room;
+        }
     }
     // a bad window only matters if it produced one of the n real symbols
     if (bad) atomicOr(err, (uint32_t)ERR_BAD_WINDOW);
@@ -402,13 +452,14 @@ int launch_sf_decode(shafa_cuda_ctx *ctx, const uint8_t *d_payload, const uint64
 
     // tables
     const size_t lut_bytes = nb * DEC_LUT_SIZE * sizeof(uint16_t);
-    const size_t tab_bytes = lut_bytes + nb * 256 * (sizeof(uint64_t) + 2);
+    const size_t tab_bytes = 2 * lut_bytes + nb * 256 * (sizeof(uint64_t) + 2);
     uint8_t *tab = (uint8_t *)scratch_get(ctx, SCR_DEC_LUT, tab_bytes);
     if (!tab) return SHAFA_LACK_OF_MEMORY;
     DecTablesGlobal g;
     g.sleft = (uint64_t *)tab;
     g.lut = (uint16_t *)(tab + nb * 256 * sizeof(uint64_t));
-    g.slen = tab + nb * 256 * sizeof(uint64_t) + lut_bytes;
+    g.lut2 = (uint16_t *)(tab + nb * 256 * sizeof(uint64_t) + lut_bytes);
+    g.slen = tab + nb * 256 * sizeof(uint64_t) + 2 * lut_bytes;
     g.ssym = g.slen + nb * 256;
 
     uint16_t *sub_info = (uint16_t *)scratch_get(ctx, SCR_DEC_SUB, nseq * DEC_THREADS * sizeof(uint16_t));
@@ -420,16 +471,22 @@ int launch_sf_decode(shafa_cuda_ctx *ctx, const uint8_t *d_payload, const uint64
     uint32_t *seq_end = (uint32_t *)(seqbuf + nseq * 8);
     uint32_t *seq_count = seq_end + nseq;
 
-    static bool attr_done = false;
-    const size_t smem = sizeof(DecShared), smem_w = sizeof(DecWriteShared);
-    if (!attr_done) {
-        SHAFA_CUDA_TRY(ctx, cudaFuncSetAttribute(k_dec_sync, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static int occ_sync = 0, occ_write = 0;
+    const size_t smem_w = sizeof(DecWriteShared);
+    if (!occ_sync) {
         SHAFA_CUDA_TRY(ctx, cudaFuncSetAttribute(k_dec_write, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w));
-        attr_done = true;
+        SHAFA_CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_sync, k_dec_sync, DEC_THREADS, 0));
+        SHAFA_CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_write, k_dec_write, DEC_THREADS, smem_w));
+        if (occ_sync < 1) occ_sync = 1;
+        if (occ_write < 1) occ_write = 1;
     }
+    // persistent CTAs, each owning a contiguous chunk of sequences (4 chunks per resident CTA for balance)
+    uint64_t grid_sync = (uint64_t)ctx->sm_count * occ_sync * 4, grid_write = (uint64_t)ctx->sm_count * occ_write * 4;
+    if (grid_sync > nseq) grid_sync = nseq;
+    if (grid_write > nseq) grid_write = nseq;
     SHAFA_LAUNCH(ctx, "dec_tables", k_dec_tables, dim3((unsigned)nb), dim3(256), 0, d_len, d_code, g);
-    SHAFA_LAUNCH(ctx, "dec_sync", k_dec_sync, dim3((unsigned)nseq), dim3(DEC_THREADS), smem, d_payload, plan, g,
-                 sub_info, seq_end, d_err);
+    SHAFA_LAUNCH(ctx, "dec_sync", k_dec_sync, dim3((unsigned)grid_sync), dim3(DEC_THREADS), 0, d_payload, plan, g, sub_info,
+                 seq_end, nseq);
     SHAFA_CHECK_LAUNCH(ctx);
     // stitch until a pass changes nothing (normally 1-2 passes)
     uint32_t *h_flag = (uint32_t *)pinned_get(ctx, 64);
@@ -446,8 +503,8 @@ int launch_sf_decode(shafa_cuda_ctx *ctx, const uint8_t *d_payload, const uint64
     }
     SHAFA_LAUNCH(ctx, "dec_count", k_dec_count, dim3((unsigned)nseq), dim3(DEC_THREADS), 0, sub_info, seq_count);
     SHAFA_LAUNCH(ctx, "dec_scan", k_dec_scan, dim3((unsigned)nb), dim3(256), 0, plan, seq_count, seq_excl, d_err);
-    SHAFA_LAUNCH(ctx, "dec_write", k_dec_write, dim3((unsigned)nseq), dim3(DEC_THREADS), smem_w, d_payload, plan, g,
-                 sub_info, seq_excl, d_sym, d_err);
+    SHAFA_LAUNCH(ctx, "dec_write", k_dec_write, dim3((unsigned)grid_write), dim3(DEC_THREADS), smem_w, d_payload, plan, g,
+                 sub_info, seq_excl, d_sym, nseq, d_err);
     SHAFA_CHECK_LAUNCH(ctx);
     return SHAFA_SUCCESS;
 }

@@ -22,11 +22,7 @@
 
 namespace shafa {
 
-constexpr int ENC_THREADS = 256;
-constexpr int ENC_ITEMS = 16;
-constexpr int ENC_TILE = ENC_THREADS * ENC_ITEMS;  // 4096
-constexpr int ENC_COPIES = 32;                     // one LUT copy per lane -> no bank conflicts
-constexpr int ENC_STAGE_WORDS = ENC_TILE * ENC_SHORT_MAX / 32 + 8;
+constexpr int ENC_COPIES = 32;  // one LUT copy per lane -> no bank conflicts
 
 // ---- exact sizes -------------------------------------------------------------------
 // one warp per block: bits = sum hist*len; flags: bit0 = has a code > ENC_SHORT_MAX,
@@ -110,8 +106,8 @@ k_sf_offsets(const uint64_t *__restrict__ bits, const uint32_t *__restrict__ fla
 
 // ---- fast path ------------------------------------------------------------------------
 struct EncShared {
-    uint32_t lut[256 * ENC_COPIES];   // lut[sym*32 + lane]
-    uint32_t stage[ENC_STAGE_WORDS];  // big-endian words of this tile's bit range
+    uint32_t lut[256 * ENC_COPIES];       // lut[sym*32 + lane]
+    uint32_t stage[ENC_STAGE_WORDS + 8];  // big-endian words of (a window of) this tile's bit range
     uint32_t entry[256];
     uint32_t scan[ENC_THREADS / 32 + 1];
     uint64_t prefix;
@@ -119,7 +115,43 @@ struct EncShared {
     uint32_t block;
 };
 
-__global__ void __launch_bounds__(ENC_THREADS)
+// ld.global.nc with the default L1 policy: a thread reads 64 contiguous bytes as four
+// 16-byte vectors, so neighbouring vectors share sectors and should hit L1
+__device__ __forceinline__ uint4 ld_nc16(const void *p)
+{
+    uint4 v;
+    asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+
+// Place the thread's codes into the (zeroed) staging window, branch-free: a code of l bits at bit
+// offset o lands in word o>>5 (and spills into the next word when it straddles); both pieces are
+// OR-ed in with shared-memory atomics, so no data-dependent "a word is full" branch diverges the warp.
+// orel = bit offset of the thread's first bit relative to the window start (negative if before it).
+template <bool ALL_VALID>
+__device__ __forceinline__ void enc_pack_thread(EncShared &sh, const uint4 (&v)[ENC_VECS], uint64_t vmask, int32_t orel,
+                                                uint32_t nw, unsigned lane)
+{
+    int32_t o = orel;
+#pragma unroll
+    for (int c = 0; c < ENC_VECS; c++) {
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+            uint32_t ee = sh.lut[byte_of(v[c], j) * ENC_COPIES + lane];
+            if (!ALL_VALID) ee = ((vmask >> (c * 16 + j)) & 1ull) ? ee : 0u;
+            const uint32_t l = ee & 31u;
+            const uint32_t q = (uint32_t)o & 31u;
+            const uint32_t w = (uint32_t)(o >> 5);                      // arithmetic shift: before the window -> huge
+            const uint64_t v64 = (uint64_t)(ee >> 5) << ((64u - q - l) & 63u);  // q + l <= 57; l = 0 carries no bits
+            const uint32_t hi = (uint32_t)(v64 >> 32), lo = (uint32_t)v64;
+            if (hi && w < nw) atomicOr(&sh.stage[w], hi);
+            if (lo && w + 1u < nw) atomicOr(&sh.stage[w + 1u], lo);
+            o += (int32_t)l;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(ENC_THREADS, 3)
 k_sf_encode(const uint8_t *__restrict__ in, const uint64_t *__restrict__ off, const uint64_t *__restrict__ tile0,
             uint32_t nb, const uint8_t *__restrict__ lens, const uint64_t *__restrict__ codes,
             const uint64_t *__restrict__ pay_off, uint8_t *__restrict__ payload, uint64_t *__restrict__ desc,
@@ -131,6 +163,7 @@ k_sf_encode(const uint8_t *__restrict__ in, const uint64_t *__restrict__ off, co
     const uint64_t total_tiles = tile0[nb];
     uint32_t cur_block = 0xffffffffu;
     bool cur_long = false;
+
     for (;;) {
         __syncthreads();  // everyone is done with the previous tile's shared state
         if (tid == 0) {
@@ -166,29 +199,34 @@ k_sf_encode(const uint8_t *__restrict__ in, const uint64_t *__restrict__ off, co
         const bool is_last = (t + 1 == tile0[b + 1]);
         const uint64_t base = (lo / ENC_TILE + (t - first_tile)) * ENC_TILE;
         const uint64_t pos = base + (uint64_t)tid * ENC_ITEMS;
+        const bool all_valid = (pos >= lo) && (pos + ENC_ITEMS <= hi);
 
-        const bool any_valid = (pos + 16 > lo) && (pos < hi);
-        const bool all_valid = (pos >= lo) && (pos + 16 <= hi);
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (any_valid) v = ld_stream16(in + pos);
-        uint32_t e[ENC_ITEMS];
+        uint4 v[ENC_VECS];
+        uint64_t vmask = 0;  // bit k: symbol k of this thread lies inside the block
+#pragma unroll
+        for (int c = 0; c < ENC_VECS; c++) {
+            const uint64_t pc = pos + 16 * c;
+            v[c] = make_uint4(0, 0, 0, 0);
+            if (pc + 16 > lo && pc < hi) v[c] = ld_nc16(in + pc);
+        }
         uint32_t bits = 0;
         if (all_valid) {
+            vmask = ~0ull;
 #pragma unroll
-            for (int j = 0; j < ENC_ITEMS; j++) {
-                const uint32_t ee = sh.lut[byte_of(v, j) * ENC_COPIES + lane];
-                e[j] = ee;
-                bits += ee & 31u;
-            }
+            for (int c = 0; c < ENC_VECS; c++)
+#pragma unroll
+                for (int j = 0; j < 16; j++) bits += sh.lut[byte_of(v[c], j) * ENC_COPIES + lane] & 31u;
         } else {
 #pragma unroll
-            for (int j = 0; j < ENC_ITEMS; j++) {
-                const uint64_t p = pos + j;
-                const bool valid = any_valid && (p >= lo) && (p < hi);
-                const uint32_t ee = valid ? sh.lut[byte_of(v, j) * ENC_COPIES + lane] : 0u;
-                e[j] = ee;
-                bits += ee & 31u;
-            }
+            for (int c = 0; c < ENC_VECS; c++)
+#pragma unroll
+                for (int j = 0; j < 16; j++) {
+                    const uint64_t q = pos + 16 * c + j;
+                    if (q >= lo && q < hi) {
+                        vmask |= 1ull << (c * 16 + j);
+                        bits += sh.lut[byte_of(v[c], j) * ENC_COPIES + lane] & 31u;
+                    }
+                }
         }
         uint32_t tile_bits;
         const uint32_t excl = block_excl_scan<ENC_THREADS>(bits, sh.scan, &tile_bits);
@@ -197,65 +235,47 @@ k_sf_encode(const uint8_t *__restrict__ in, const uint64_t *__restrict__ off, co
             if (lane == 0) sh.prefix = pfx;
         }
         __syncthreads();
-        const uint64_t P = sh.prefix;               // bits of this block before this tile
+        const uint64_t P = sh.prefix;  // bits of this block before this tile
         const uint64_t E = P + tile_bits;
         const uint64_t W0 = P >> 5;
-        const uint32_t nwords = (uint32_t)(((E + 31) >> 5) - W0);
-        for (uint32_t k = tid; k < nwords; k += ENC_THREADS) sh.stage[k] = 0;
-        __syncthreads();
+        const uint64_t Wtouch = (E + 31) >> 5;                  // words holding bits of this tile: [W0, Wtouch)
+        const uint64_t Wown = is_last ? Wtouch : (E >> 5);      // words whose last bit lies in [P, E) (all, for the last tile)
+        const uint64_t p = P + excl;                            // my first bit
+        const uint64_t wf = p >> 5, wl = (p + bits + 31) >> 5;  // my words: [wf, wl)
+        uint32_t *out32 = reinterpret_cast<uint32_t *>(payload + pay_off[b]);
 
-        // ---- pack this thread's codes (right-aligned 64-bit accumulator; a word leaves whenever 32 bits are ready) ----
-        {
-            const uint64_t p = P + excl;
-            uint32_t wrel = (uint32_t)((p >> 5) - W0);
-            uint32_t filled = (uint32_t)(p & 31u);  // leading bits of the first word belong to the previous thread
-            bool shared_first = filled != 0;
-            uint64_t acc = 0;
-#pragma unroll
-            for (int j = 0; j < ENC_ITEMS; j++) {
-                const uint32_t l = e[j] & 31u;
-                acc = (acc << l) | (uint64_t)(e[j] >> 5);
-                filled += l;
-                if (filled >= 32) {
-                    const uint32_t w = (uint32_t)(acc >> (filled - 32));
-                    if (shared_first)
-                        atomicOr(&sh.stage[wrel], w);
-                    else
-                        sh.stage[wrel] = w;
-                    shared_first = false;
-                    wrel++;
-                    filled -= 32;
+        // the tile's bit range is materialised window by window (one window unless codes are very long here)
+        for (uint64_t win = W0; win < Wtouch; win += ENC_STAGE_WORDS) {
+            const uint32_t nw = (uint32_t)((Wtouch - win < (uint64_t)ENC_STAGE_WORDS) ? (Wtouch - win) : ENC_STAGE_WORDS);
+            for (uint32_t k = tid; k < nw; k += ENC_THREADS) sh.stage[k] = 0;
+            __syncthreads();
+            if (bits && wl > win && wf < win + nw) {
+                const int32_t orel = (int32_t)((int64_t)p - (int64_t)(win << 5));  // |orel| < 2^31: a tile holds < 2^19 bits
+                if (all_valid)
+                    enc_pack_thread<true>(sh, v, vmask, orel, nw, lane);
+                else
+                    enc_pack_thread<false>(sh, v, vmask, orel, nw, lane);
+            }
+            // leading partial word: bits of the symbols just before this tile
+            if (warp == 1 && win == W0 && !is_first && (P & 31u)) {
+                const uint32_t r = (uint32_t)(P & 31u);
+                uint32_t ee = 0;  // not the first tile => base > lo
+                if (base >= lo + 1 + lane) ee = sh.lut[(uint32_t)in[base - 1 - lane] * ENC_COPIES + lane];
+                const uint32_t l = ee & 31u;
+                const uint32_t s_incl = warp_incl_scan(l);
+                const uint32_t s_prev = s_incl - l;  // bits of nearer symbols
+                uint32_t w = 0;
+                if (l && s_prev < r) {
+                    const uint32_t room = r - s_prev;  // 1..31 bits of the word still free towards the MSB side
+                    w = ((ee >> 5) & ((1u << room) - 1u)) << (32 - r + s_prev);
                 }
+                w = __reduce_or_sync(FULL, w);
+                if (lane == 0 && w) atomicOr(&sh.stage[0], w);
             }
-            if (filled) {
-                const uint32_t w = (uint32_t)acc << (32 - filled);  // bits above `filled` fall off the top
-                if (w) atomicOr(&sh.stage[wrel], w);
-            }
-        }
-        // ---- leading partial word: bits of the symbols just before this tile ----
-        if (warp == 1 && !is_first && (P & 31u)) {
-            const uint32_t r = (uint32_t)(P & 31u);
-            const uint64_t tile_lo = base;  // not the first tile => base > lo
-            uint32_t ee = 0;
-            if (tile_lo >= lo + 1 + lane) ee = sh.lut[(uint32_t)in[tile_lo - 1 - lane] * ENC_COPIES + lane];
-            const uint32_t l = ee & 31u;
-            const uint32_t s_incl = warp_incl_scan(l);
-            const uint32_t s_prev = s_incl - l;  // bits of nearer symbols
-            uint32_t w = 0;
-            if (l && s_prev < r) {
-                const uint32_t room = r - s_prev;  // 1..31 bits of the word still free towards the MSB side
-                const uint32_t part = (ee >> 5) & ((1u << room) - 1u);
-                w = part << (32 - r + s_prev);
-            }
-            w = __reduce_or_sync(FULL, w);
-            if (lane == 0 && w) atomicOr(&sh.stage[0], w);
-        }
-        __syncthreads();
-        // ---- store the words this tile owns: those whose last bit lies in [P, E) ----
-        {
-            const uint64_t wend = is_last ? ((E + 31) >> 5) : (E >> 5);
-            uint32_t *out32 = reinterpret_cast<uint32_t *>(payload + pay_off[b]);
-            for (uint64_t w = W0 + tid; w < wend; w += ENC_THREADS) st_stream4(out32 + w, bswap32(sh.stage[w - W0]));
+            __syncthreads();
+            const uint64_t cend = (Wown < win + nw) ? Wown : (win + nw);
+            for (uint64_t w = win + tid; w < cend; w += ENC_THREADS) st_stream4(out32 + w, bswap32(sh.stage[w - win]));
+            if (win + ENC_STAGE_WORDS < Wtouch) __syncthreads();  // the next window re-zeroes the stage
         }
     }
     (void)err;  // a symbol without a code is caught by k_sf_block_bits (histogram x length) before this kernel runs

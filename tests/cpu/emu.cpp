@@ -70,23 +70,25 @@ static Bytes gen(std::mt19937 &rng, size_t n, int kind)
 }
 
 // ------------------------------------------------------------------ RLE encode emulation (rle_encode.cu)
+// 16 KiB tiles, 64 contiguous bytes per thread, 64-bit masks
 static uint32_t rng_noise = 0xa5a5a5a5u;
 static Bytes emu_rle_encode_block(const uint8_t *blk, uint64_t len)
 {
     Bytes out;
+    const int PT = RLE_ITEMS * RLE_VECS;  // 64
     const uint64_t ntiles = (len + RLE_TILE - 1) / RLE_TILE;
     std::vector<uint64_t> run_open(ntiles);  // chain #1: open run length at each tile's end
     for (uint64_t ti = 0; ti < ntiles; ti++) {
         const uint64_t tile_lo = ti * RLE_TILE;
         const uint32_t tile_len = (uint32_t)std::min<uint64_t>(RLE_TILE, len - tile_lo);
         const uint32_t valid_len = (uint32_t)std::min<uint64_t>(RLE_TILE + RLE_HALO, len - tile_lo);
-        uint32_t heads[RLE_HEAD_WORDS + 2] = {0};
+        std::vector<uint32_t> headsv(RLE_HEAD_WORDS + 2, 0);
+        uint32_t *heads = headsv.data();
         for (uint32_t p = 0; p < RLE_TILE + RLE_HALO; p++) {
             bool head = (p >= valid_len) || (p == 0 && ti == 0) || (blk[tile_lo + p] != blk[tile_lo + p - 1]);
             if (head) heads[p >> 5] |= 1u << (p & 31);
         }
-        // last head among valid tile positions
-        int lastv = -1;
+        int lastv = -1;  // last head among valid tile positions
         for (int p = (int)tile_len - 1; p >= 0; p--)
             if ((heads[p >> 5] >> (p & 31)) & 1) {
                 lastv = p;
@@ -101,52 +103,64 @@ static Bytes emu_rle_encode_block(const uint8_t *blk, uint64_t len)
             run_in = run_open[ti - 1];
             run_open[ti] = run_in + tile_len;
         }
-        // threads
         Bytes stage(2 * RLE_TILE + 64);
         uint32_t o = 0;
         int lh = -1;  // last head before the thread's first position
-        for (uint32_t tid = 0; tid < RLE_TILE / RLE_ITEMS; tid++) {
-            const uint32_t p0 = tid * 16;
-            const int nvalid = p0 >= tile_len ? 0 : (int)std::min<uint32_t>(16, tile_len - p0);
-            uint32_t c0 = 0;
+        auto Ebit = [&](int64_t a) -> uint64_t { return (a > 0 && a < (int64_t)len && blk[a] == blk[a - 1]) ? 1ull : 0ull; };
+        for (uint32_t tid = 0; tid < (uint32_t)RLE_THREADS; tid++) {
+            const uint32_t p0 = tid * PT;
+            const int nvalid = p0 >= tile_len ? 0 : (int)std::min<uint32_t>(PT, tile_len - p0);
+            uint64_t lit = 0, tri = 0;
             if (nvalid) {
-                const uint64_t k = lh >= 0 ? (uint64_t)(p0 - lh) : (uint64_t)p0 + run_in;
-                c0 = (uint32_t)(k % 255);
-            }
-            auto symf = [&](int j) -> uint32_t { return blk[tile_lo + p0 + j]; };
-            RleEmit em;
-            em.lit = em.tri = em.bytes = 0;
-            em.cnt[0] = em.cnt[1] = em.cnt[2] = em.cnt[3] = 0;
-            if (nvalid) {
-                // E bit of an absolute block position (0 at the block start and at/after the block end)
-                auto Ebit = [&](int64_t a) -> uint32_t { return (a > 0 && a < (int64_t)len && blk[a] == blk[a - 1]) ? 1u : 0u; };
-                uint32_t ewin = 0, z16 = 0;
-                for (int i = 6; i <= 26; i++) ewin |= Ebit((int64_t)tile_lo + p0 - 8 + i) << i;  // only bits 6..26 are specified
-                ewin |= 0xf800003fu & (rng_noise = rng_noise * 1664525u + 1013904223u);                                              // unspecified bits may hold anything
-                for (int j = 0; j < nvalid; j++) z16 |= (blk[tile_lo + p0 + j] == 0 ? 1u : 0u) << j;
-                const uint32_t valid16 = nvalid >= 16 ? 0xffffu : ((1u << nvalid) - 1u);
+                const uint64_t valid64 = nvalid >= 64 ? ~0ull : ((1ull << nvalid) - 1ull);
+                uint64_t E = 0, Z = 0;
+                for (int j = 0; j < nvalid; j++) {
+                    E |= Ebit((int64_t)tile_lo + p0 + j) << j;
+                    Z |= (uint64_t)(blk[tile_lo + p0 + j] == 0) << j;
+                }
+                const uint32_t before = (uint32_t)(Ebit((int64_t)tile_lo + p0 - 2) | (Ebit((int64_t)tile_lo + p0 - 1) << 1));
+                uint32_t after = 0;
+                for (int i = 0; i < 3; i++) after |= (uint32_t)Ebit((int64_t)tile_lo + p0 + 64 + i) << i;
+                rng_noise = rng_noise * 1664525u + 1013904223u;
                 const uint64_t k0 = lh >= 0 ? (uint64_t)(p0 - lh) : (uint64_t)p0 + run_in;
-                const uint32_t e0 = (ewin >> 8) & 1u;
-                if (e0 && k0 + 15 >= 255) {
-                    em = rle_emit_thread(heads, p0, nvalid, (uint32_t)(k0 % 255), symf);
+                const uint64_t my_heads = ~E;
+                // the general rule, group by group (this is also the kernel's slow path)
+                uint64_t glit = 0, gtri = 0;
+                for (int c = 0; c < RLE_VECS; c++) {
+                    const int nv = nvalid - 16 * c;
+                    if (nv <= 0) break;
+                    const uint64_t hb = c == 0 ? 0ull : (my_heads & ((1ull << (16 * c)) - 1ull));
+                    uint64_t kc;
+                    if (hb)
+                        kc = 16 * c - (63 - __builtin_clzll(hb));
+                    else
+                        kc = ((E & 1ull) ? k0 : 0) + 16 * c;  // if p0 is a head, hb is non-zero for c > 0 and k = 0 for c = 0
+                    auto symc = [&](int j) -> uint32_t { return blk[tile_lo + p0 + 16 * c + j]; };
+                    const RleEmit em = rle_emit_thread(heads, p0 + 16 * c, std::min(nv, 16), (uint32_t)(kc % 255), symc);
+                    glit |= (uint64_t)em.lit << (16 * c);
+                    gtri |= (uint64_t)em.tri << (16 * c);
+                }
+                if ((E & 1ull) && k0 + (PT - 1) >= 255) {
+                    lit = glit;
+                    tri = gtri;
                 } else {
-                    const RleMasks m = rle_fast_masks(ewin, z16, valid16);
-                    em.lit = m.lit;
-                    em.tri = m.tri;
-                    for (int j = 0; j < 16; j++)
-                        if ((m.tri >> j) & 1) em.cnt[j >> 2] |= rle_run_remaining(heads, p0 + j) << (8 * (j & 3));
-                    em.bytes = __builtin_popcount(m.lit) + 3 * __builtin_popcount(m.tri);
-                    // the general rule must agree wherever the fast rule is used
-                    RleEmit ref = rle_emit_thread(heads, p0, nvalid, c0, symf);
-                    CHECK(ref.lit == em.lit && ref.tri == em.tri && ref.bytes == em.bytes && !memcmp(ref.cnt, em.cnt, sizeof ref.cnt),
-                          "fast masks differ from the general rule (tile %llu tid %u)", (unsigned long long)ti, tid);
+                    const RleMasks64 m = rle_fast_masks64(E, before | (rng_noise & ~3u), after | (rng_noise & ~7u), Z & valid64, valid64);
+                    lit = m.lit;
+                    tri = m.tri;
+                    CHECK(lit == glit && tri == gtri, "fast masks differ from the general rule (tile %llu tid %u)", (unsigned long long)ti, tid);
                 }
             }
-            uint32_t w = rle_write_thread(em, stage.data() + o, symf);
-            CHECK(w == em.bytes, "rle write/emit mismatch");
-            o += w;
-            // advance lh over this thread's 16 positions (heads beyond tile_len pollute lh only for invalid threads)
-            for (uint32_t p = p0; p < p0 + 16; p++)
+            for (int j = 0; j < PT; j++) {
+                const uint32_t sy = (j < nvalid) ? blk[tile_lo + p0 + j] : 0;
+                if ((tri >> j) & 1) {
+                    stage[o++] = 0;
+                    stage[o++] = (uint8_t)sy;
+                    stage[o++] = (uint8_t)rle_run_remaining(heads, p0 + j);
+                } else if ((lit >> j) & 1) {
+                    stage[o++] = (uint8_t)sy;
+                }
+            }
+            for (uint32_t p = p0; p < p0 + (uint32_t)PT; p++)
                 if ((heads[p >> 5] >> (p & 31)) & 1) lh = (int)p;
         }
         out.insert(out.end(), stage.begin(), stage.begin() + o);
@@ -156,7 +170,7 @@ static Bytes emu_rle_encode_block(const uint8_t *blk, uint64_t len)
 
 static void test_rle_encode(std::mt19937 &rng)
 {
-    const size_t sizes[] = {1, 2, 15, 16, 17, 254, 255, 256, 4095, 4096, 4097, 4096 + 255, 8192, 8192 + 3, 12289, 40000, 70000};
+    const size_t sizes[] = {1, 2, 15, 16, 17, 63, 64, 65, 254, 255, 256, 4095, 4096, 4097, 16383, 16384, 16385, 16384 + 255, 32768 + 3, 40000, 70000};
     for (int kind = 0; kind < 5; kind++)
         for (size_t n : sizes) {
             Bytes d = gen(rng, n + 1, kind);
@@ -170,12 +184,12 @@ static void test_rle_encode(std::mt19937 &rng)
 }
 
 // ------------------------------------------------------------------ RLE decode emulation (rle_decode.cu)
-// stream = concatenated ragged blocks; windows are 4096-aligned in stream space
+// stream = concatenated ragged blocks; windows are 16 KiB-aligned in stream space, 64 bytes per thread
 static Bytes emu_rle_decode(const Bytes &stream, const std::vector<uint64_t> &off, std::vector<uint64_t> &fin, bool &trunc)
 {
     Bytes out;
     trunc = false;
-    const int T = 4096;
+    const int T = 16384, PT = 64, NT = 256;
     for (size_t b = 0; b + 1 < off.size(); b++) {
         const uint64_t lo = off[b], hi = off[b + 1];
         const uint64_t out_before = out.size();
@@ -186,31 +200,54 @@ static Bytes emu_rle_decode(const Bytes &stream, const std::vector<uint64_t> &of
         uint32_t tile_entry = 0;
         for (uint64_t w = lo / T; w <= (hi - 1) / T; w++) {
             const uint64_t base = w * T;
-            uint32_t maps[256], st = tile_entry;
-            int J0[256], N[256];
-            for (int tid = 0; tid < 256; tid++) {
-                const uint64_t pos = base + tid * 16;
+            std::vector<uint32_t> maps(NT);
+            std::vector<int> J0(NT), N(NT);
+            std::vector<uint64_t> ZZ(NT);
+            for (int tid = 0; tid < NT; tid++) {
+                const uint64_t pos = base + (uint64_t)tid * PT;
                 int j0 = 0, j1 = 0;
-                if (pos + 16 > lo && pos < hi) {
+                if (pos + PT > lo && pos < hi) {
                     j0 = lo > pos ? (int)(lo - pos) : 0;
-                    j1 = hi < pos + 16 ? (int)(hi - pos) : 16;
+                    j1 = hi < pos + PT ? (int)(hi - pos) : PT;
                 }
-                uint32_t z = 0;
+                uint64_t z = 0;
                 for (int j = j0; j < j1; j++)
-                    if (stream[pos + j] == 0) z |= 1u << (j - j0);
+                    if (stream[pos + j] == 0) z |= 1ull << (j - j0);
                 J0[tid] = j0;
                 N[tid] = j1 - j0;
-                maps[tid] = fsm_thread_map_fast(z, j1 - j0);
+                ZZ[tid] = z;
+                maps[tid] = fsm_map64(z, j1 - j0);
             }
-            uint32_t excl = FSM_IDENTITY;
-            for (int tid = 0; tid < 256; tid++) {
-                const uint64_t pos = base + tid * 16;
+            uint32_t excl = FSM_IDENTITY, st = tile_entry;
+            for (int tid = 0; tid < NT; tid++) {
+                const uint64_t pos = base + (uint64_t)tid * PT;
                 const uint32_t my_entry = fsm_apply(excl, tile_entry);
                 CHECK(my_entry == st, "fsm map scan disagrees with sequential state (tid %d)", tid);
-                uint32_t prevb = 0;
-                if (N[tid] > 0 && my_entry == 2 && pos + J0[tid] > lo) prevb = stream[pos + J0[tid] - 1];
-                auto bytef = [&](int q) -> uint32_t { return stream[pos + J0[tid] + q]; };
-                st = rle_parse_thread(my_entry, N[tid], prevb, bytef, [&](uint32_t len, uint32_t sym) { out.insert(out.end(), len, (uint8_t)sym); });
+                const int n = N[tid], j0 = J0[tid];
+                const FsmWalk wk = fsm_walk64(ZZ[tid], n, my_entry);
+                const RleDecMasks m = rle_dec_masks64(wk.esc, n, my_entry);
+                // sequential reference for this thread's bytes
+                {
+                    uint32_t s = my_entry;
+                    uint64_t rlit = 0, rrun = 0;
+                    for (int q = 0; q < n; q++) {
+                        const uint8_t v = stream[pos + j0 + q];
+                        if (s == 0) {
+                            if (v == 0) s = 1; else rlit |= 1ull << q;
+                        } else if (s == 1) s = 2;
+                        else { rrun |= 1ull << q; s = 0; }
+                    }
+                    CHECK(rlit == m.lit && rrun == m.run && s == wk.exit, "decode masks/exit differ from the sequential automaton (tid %d n %d entry %u)", tid, n, my_entry);
+                    st = s;
+                }
+                for (int q = 0; q < n; q++) {
+                    const uint8_t cur = stream[pos + j0 + q];
+                    if ((m.run >> q) & 1) {
+                        const uint8_t sym = stream[pos + j0 + q - 1];
+                        out.insert(out.end(), cur ? cur : 1, sym);
+                    } else if ((m.lit >> q) & 1)
+                        out.push_back(cur);
+                }
                 excl = fsm_compose(excl, maps[tid]);
             }
             CHECK(fsm_apply(excl, tile_entry) == st, "tile map exit mismatch");
@@ -356,9 +393,11 @@ static void test_sf_build(std::mt19937 &rng)
 }
 
 // ------------------------------------------------------------------ SF encode emulation (sf_encode.cu fast path)
-static Bytes emu_sf_encode(const Bytes &stream, uint64_t lo, uint64_t hi, const uint8_t *len, const uint64_t *code)
+// 16 KiB tiles, 64 contiguous symbols per thread, bit range materialised window by window
+static Bytes emu_sf_encode(const Bytes &stream, uint64_t lo, uint64_t hi, const uint8_t *len, const uint64_t *code,
+                           uint32_t stage_words = ENC_STAGE_WORDS)
 {
-    const int T = 4096;
+    const int T = ENC_TILE, NT = ENC_THREADS, IT = ENC_ITEMS;
     uint32_t lut[256];
     for (int s = 0; s < 256; s++) lut[s] = enc_entry(code[s], len[s]);
     uint64_t total_bits = 0;
@@ -370,73 +409,65 @@ static Bytes emu_sf_encode(const Bytes &stream, uint64_t lo, uint64_t hi, const 
     for (uint64_t w = w_first; w <= w_last; w++) {
         const uint64_t base = w * T;
         const bool is_first = w == w_first, is_last = w == w_last;
-        uint32_t e[256][16], bits[256];
+        std::vector<uint32_t> bits(NT, 0);
         uint32_t tile_bits = 0;
-        for (int tid = 0; tid < 256; tid++) {
-            bits[tid] = 0;
-            for (int j = 0; j < 16; j++) {
-                const uint64_t p = base + tid * 16 + j;
-                e[tid][j] = (p >= lo && p < hi) ? lut[stream[p]] : 0;
-                bits[tid] += e[tid][j] & 31;
+        for (int tid = 0; tid < NT; tid++) {
+            for (int k = 0; k < IT; k++) {
+                const uint64_t q = base + (uint64_t)tid * IT + k;
+                if (q >= lo && q < hi) bits[tid] += lut[stream[q]] & 31;
             }
             tile_bits += bits[tid];
         }
-        const uint64_t E = P + tile_bits, W0 = P >> 5;
-        std::vector<uint32_t> stage(((E + 31) >> 5) - W0 + 1, 0);
-        std::vector<int> plain(stage.size(), 0);
-        uint64_t excl = 0;
-        for (int tid = 0; tid < 256; tid++) {
-            const uint64_t p = P + excl;
-            uint32_t wrel = (uint32_t)((p >> 5) - W0), filled = p & 31;
-            bool shared_first = filled != 0;
-            uint64_t acc = 0;
-            for (int j = 0; j < 16; j++) {
-                const uint32_t l = e[tid][j] & 31;
-                acc = (acc << l) | (uint64_t)(e[tid][j] >> 5);
-                filled += l;
-                if (filled >= 32) {
-                    const uint32_t wv = (uint32_t)(acc >> (filled - 32));
-                    if (shared_first)
-                        stage[wrel] |= wv;
-                    else {
-                        CHECK(stage[wrel] == 0 && !plain[wrel], "plain store over a non-empty word");
-                        stage[wrel] = wv;
-                        plain[wrel] = 1;
+        const uint64_t E = P + tile_bits, W0 = P >> 5, Wtouch = (E + 31) >> 5, Wown = is_last ? Wtouch : (E >> 5);
+        for (uint64_t win = W0; win < Wtouch; win += stage_words) {
+            const uint32_t nw = (uint32_t)std::min<uint64_t>(Wtouch - win, stage_words);
+            std::vector<uint32_t> stage(nw, 0);
+            uint64_t excl = 0;
+            for (int tid = 0; tid < NT; tid++) {
+                const uint64_t p = P + excl;
+                const uint64_t wf = p >> 5, wl = (p + bits[tid] + 31) >> 5;
+                if (bits[tid] && wl > win && wf < win + nw) {
+                    int32_t o = (int32_t)((int64_t)p - (int64_t)(win << 5));
+                    for (int k = 0; k < IT; k++) {
+                        const uint64_t q64 = base + (uint64_t)tid * IT + k;
+                        const uint32_t ee = (q64 >= lo && q64 < hi) ? lut[stream[q64]] : 0;
+                        const uint32_t l = ee & 31, q = (uint32_t)o & 31u, wi = (uint32_t)(o >> 5);
+                        const uint64_t v64 = (uint64_t)(ee >> 5) << ((64u - q - l) & 63u);
+                        const uint32_t hiw = (uint32_t)(v64 >> 32), low = (uint32_t)v64;
+                        if (hiw && wi < nw) {
+                            CHECK((stage[wi] & hiw) == 0, "overlapping bits in a staging word");
+                            stage[wi] |= hiw;
+                        }
+                        if (low && wi + 1u < nw) {
+                            CHECK((stage[wi + 1] & low) == 0, "overlapping bits in a staging word");
+                            stage[wi + 1] |= low;
+                        }
+                        o += (int32_t)l;
                     }
-                    shared_first = false;
-                    wrel++;
-                    filled -= 32;
                 }
+                excl += bits[tid];
             }
-            if (filled) {
-                const uint32_t wv = (uint32_t)acc << (32 - filled);
-                if (wv) {
-                    CHECK(!plain[wrel], "atomicOr onto a plainly stored word");
-                    stage[wrel] |= wv;
+            if (win == W0 && !is_first && (P & 31)) {  // halo: lanes 0..31 look at the symbols before the tile
+                const uint32_t r = P & 31;
+                uint32_t s_prev = 0, wv = 0;
+                for (int lane = 0; lane < 32; lane++) {
+                    uint32_t ee = 0;
+                    if (base >= lo + 1 + lane) ee = lut[stream[base - 1 - lane]];
+                    const uint32_t l = ee & 31;
+                    if (l && s_prev < r) {
+                        const uint32_t room = r - s_prev;
+                        wv |= ((ee >> 5) & ((1u << room) - 1u)) << (32 - r + s_prev);
+                    }
+                    s_prev += l;
                 }
+                stage[0] |= wv;
             }
-            excl += bits[tid];
-        }
-        if (!is_first && (P & 31)) {  // halo: lanes 0..31 look at the symbols before the tile
-            const uint32_t r = P & 31;
-            uint32_t s_prev = 0, wv = 0;
-            for (int lane = 0; lane < 32; lane++) {
-                uint32_t ee = 0;
-                if (base >= lo + 1 + lane) ee = lut[stream[base - 1 - lane]];
-                const uint32_t l = ee & 31;
-                if (l && s_prev < r) {
-                    const uint32_t room = r - s_prev;
-                    wv |= ((ee >> 5) & ((1u << room) - 1u)) << (32 - r + s_prev);
-                }
-                s_prev += l;
+            const uint64_t cend = std::min<uint64_t>(Wown, win + nw);
+            for (uint64_t ww = win; ww < cend; ww++) {
+                CHECK(!written[ww], "output word %llu written twice", (unsigned long long)ww);
+                written[ww] = 1;
+                outw[ww] = stage[ww - win];
             }
-            stage[0] |= wv;
-        }
-        const uint64_t wend = is_last ? ((E + 31) >> 5) : (E >> 5);
-        for (uint64_t ww = W0; ww < wend; ww++) {
-            CHECK(!written[ww], "output word %llu written twice", (unsigned long long)ww);
-            written[ww] = 1;
-            outw[ww] = stage[ww - W0];
         }
         P = E;
     }
@@ -457,13 +488,15 @@ static void codes_to_strings(const uint8_t *len, const uint64_t *code, char (*ou
 
 // ------------------------------------------------------------------ SF decode emulation (sf_decode.cu)
 struct EmuTables {
-    std::vector<uint16_t> lut;
+    std::vector<uint16_t> lut, lut2;
     uint64_t sleft[256];
     uint8_t slen[256], ssym[256];
-    DecTables view() const
+    DecView view(const uint64_t *pairs) const
     {
-        DecTables t;
-        t.lut = lut.data();
+        DecView t;
+        t.pairs = pairs;
+        t.lut1 = lut.data();
+        t.lut2 = lut2.data();
         t.sleft = sleft;
         t.slen = slen;
         t.ssym = ssym;
@@ -508,20 +541,21 @@ static void emu_dec_tables(const uint8_t *len, const uint64_t *code, EmuTables &
         }
         T.lut[e] = entry;
     }
+    T.lut2.assign(DEC_LUT_SIZE, 0);
+    for (int e = 0; e < DEC_LUT_SIZE; e++) T.lut2[e] = dec_lut2_entry(T.lut.data(), (uint32_t)e);
 }
 
 static Bytes emu_sf_decode(const Bytes &payload, uint64_t n, const uint8_t *len, const uint64_t *code, bool &bad, int *stitch_passes)
 {
     EmuTables T;
     emu_dec_tables(len, code, T);
-    const DecTables t = T.view();
     const uint64_t z = payload.size();
     const uint64_t nseq = (z + DEC_SEQ_BYTES - 1) / DEC_SEQ_BYTES;
     std::vector<uint16_t> start(nseq * DEC_THREADS), count(nseq * DEC_THREADS);
     std::vector<uint32_t> seq_end(nseq);
-    auto load_words = [&](uint64_t seq, std::vector<uint32_t> &words) {
-        words.assign(DEC_SEQ_WORDS + DEC_WORDS_PAD, 0);
-        for (int i = 0; i < DEC_SEQ_WORDS + DEC_WORDS_PAD; i++) {
+    auto load_pairs = [&](uint64_t seq, std::vector<uint64_t> &pairs) {
+        std::vector<uint32_t> words(DEC_SEQ_WORDS + DEC_WORDS_PAD + 4, 0);
+        for (size_t i = 0; i < words.size(); i++) {
             uint32_t w = 0;
             for (int k = 0; k < 4; k++) {
                 const uint64_t bo = seq * DEC_SEQ_BYTES + (uint64_t)i * 4 + k;
@@ -529,18 +563,23 @@ static Bytes emu_sf_decode(const Bytes &payload, uint64_t n, const uint8_t *len,
             }
             words[i] = w;
         }
+        pairs.assign(DEC_SEQ_WORDS + DEC_WORDS_PAD, 0);
+        for (size_t i = 0; i < pairs.size(); i++) pairs[i] = ((uint64_t)words[i] << 32) | words[i + 1];
     };
     // phase 1
     for (uint64_t seq = 0; seq < nseq; seq++) {
-        std::vector<uint32_t> words;
-        load_words(seq, words);
+        std::vector<uint64_t> pairs;
+        load_pairs(seq, pairs);
+        const DecView t = T.view(pairs.data());
         const uint64_t bits_left = (z - seq * DEC_SEQ_BYTES) * 8;
         const uint32_t limit = (uint32_t)std::min<uint64_t>(bits_left, DEC_SEQ_BYTES * 8);
         uint32_t st[DEC_THREADS] = {0}, en[DEC_THREADS], cn[DEC_THREADS];
         auto run = [&](int tid) {
             const uint32_t sub_lo = tid * DEC_SUB_BITS, sub_hi = sub_lo + DEC_SUB_BITS;
             const uint32_t stop = std::min(sub_hi, limit);
-            DecSub r = dec_subsequence(words.data(), t, sub_lo + st[tid], stop, DecNoEmit());
+            DecSub r = dec_count_subsequence(t, sub_lo + st[tid], stop);
+            DecSub r1 = dec_emit_subsequence(t, sub_lo + st[tid], stop, DecNoEmit());
+            CHECK(r.end == r1.end && r.count == r1.count, "multi-symbol and single-symbol walks disagree");
             en[tid] = r.end > sub_hi ? r.end - sub_hi : 0;
             cn[tid] = r.count;
         };
@@ -571,15 +610,16 @@ static Bytes emu_sf_decode(const Bytes &payload, uint64_t n, const uint8_t *len,
         bool touched = false;
         for (uint64_t seq = 1; seq < nseq; seq++) {
             uint32_t cur = seq_end[seq - 1];
-            std::vector<uint32_t> words;
-            load_words(seq, words);
+            std::vector<uint64_t> pairs;
+            load_pairs(seq, pairs);
+            const DecView t = T.view(pairs.data());
             const uint64_t bits_left = (z - seq * DEC_SEQ_BYTES) * 8;
             const uint32_t limit = (uint32_t)std::min<uint64_t>(bits_left, DEC_SEQ_BYTES * 8);
             for (int k = 0; k < DEC_THREADS; k++) {
                 const uint64_t gi = seq * DEC_THREADS + k;
                 if (start[gi] == cur) break;
                 const uint32_t sub_lo = k * DEC_SUB_BITS, sub_hi = sub_lo + DEC_SUB_BITS;
-                DecSub r = dec_subsequence(words.data(), t, sub_lo + cur, std::min(sub_hi, limit), DecNoEmit());
+                DecSub r = dec_count_subsequence(t, sub_lo + cur, std::min(sub_hi, limit));
                 start[gi] = (uint16_t)cur;
                 count[gi] = (uint16_t)r.count;
                 touched = true;
@@ -596,8 +636,9 @@ static Bytes emu_sf_decode(const Bytes &payload, uint64_t n, const uint8_t *len,
     uint64_t first = 0;
     bad = false;
     for (uint64_t seq = 0; seq < nseq; seq++) {
-        std::vector<uint32_t> words;
-        load_words(seq, words);
+        std::vector<uint64_t> pairs;
+        load_pairs(seq, pairs);
+        const DecView t = T.view(pairs.data());
         const uint64_t bits_left = (z - seq * DEC_SEQ_BYTES) * 8;
         const uint32_t limit = (uint32_t)std::min<uint64_t>(bits_left, DEC_SEQ_BYTES * 8);
         for (int tid = 0; tid < DEC_THREADS; tid++) {
@@ -606,8 +647,8 @@ static Bytes emu_sf_decode(const Bytes &payload, uint64_t n, const uint8_t *len,
                 const uint32_t sub_lo = tid * DEC_SUB_BITS, sub_hi = sub_lo + DEC_SUB_BITS;
                 const uint64_t room = n - first;
                 uint8_t *dst = out.data() + first;
-                DecSub r = dec_subsequence(words.data(), t, sub_lo + start[gi], std::min(sub_hi, limit),
-                                           [&](uint32_t i, uint32_t sym) { if (i < room) dst[i] = (uint8_t)sym; });
+                DecSub r = dec_emit_subsequence(t, sub_lo + start[gi], std::min(sub_hi, limit),
+                                                [&](uint32_t i, uint32_t sym) { if (i < room) dst[i] = (uint8_t)sym; });
                 CHECK(r.count == count[gi], "final decode count differs from the recorded count");
                 if (r.bad) bad = true;
             }
@@ -658,6 +699,8 @@ static void test_sf_codec(std::mt19937 &rng)
         stream.resize(stream.size() + 64, 0xBB);
         Bytes got = emu_sf_encode(stream, lo, lo + n, len, code);
         CHECK(got == want, "sf_encode rep %d n %zu maxlen %d", rep, n, maxlen);
+        Bytes got2 = emu_sf_encode(stream, lo, lo + n, len, code, 37 + rep);   // tiny staging windows
+        CHECK(got2 == want, "sf_encode (windowed) rep %d n %zu maxlen %d", rep, n, maxlen);
         bool bad;
         int passes;
         Bytes dec = emu_sf_decode(want, n, len, code, bad, &passes);

@@ -193,6 +193,19 @@ def test_sf_encode_long_codes(shafa, orc, pkg):
     _check_sf_encode_decode(shafa, orc, stream, offs, True)
 
 
+def test_sf_encode_tile_with_long_codes_everywhere(shafa, orc):
+    """A 16 KiB tile made only of rare symbols (>= 13-bit codes) needs more than one staging window."""
+    rng = np.random.default_rng(3)
+    common = np.repeat(np.arange(6, dtype=np.uint8), [1_500_000, 750_000, 375_000, 187_000, 94_000, 47_000])
+    rng.shuffle(common)
+    rare = np.arange(10, 250, dtype=np.uint8)
+    body = np.concatenate([common[:1_000_003], np.tile(rare, 170), common[1_000_003:]])
+    offs = np.array([0, body.size], dtype=np.uint64)
+    ln, _, _ = _codes_for(orc, body, offs)
+    assert 12 < ln[0][rare].min() and ln[0].max() <= 26
+    _check_sf_encode_decode(shafa, orc, body, offs, False)
+
+
 def test_sf_encode_symbol_without_code(shafa, orc, pkg):
     data = pkg.datagen.zipf(50_000, seed=1)
     offs = np.array([0, data.size], dtype=np.uint64)
