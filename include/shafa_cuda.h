@@ -190,6 +190,11 @@ typedef struct {
 /* F -> T -> C for one host buffer (H2D, kernels, D2H inside). */
 int shafa_cuda_encode_host(shafa_cuda_ctx *ctx, const uint8_t *h_in, uint64_t n, uint64_t block_size,
                            int force_rle, int force_freq, shafa_cuda_encoded *out);
+/* The same for a shard of a file that does NOT contain the file's block 0 (multi-GPU: blocks are
+ * independent, the only file-wide decision is block 0's R/N gate, f.c:246-258): rle_mode is given by
+ * the owner of block 0 instead of being probed.  h_in must start on a block boundary of the file. */
+int shafa_cuda_encode_shard_host(shafa_cuda_ctx *ctx, const uint8_t *h_in, uint64_t n, uint64_t block_size,
+                                 int rle_mode, int force_freq, shafa_cuda_encoded *out);
 void shafa_cuda_encoded_free(shafa_cuda_encoded *e);
 
 /* D for host buffers: SF decode of B blocks (tables given as len/code arrays),

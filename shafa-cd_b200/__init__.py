@@ -8,7 +8,7 @@ pipeline behind a C ABI (include/shafa_cuda.h).  See DESIGN.md.
 
 Import through `__graft_entry__.load_package()` (the directory name has a hyphen).
 """
-from . import datagen  # noqa: F401
+from . import datagen, sharding  # noqa: F401
 from .binding import (  # noqa: F401
     DeviceBuffer,
     Encoded,

@@ -98,6 +98,7 @@ def load_library() -> C.CDLL:
     L.shafa_cuda_sf_decode_blocks.argtypes = [vp, u8p, vp, vp, vp, u64, vp, vp, u8p, u64]
     L.shafa_cuda_rle_decode_blocks.argtypes = [vp, u8p, vp, u64, u8p, u64, vp]
     L.shafa_cuda_encode_host.argtypes = [vp, vp, u64, u64, C.c_int, C.c_int, C.POINTER(EncodedC)]
+    L.shafa_cuda_encode_shard_host.argtypes = [vp, vp, u64, u64, C.c_int, C.c_int, C.POINTER(EncodedC)]
     L.shafa_cuda_encoded_free.argtypes = [C.POINTER(EncodedC)]
     L.shafa_cuda_decode_host.argtypes = [vp, vp, vp, vp, vp, u64, vp, vp, C.c_int, vp, u64, u64p, vp]
     L.shafa_cuda_rle_decode_host.argtypes = [vp, vp, vp, u64, vp, u64, u64p, vp]
@@ -436,6 +437,16 @@ class Shafa:
 
     def encode(self, data, block_size: int, force_rle=False, force_freq=False) -> Encoded:
         c = self.encode_raw(data, block_size, force_rle, force_freq)
+        try:
+            return Encoded(c)
+        finally:
+            self.encoded_free(c)
+
+    def encode_shard(self, data, block_size: int, rle_mode: bool, force_freq=False) -> Encoded:
+        """F -> T -> C for a shard that does not hold the file's block 0 (mode decided by its owner)."""
+        a = _u8(data)
+        c = EncodedC()
+        self._check(self.lib.shafa_cuda_encode_shard_host(self.ctx, a.ctypes.data, a.size, block_size, int(rle_mode), int(force_freq), C.byref(c)))
         try:
             return Encoded(c)
         finally:

@@ -461,14 +461,16 @@ void shafa_cuda_encoded_free(shafa_cuda_encoded *e)
 
 static inline uint64_t round16(uint64_t x) { return (x + 15) & ~15ull; }
 
-int shafa_cuda_encode_host(shafa_cuda_ctx *ctx, const uint8_t *h_in, uint64_t n, uint64_t block_size, int force_rle,
-                           int force_freq, shafa_cuda_encoded *out)
+// mode: -1 = probe block 0 (whole file), 0 / 1 = N / R decided elsewhere (shard without the file's block 0)
+static int encode_host_impl(shafa_cuda_ctx *ctx, const uint8_t *h_in, uint64_t n, uint64_t block_size, int force_rle,
+                            int force_freq, int mode, shafa_cuda_encoded *out)
 {
     CTX_ENTER(ctx);
     if (!out || !h_in) return SHAFA_OUTSIDE_MODULE;
     if (block_size < 512) block_size = 512;                       // utils/file.c:61-65
     if (block_size > 67108864ull) return SHAFA_FILE_STREAM_FAILED;
-    if (n < 1024) return SHAFA_FILE_TOO_SMALL;                    // f.c:220,366
+    if (mode < 0 && n < 1024) return SHAFA_FILE_TOO_SMALL;        // f.c:220,366 (a file-level rule)
+    if (n == 0) return SHAFA_FILE_TOO_SMALL;
     const uint64_t nb = (n + block_size - 1) / block_size;        // utils/file.c:80-85
     uint8_t *user_rle = out->rle, *user_payload = out->payload;
     const uint64_t user_rle_cap = out->rle_capacity, user_payload_cap = out->payload_capacity;
@@ -505,9 +507,13 @@ int shafa_cuda_encode_host(shafa_cuda_ctx *ctx, const uint8_t *h_in, uint64_t n,
         if ((rc = shafa_cuda_memcpy_h2d(ctx, d_in, h_in, n))) goto done;
 
         // ---- F: block-0 probe decides R/N for the whole file (f.c:246-258) ----
-        uint64_t rle0 = 0;
-        if ((rc = shafa_cuda_rle_encode_blocks(ctx, d_in, out->block_sizes[0], block_size, nullptr, 0, &rle0, nullptr))) goto done;
-        out->rle_mode = shafa_cuda_rle_gate(out->block_sizes[0], rle0, force_rle);
+        if (mode < 0) {
+            uint64_t rle0 = 0;
+            if ((rc = shafa_cuda_rle_encode_blocks(ctx, d_in, out->block_sizes[0], block_size, nullptr, 0, &rle0, nullptr))) goto done;
+            out->rle_mode = shafa_cuda_rle_gate(out->block_sizes[0], rle0, force_rle);
+        } else {
+            out->rle_mode = mode != 0;
+        }
 
         const uint8_t *d_sym = d_in;
         if (out->rle_mode) {
@@ -590,6 +596,18 @@ done:
         shafa_cuda_encoded_free(out);
     }
     return rc;
+}
+
+int shafa_cuda_encode_host(shafa_cuda_ctx *ctx, const uint8_t *h_in, uint64_t n, uint64_t block_size, int force_rle,
+                           int force_freq, shafa_cuda_encoded *out)
+{
+    return encode_host_impl(ctx, h_in, n, block_size, force_rle, force_freq, -1, out);
+}
+
+int shafa_cuda_encode_shard_host(shafa_cuda_ctx *ctx, const uint8_t *h_in, uint64_t n, uint64_t block_size, int rle_mode,
+                                 int force_freq, shafa_cuda_encoded *out)
+{
+    return encode_host_impl(ctx, h_in, n, block_size, 0, force_freq, rle_mode ? 1 : 0, out);
 }
 
 int shafa_cuda_rle_decode_host(shafa_cuda_ctx *ctx, const uint8_t *h_rle, const uint64_t *h_offsets, uint64_t nb,

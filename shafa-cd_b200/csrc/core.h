@@ -447,16 +447,23 @@ struct DecSub {
 // The sequence's payload is kept as an array of overlapping pairs: pairs[i] = (w[i] << 32) | w[i+1]
 // (big-endian words), so the 32 bits starting at any bit q are one 64-bit load and a funnel shift and
 // there is no refill branch to diverge a warp.
+// The pair array is stored transposed: thread t of a CTA walks words 4t .. 4t+5 of the sequence, so
+// word i lives at (i & 3) * 257 + (i >> 2): the 32 lanes of a warp then read 32 consecutive 64-bit
+// slots (no shared-memory bank conflicts) instead of slots 16 bytes apart.
+constexpr int DEC_PAIR_ROW = DEC_THREADS + 1;            // 257
+constexpr int DEC_PAIR_SLOTS = 4 * DEC_PAIR_ROW;         // 1028 >= DEC_SEQ_WORDS + DEC_WORDS_PAD
+SHAFA_HD uint32_t dec_pair_slot(uint32_t i) { return (i & 3u) * (uint32_t)DEC_PAIR_ROW + (i >> 2); }
+
 SHAFA_HD uint32_t dec_window32(const uint64_t *pairs, uint32_t q)
 {
-    const uint64_t pr = pairs[q >> 5];
+    const uint64_t pr = pairs[dec_pair_slot(q >> 5)];
     return (uint32_t)((pr << (q & 31u)) >> 32);
 }
 SHAFA_HD uint64_t dec_window64(const uint64_t *pairs, uint32_t q)
 {
     const uint32_t i = q >> 5, sh = q & 31u;
-    const uint64_t hi = pairs[i];
-    return sh ? ((hi << sh) | ((pairs[i + 1] & 0xffffffffull) >> (32 - sh))) : hi;  // low word of pairs[i+1] is w[i+2]
+    const uint64_t hi = pairs[dec_pair_slot(i)];
+    return sh ? ((hi << sh) | ((pairs[dec_pair_slot(i + 1)] & 0xffffffffull) >> (32 - sh))) : hi;  // low word of pair i+1 is w[i+2]
 }
 
 // Tables of one block as seen by a decoding thread (shared memory on the GPU).

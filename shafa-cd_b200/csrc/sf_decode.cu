@@ -101,7 +101,7 @@ struct DecPlan {
 constexpr int DEC_STAGE = 16384;  // symbols of one sequence staged in shared memory before the coalesced copy-out
 
 struct DecShared {
-    uint64_t pairs[DEC_SEQ_WORDS + DEC_WORDS_PAD];  // pairs[i] = (w[i] << 32) | w[i+1], big-endian words
+    uint64_t pairs[DEC_PAIR_SLOTS];  // pair i = (w[i] << 32) | w[i+1] (big-endian words) at slot dec_pair_slot(i)
     uint32_t words[DEC_SEQ_WORDS + DEC_WORDS_PAD + 4];
     uint16_t lut1[DEC_LUT_SIZE];
     uint16_t lut2[DEC_LUT_SIZE];
@@ -157,7 +157,7 @@ __device__ __forceinline__ void dec_load_words(DecShared &sh, const uint8_t *pay
 __device__ __forceinline__ void dec_build_pairs(DecShared &sh)
 {
     for (int i = threadIdx.x; i < DEC_SEQ_WORDS + DEC_WORDS_PAD; i += DEC_THREADS)
-        sh.pairs[i] = ((uint64_t)sh.words[i] << 32) | (uint64_t)sh.words[i + 1];
+        sh.pairs[dec_pair_slot((uint32_t)i)] = ((uint64_t)sh.words[i] << 32) | (uint64_t)sh.words[i + 1];
 }
 
 __device__ __forceinline__ DecView dec_view_of(const DecShared &sh)

@@ -563,8 +563,8 @@ static Bytes emu_sf_decode(const Bytes &payload, uint64_t n, const uint8_t *len,
             }
             words[i] = w;
         }
-        pairs.assign(DEC_SEQ_WORDS + DEC_WORDS_PAD, 0);
-        for (size_t i = 0; i < pairs.size(); i++) pairs[i] = ((uint64_t)words[i] << 32) | words[i + 1];
+        pairs.assign(DEC_PAIR_SLOTS, 0);
+        for (size_t i = 0; i < (size_t)(DEC_SEQ_WORDS + DEC_WORDS_PAD); i++) pairs[dec_pair_slot((uint32_t)i)] = ((uint64_t)words[i] << 32) | words[i + 1];
     };
     // phase 1
     for (uint64_t seq = 0; seq < nseq; seq++) {
