@@ -85,6 +85,17 @@ void *pinned_get(shafa_cuda_ctx *ctx, size_t bytes)
     return p;
 }
 
+shafa_cuda_ctx *worker_ctx(shafa_cuda_ctx *ctx, int i)
+{
+    if (i < 0 || i >= 4) return nullptr;
+    if (!ctx->workers[i]) {
+        shafa_cuda_ctx *w = nullptr;
+        if (shafa_cuda_create(ctx->device, &w) != SHAFA_SUCCESS) return nullptr;
+        ctx->workers[i] = w;
+    }
+    return ctx->workers[i];
+}
+
 uint32_t *misc_ptr(shafa_cuda_ctx *ctx, int which)
 {
     uint32_t *base = (uint32_t *)scratch_get(ctx, SCR_MISC, MISC_WORDS * sizeof(uint32_t));
@@ -216,6 +227,8 @@ int shafa_cuda_create(int device, shafa_cuda_ctx **out)
 int shafa_cuda_destroy(shafa_cuda_ctx *ctx)
 {
     if (!ctx) return SHAFA_SUCCESS;
+    for (int i = 0; i < 4; i++)
+        if (ctx->workers[i]) shafa_cuda_destroy(ctx->workers[i]);
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     prof_resolve(ctx);
@@ -601,12 +614,18 @@ done:
 int shafa_cuda_encode_host(shafa_cuda_ctx *ctx, const uint8_t *h_in, uint64_t n, uint64_t block_size, int force_rle,
                            int force_freq, shafa_cuda_encoded *out)
 {
+    if (out && out->payload && out->payload_capacity && out->rle && out->rle_capacity && n >= (64ull << 20) && ctx &&
+        ctx->stream == ctx->own_stream)
+        return encode_host_pipelined(ctx, h_in, n, block_size, force_rle, force_freq, -1, out);
     return encode_host_impl(ctx, h_in, n, block_size, force_rle, force_freq, -1, out);
 }
 
 int shafa_cuda_encode_shard_host(shafa_cuda_ctx *ctx, const uint8_t *h_in, uint64_t n, uint64_t block_size, int rle_mode,
                                  int force_freq, shafa_cuda_encoded *out)
 {
+    if (out && out->payload && out->payload_capacity && out->rle && out->rle_capacity && n >= (64ull << 20) && ctx &&
+        ctx->stream == ctx->own_stream)
+        return encode_host_pipelined(ctx, h_in, n, block_size, 0, force_freq, rle_mode ? 1 : 0, out);
     return encode_host_impl(ctx, h_in, n, block_size, 0, force_freq, rle_mode ? 1 : 0, out);
 }
 
@@ -640,6 +659,13 @@ int shafa_cuda_decode_host(shafa_cuda_ctx *ctx, const uint8_t *h_payload, const 
     CTX_ENTER(ctx);
     if (h_out_size) *h_out_size = 0;
     if (nb == 0) return SHAFA_SUCCESS;
+    {
+        uint64_t sym_total = 0;
+        for (uint64_t b = 0; b < nb; b++) sym_total += h_n[b];
+        if (nb >= 8 && sym_total >= (64ull << 20) && ctx->stream == ctx->own_stream)
+            return decode_host_pipelined(ctx, h_payload, h_payload_offsets, h_z, h_n, nb, h_len, h_code, rle_expand, h_out,
+                                         out_capacity, h_out_size, h_final_sizes);
+    }
     uint64_t ptotal = 0, stotal = 0;
     for (uint64_t b = 0; b < nb; b++) {
         const uint64_t e = h_payload_offsets[b] + round16(h_z[b]);

@@ -1,0 +1,370 @@
+// host_pipeline.cu -- chunked, overlapped versions of the whole-shard host-buffer calls.
+//
+// The reference overlaps per-block work with ordered output through its pthread join chain
+// (utils/multithread.c:70-87).  Here the blocks of a shard are cut into chunks; worker threads,
+// each with its own context (stream + scratch), run chunk after chunk through
+//   H2D copy -> kernels -> D2H copy,
+// so the copies of one chunk overlap the kernels and the opposite-direction copies of the others
+// (PCIe is full duplex).  Results land directly at their final place in the caller's buffers:
+// a chunk learns where its .rle bytes / payload slots / decoded bytes start from its predecessor
+// through a small "base offset" chain, which is the only ordering between chunks (the analogue of
+// the reference's write-in-block-order rule).
+#include <stdlib.h>
+
+#include <atomic>
+#include <condition_variable>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+#include "internal.h"
+
+namespace shafa {
+
+namespace {
+
+constexpr int PIPE_MAX_WORKERS = 4;  // = number of worker contexts a context can own
+
+// tunables (environment overrides are for experiments; defaults were picked on a B200 / PCIe Gen5 host)
+int pipe_workers()
+{
+    const char *e = getenv("SHAFA_PIPE_WORKERS");
+    int w = e ? atoi(e) : 4;
+    return w < 1 ? 1 : (w > PIPE_MAX_WORKERS ? PIPE_MAX_WORKERS : w);
+}
+uint64_t pipe_chunk_bytes()
+{
+    const char *e = getenv("SHAFA_PIPE_CHUNK_MB");
+    const long mb = e ? atol(e) : 64;
+    return (uint64_t)(mb < 1 ? 1 : mb) << 20;
+}
+
+struct Chain {
+    std::mutex m;
+    std::condition_variable cv;
+    std::vector<uint64_t> base;
+    std::vector<char> ready;
+    bool dead = false;
+    explicit Chain(size_t n) : base(n + 1, 0), ready(n + 1, 0) { ready[0] = 1; }
+    bool wait(size_t c, uint64_t *v)
+    {
+        std::unique_lock<std::mutex> lk(m);
+        cv.wait(lk, [&] { return dead || ready[c]; });
+        if (!ready[c]) return false;
+        *v = base[c];
+        return true;
+    }
+    void publish(size_t c, uint64_t v)
+    {
+        {
+            std::lock_guard<std::mutex> lk(m);
+            base[c] = v;
+            ready[c] = 1;
+        }
+        cv.notify_all();
+    }
+    void abort()
+    {
+        {
+            std::lock_guard<std::mutex> lk(m);
+            dead = true;
+        }
+        cv.notify_all();
+    }
+};
+
+inline uint64_t round16(uint64_t x) { return (x + 15) & ~15ull; }
+
+struct Chunks {
+    uint64_t per;    // blocks per chunk
+    uint64_t count;  // number of chunks
+};
+
+Chunks plan_chunks(uint64_t nb, uint64_t bytes)
+{
+    const uint64_t chunk = pipe_chunk_bytes();
+    uint64_t want = (bytes + chunk - 1) / chunk;
+    if (want < 2 * (uint64_t)pipe_workers()) want = 2 * (uint64_t)pipe_workers();  // enough chunks to keep both copy directions busy
+    if (want > nb) want = nb;
+    if (want < 1) want = 1;
+    Chunks c;
+    c.per = (nb + want - 1) / want;
+    c.count = (nb + c.per - 1) / c.per;
+    return c;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------
+// encode
+// ---------------------------------------------------------------------------------------------------
+int encode_host_pipelined(shafa_cuda_ctx *ctx, const uint8_t *h_in, uint64_t n, uint64_t block_size, int force_rle,
+                          int force_freq, int mode, shafa_cuda_encoded *out)
+{
+    if (!ctx || !out || !h_in) return SHAFA_OUTSIDE_MODULE;
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return SHAFA_THREAD_CREATION_FAILED;
+    if (block_size < 512) block_size = 512;  // utils/file.c:61-65
+    if (block_size > 67108864ull) return SHAFA_FILE_STREAM_FAILED;
+    if (mode < 0 && n < 1024) return SHAFA_FILE_TOO_SMALL;  // f.c:220,366
+    if (n == 0) return SHAFA_FILE_TOO_SMALL;
+    const uint64_t nb = (n + block_size - 1) / block_size;  // utils/file.c:80-85
+    uint8_t *const user_rle = out->rle, *const user_payload = out->payload;
+    const uint64_t rle_cap = out->rle_capacity, pay_cap = out->payload_capacity;
+    memset(out, 0, sizeof *out);
+    out->n = n;
+    out->block_size = block_size;
+    out->n_blocks = nb;
+    out->block_sizes = (uint64_t *)malloc(nb * sizeof(uint64_t));
+    out->sym_sizes = (uint64_t *)malloc(nb * sizeof(uint64_t));
+    out->hist = (uint64_t *)malloc(nb * 256 * sizeof(uint64_t));
+    out->code_len = (uint8_t *)malloc(nb * 256);
+    out->code_bits = (uint64_t *)malloc(nb * 256 * sizeof(uint64_t));
+    out->payload_offsets = (uint64_t *)malloc(nb * sizeof(uint64_t));
+    out->z = (uint64_t *)malloc(nb * sizeof(uint64_t));
+    if (force_freq) out->hist_orig = (uint64_t *)malloc(nb * 256 * sizeof(uint64_t));
+    int rc = SHAFA_SUCCESS;
+    if (!out->block_sizes || !out->sym_sizes || !out->hist || !out->code_len || !out->code_bits || !out->payload_offsets ||
+        !out->z || (force_freq && !out->hist_orig))
+        rc = SHAFA_LACK_OF_MEMORY;
+    if (!rc) {
+        for (uint64_t b = 0; b < nb; b++) out->block_sizes[b] = (b == nb - 1) ? n - b * block_size : block_size;
+        // ---- block 0 decides R/N for the whole file (f.c:246-258) ----
+        if (mode < 0) {
+            const uint64_t n0 = out->block_sizes[0];
+            uint8_t *d0 = (uint8_t *)scratch_get(ctx, SCR_STAGE_A, round16(n0) + 64);
+            uint64_t rle0 = 0;
+            if (!d0)
+                rc = SHAFA_LACK_OF_MEMORY;
+            else if (!(rc = shafa_cuda_memcpy_h2d(ctx, d0, h_in, n0)) &&
+                     !(rc = shafa_cuda_rle_encode_blocks(ctx, d0, n0, block_size, nullptr, 0, &rle0, nullptr)))
+                mode = shafa_cuda_rle_gate(n0, rle0, force_rle);
+        }
+    }
+    if (rc) {
+        shafa_cuda_encoded_free(out);
+        return rc;
+    }
+    out->rle_mode = mode != 0;
+    if (!out->rle_mode && out->hist_orig) {  // N mode: the one .freq IS the original's (f.c:322-331)
+        free(out->hist_orig);
+        out->hist_orig = nullptr;
+    }
+    out->rle = out->rle_mode ? user_rle : nullptr;
+    out->rle_capacity = rle_cap;
+    out->payload = user_payload;
+    out->payload_capacity = pay_cap;
+
+    const Chunks ch = plan_chunks(nb, n);
+    Chain rle_chain(ch.count), pay_chain(ch.count);
+    std::atomic<uint64_t> next{0};
+    std::atomic<int> err{0};
+    const bool rle_mode = out->rle_mode, want_orig = out->hist_orig != nullptr;
+
+    auto fail = [&](int code) {
+        int expected = 0;
+        err.compare_exchange_strong(expected, code);
+        rle_chain.abort();
+        pay_chain.abort();
+    };
+
+    auto work = [&](int widx) {
+        shafa_cuda_ctx *w = worker_ctx(ctx, widx);
+        if (!w) return fail(SHAFA_LACK_OF_MEMORY);
+        for (;;) {
+            const uint64_t c = next.fetch_add(1);
+            if (c >= ch.count || err.load()) return;
+            const uint64_t b0 = c * ch.per, b1 = (b0 + ch.per < nb) ? b0 + ch.per : nb, cb = b1 - b0;
+            const uint64_t lo = b0 * block_size, hi = (b1 * block_size < n) ? b1 * block_size : n, cn = hi - lo;
+            int r;
+            uint8_t *d_in = (uint8_t *)scratch_get(w, SCR_STAGE_A, round16(cn) + 64);
+            uint64_t *d_hist = (uint64_t *)scratch_get(w, SCR_STAGE_C, cb * 256 * sizeof(uint64_t));
+            uint64_t *d_code = (uint64_t *)scratch_get(w, SCR_STAGE_D, cb * 256 * (sizeof(uint64_t) + 1));
+            if (!d_in || !d_hist || !d_code) return fail(SHAFA_LACK_OF_MEMORY);
+            uint8_t *d_len = (uint8_t *)(d_code + cb * 256);
+            if ((r = shafa_cuda_memcpy_h2d(w, d_in, h_in + lo, cn))) return fail(r);
+            std::vector<uint64_t> offsets(cb + 1, 0);
+            const uint8_t *d_sym = d_in;
+            if (rle_mode) {
+                const uint64_t cap = 2 * cn + 3 * cb + 64;  // f.c:244 per block
+                uint8_t *d_rle = (uint8_t *)scratch_get(w, SCR_STAGE_B, cap);
+                if (!d_rle) return fail(SHAFA_LACK_OF_MEMORY);
+                if ((r = shafa_cuda_rle_encode_blocks(w, d_in, cn, block_size, d_rle, cap, out->sym_sizes + b0, d_hist))) return fail(r);
+                uint64_t tot = 0;
+                for (uint64_t b = 0; b < cb; b++) tot += out->sym_sizes[b0 + b];
+                uint64_t base;
+                if (!rle_chain.wait(c, &base)) return;
+                if (base + tot > rle_cap) return fail(SHAFA_LACK_OF_MEMORY);
+                rle_chain.publish(c + 1, base + tot);
+                if ((r = shafa_cuda_memcpy_d2h(w, out->rle + base, d_rle, tot))) return fail(r);
+                d_sym = d_rle;
+                if (want_orig) {  // f.c:322-331: the original's histograms too
+                    uint64_t *d_ho = (uint64_t *)scratch_get(w, SCR_STAGE_E, cb * 256 * sizeof(uint64_t));
+                    if (!d_ho) return fail(SHAFA_LACK_OF_MEMORY);
+                    for (uint64_t b = 0; b < cb; b++) offsets[b + 1] = offsets[b] + out->block_sizes[b0 + b];
+                    if ((r = shafa_cuda_histogram_blocks(w, d_in, offsets.data(), cb, d_ho))) return fail(r);
+                    if ((r = shafa_cuda_memcpy_d2h(w, out->hist_orig + b0 * 256, d_ho, cb * 256 * sizeof(uint64_t)))) return fail(r);
+                }
+            } else {
+                memcpy(out->sym_sizes + b0, out->block_sizes + b0, cb * sizeof(uint64_t));
+            }
+            for (uint64_t b = 0; b < cb; b++) offsets[b + 1] = offsets[b] + out->sym_sizes[b0 + b];
+            if (!rle_mode && (r = shafa_cuda_histogram_blocks(w, d_in, offsets.data(), cb, d_hist))) return fail(r);
+            if ((r = shafa_cuda_memcpy_d2h(w, out->hist + b0 * 256, d_hist, cb * 256 * sizeof(uint64_t)))) return fail(r);
+            // ---- T ----
+            if ((r = shafa_cuda_sf_build_codes(w, d_hist, cb, d_len, d_code))) return fail(r);
+            if ((r = shafa_cuda_memcpy_d2h(w, out->code_bits + b0 * 256, d_code, cb * 256 * sizeof(uint64_t)))) return fail(r);
+            if ((r = shafa_cuda_memcpy_d2h(w, out->code_len + b0 * 256, d_len, cb * 256))) return fail(r);
+            // ---- C ----  Fano codes average <= H + 1 <= 9 bits/symbol
+            const uint64_t pcap = offsets[cb] + offsets[cb] / 8 + 32 * cb + 4096;
+            uint8_t *d_payload = (uint8_t *)scratch_get(w, SCR_STAGE_F, pcap);
+            if (!d_payload) return fail(SHAFA_LACK_OF_MEMORY);
+            if ((r = shafa_cuda_sf_encode_blocks(w, d_sym, offsets.data(), cb, d_len, d_code, d_hist, d_payload, pcap,
+                                                 out->payload_offsets + b0, out->z + b0)))
+                return fail(r);
+            const uint64_t ptot = out->payload_offsets[b1 - 1] + round16(out->z[b1 - 1]);
+            uint64_t pbase;
+            if (!pay_chain.wait(c, &pbase)) return;
+            if (pbase + ptot > pay_cap) return fail(SHAFA_LACK_OF_MEMORY);
+            pay_chain.publish(c + 1, pbase + ptot);
+            for (uint64_t b = b0; b < b1; b++) out->payload_offsets[b] += pbase;
+            if ((r = shafa_cuda_memcpy_d2h(w, out->payload + pbase, d_payload, ptot))) return fail(r);
+            if ((r = shafa_cuda_synchronize(w))) return fail(r);
+        }
+    };
+
+    {
+        std::vector<std::thread> threads;
+        const int nw = (int)((ch.count < (uint64_t)pipe_workers()) ? ch.count : pipe_workers());
+        for (int i = 0; i < nw; i++) threads.emplace_back(work, i);
+        for (auto &t : threads) t.join();
+    }
+    rc = err.load();
+    if (rc) {
+        if (ctx->workers[0]) set_error(ctx, rc, "pipelined encode: %s", shafa_cuda_last_error(ctx->workers[0]));
+        out->rle = nullptr;  // caller-owned buffers stay with the caller
+        out->payload = nullptr;
+        shafa_cuda_encoded_free(out);
+        return rc;
+    }
+    out->rle_total = rle_mode ? rle_chain.base[ch.count] : 0;
+    out->payload_total = pay_chain.base[ch.count];
+    out->owns_rle = out->owns_payload = 0;
+    return SHAFA_SUCCESS;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// decode
+// ---------------------------------------------------------------------------------------------------
+int decode_host_pipelined(shafa_cuda_ctx *ctx, const uint8_t *h_payload, const uint64_t *h_payload_offsets,
+                          const uint64_t *h_z, const uint64_t *h_n, uint64_t nb, const uint8_t *h_len,
+                          const uint64_t *h_code, int rle_expand, uint8_t *h_out, uint64_t out_capacity,
+                          uint64_t *h_out_size, uint64_t *h_final_sizes)
+{
+    if (!ctx) return SHAFA_OUTSIDE_MODULE;
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return SHAFA_THREAD_CREATION_FAILED;
+    if (h_out_size) *h_out_size = 0;
+    uint64_t sym_total = 0;
+    for (uint64_t b = 0; b < nb; b++) sym_total += h_n[b];
+    const Chunks ch = plan_chunks(nb, sym_total);
+    Chain out_chain(ch.count);
+    std::atomic<uint64_t> next{0};
+    std::atomic<int> err{0};
+    std::vector<uint64_t> fin_local;
+    uint64_t *fin = h_final_sizes;
+    if (!fin) {
+        fin_local.assign(nb, 0);
+        fin = fin_local.data();
+    }
+    auto fail = [&](int code) {
+        int expected = 0;
+        err.compare_exchange_strong(expected, code);
+        out_chain.abort();
+    };
+    auto work = [&](int widx) {
+        shafa_cuda_ctx *w = worker_ctx(ctx, widx);
+        if (!w) return fail(SHAFA_LACK_OF_MEMORY);
+        for (;;) {
+            const uint64_t c = next.fetch_add(1);
+            if (c >= ch.count || err.load()) return;
+            const uint64_t b0 = c * ch.per, b1 = (b0 + ch.per < nb) ? b0 + ch.per : nb, cb = b1 - b0;
+            int r;
+            // payload slice of this chunk: slots are laid out in block order by the encoder / the .shaf reader;
+            // be general and take min/max over the chunk's blocks
+            uint64_t plo = ~0ull, phi = 0, stot = 0;
+            for (uint64_t b = b0; b < b1; b++) {
+                if (h_payload_offsets[b] < plo) plo = h_payload_offsets[b];
+                const uint64_t e = h_payload_offsets[b] + h_z[b];
+                if (e > phi) phi = e;
+                stot += h_n[b];
+            }
+            if (phi < plo) phi = plo;
+            std::vector<uint64_t> poff(cb), offsets(cb + 1, 0);
+            for (uint64_t b = 0; b < cb; b++) {
+                poff[b] = h_payload_offsets[b0 + b] - plo;
+                offsets[b + 1] = offsets[b] + h_n[b0 + b];
+            }
+            uint8_t *d_payload = (uint8_t *)scratch_get(w, SCR_STAGE_A, round16(phi - plo) + 64);
+            uint8_t *d_sym = (uint8_t *)scratch_get(w, SCR_STAGE_B, round16(stot) + 64);
+            uint64_t *d_code = (uint64_t *)scratch_get(w, SCR_STAGE_D, cb * 256 * (sizeof(uint64_t) + 1));
+            if (!d_payload || !d_sym || !d_code) return fail(SHAFA_LACK_OF_MEMORY);
+            uint8_t *d_len = (uint8_t *)(d_code + cb * 256);
+            if ((r = shafa_cuda_memcpy_h2d(w, d_payload, h_payload + plo, phi - plo))) return fail(r);
+            if ((r = shafa_cuda_memcpy_h2d(w, d_code, h_code + b0 * 256, cb * 256 * sizeof(uint64_t)))) return fail(r);
+            if ((r = shafa_cuda_memcpy_h2d(w, d_len, h_len + b0 * 256, cb * 256))) return fail(r);
+            if ((r = shafa_cuda_sf_decode_blocks(w, d_payload, poff.data(), h_z + b0, h_n + b0, cb, d_len, d_code, d_sym,
+                                                 round16(stot) + 64)))
+                return fail(r);
+            uint64_t produced = stot;
+            const uint8_t *d_result = d_sym;
+            if (rle_expand) {
+                // expansion of this chunk: sizes are not known in advance -> the reference's own first guess per block
+                // (d.c:129-136), then the exact size if that was too small
+                uint64_t cap = 0;
+                for (uint64_t b = 0; b < cb; b++) {
+                    const uint64_t s = h_n[b0 + b];
+                    cap += (s <= 65536 ? 65536 : s <= 655360 ? 655360 : s <= 8388608 ? 8388608 : 67108864) + 1024;
+                }
+                uint8_t *d_out = (uint8_t *)scratch_get(w, SCR_STAGE_F, round16(cap) + 64);
+                if (!d_out) return fail(SHAFA_LACK_OF_MEMORY);
+                r = shafa_cuda_rle_decode_blocks(w, d_sym, offsets.data(), cb, d_out, cap, fin + b0);
+                if (r == SHAFA_LACK_OF_MEMORY) {
+                    cap = 0;
+                    for (uint64_t b = 0; b < cb; b++) cap += fin[b0 + b];
+                    d_out = (uint8_t *)scratch_get(w, SCR_STAGE_F, round16(cap) + 64);
+                    if (!d_out) return fail(SHAFA_LACK_OF_MEMORY);
+                    r = shafa_cuda_rle_decode_blocks(w, d_sym, offsets.data(), cb, d_out, cap, fin + b0);
+                }
+                if (r) return fail(r);
+                produced = 0;
+                for (uint64_t b = 0; b < cb; b++) produced += fin[b0 + b];
+                d_result = d_out;
+            } else {
+                for (uint64_t b = 0; b < cb; b++) fin[b0 + b] = h_n[b0 + b];
+            }
+            uint64_t base;
+            if (!out_chain.wait(c, &base)) return;
+            out_chain.publish(c + 1, base + produced);
+            if (base + produced <= out_capacity) {
+                if ((r = shafa_cuda_memcpy_d2h(w, h_out + base, d_result, produced))) return fail(r);
+                if ((r = shafa_cuda_synchronize(w))) return fail(r);
+            }  // else: keep going so that the total size is reported (the caller may retry with a larger buffer)
+        }
+    };
+    {
+        std::vector<std::thread> threads;
+        const int nw = (int)((ch.count < (uint64_t)pipe_workers()) ? ch.count : pipe_workers());
+        for (int i = 0; i < nw; i++) threads.emplace_back(work, i);
+        for (auto &t : threads) t.join();
+    }
+    const int rc = err.load();
+    if (rc) {
+        if (ctx->workers[0]) set_error(ctx, rc, "pipelined decode: %s", shafa_cuda_last_error(ctx->workers[0]));
+        return rc;
+    }
+    const uint64_t total = out_chain.base[ch.count];
+    if (h_out_size) *h_out_size = total;
+    if (total > out_capacity) return set_error(ctx, SHAFA_LACK_OF_MEMORY, "decode: output needs %llu bytes", (unsigned long long)total);
+    return SHAFA_SUCCESS;
+}
+
+}  // namespace shafa

@@ -57,6 +57,10 @@ struct shafa_cuda_ctx {
     std::vector<shafa_kernel_stat> stats;
     std::vector<shafa::PendingTiming> pending;
     std::vector<cudaEvent_t> event_pool;
+    // worker contexts (own stream + scratch) of the pipelined host-buffer calls; owned by this context
+    shafa_cuda_ctx *workers[4] = {nullptr, nullptr, nullptr, nullptr};
+    // per-context (= per-device) cache of kernel attributes / occupancy, see shafa::OccId
+    int occ[16] = {0};
 };
 
 namespace shafa {
@@ -100,8 +104,18 @@ enum ErrBits : uint32_t {
     ERR_CAPACITY = 32,       // output buffer too small
     ERR_RLE_TRUNCATED = 64   // RLE block ends inside a triple
 };
+enum OccId { OCC_SF_ENCODE = 0, OCC_RLE_ENC = 1 /* +variant 0..3 */, OCC_RLE_DEC = 5, OCC_DEC_SYNC = 6, OCC_DEC_WRITE = 7 };
 enum MiscSlot { MISC_COUNTER = 0, MISC_FLAG = 16, MISC_ERR = 32, MISC_WORDS = 64 };  // uint32 indices into SCR_MISC
 uint32_t *misc_ptr(shafa_cuda_ctx *ctx, int which);
+shafa_cuda_ctx *worker_ctx(shafa_cuda_ctx *ctx, int i);  // lazily created child context i (0..3) on the same device
+
+// host_pipeline.cu: chunked, overlapped versions of the whole-shard host calls (nullptr-safe fallbacks live in api.cu)
+int encode_host_pipelined(shafa_cuda_ctx *ctx, const uint8_t *h_in, uint64_t n, uint64_t block_size, int force_rle,
+                          int force_freq, int mode, shafa_cuda_encoded *out);
+int decode_host_pipelined(shafa_cuda_ctx *ctx, const uint8_t *h_payload, const uint64_t *h_payload_offsets,
+                          const uint64_t *h_z, const uint64_t *h_n, uint64_t nb, const uint8_t *h_len,
+                          const uint64_t *h_code, int rle_expand, uint8_t *h_out, uint64_t out_capacity,
+                          uint64_t *h_out_size, uint64_t *h_final_sizes);
 
 // hist.cu
 int launch_histogram(shafa_cuda_ctx *ctx, const uint8_t *d_in, const uint64_t *h_off, uint64_t nb, uint64_t *d_hist);

@@ -312,7 +312,7 @@ int launch_rle_decode(shafa_cuda_ctx *ctx, const uint8_t *d_rle, const uint64_t 
 {
     if (nb == 0) return SHAFA_SUCCESS;
     if (((uintptr_t)d_rle & 15) || ((uintptr_t)d_out & 15)) return set_error(ctx, SHAFA_FILE_STREAM_FAILED, "rle_decode: buffers must be 16-byte aligned");
-    static int occ = 0;
+    int &occ = ctx->occ[OCC_RLE_DEC];
     if (!occ) {
         SHAFA_CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_rle_decode, RLD_THREADS, 0));
         if (occ < 1) occ = 1;

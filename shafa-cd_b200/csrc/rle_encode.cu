@@ -319,7 +319,7 @@ int launch_rle_encode(shafa_cuda_ctx *ctx, const uint8_t *d_in, uint64_t n, uint
     const uint64_t total_tiles = (nb - 1) * tpb + (last_len + RLE_TILE - 1) / RLE_TILE;
     if (tpb > 0xffffffffull || total_tiles > 0xfffffff0ull) return set_error(ctx, SHAFA_LACK_OF_MEMORY, "rle_encode: too many tiles");
 
-    static int occ[4] = {0, 0, 0, 0};
+    int *occ = ctx->occ + OCC_RLE_ENC;
     const size_t smem = sizeof(RleEncShared);
     const int variant = (d_rle ? 2 : 0) | (d_hist ? 1 : 0);
     void (*kern)(const uint8_t *, uint64_t, uint64_t, uint32_t, uint64_t, uint8_t *, uint64_t, unsigned long long *,

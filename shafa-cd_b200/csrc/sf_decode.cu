@@ -471,7 +471,7 @@ int launch_sf_decode(shafa_cuda_ctx *ctx, const uint8_t *d_payload, const uint64
     uint32_t *seq_end = (uint32_t *)(seqbuf + nseq * 8);
     uint32_t *seq_count = seq_end + nseq;
 
-    static int occ_sync = 0, occ_write = 0;
+    int &occ_sync = ctx->occ[OCC_DEC_SYNC], &occ_write = ctx->occ[OCC_DEC_WRITE];
     const size_t smem_w = sizeof(DecWriteShared);
     if (!occ_sync) {
         SHAFA_CUDA_TRY(ctx, cudaFuncSetAttribute(k_dec_write, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w));

@@ -358,7 +358,7 @@ int launch_sf_encode(shafa_cuda_ctx *ctx, const uint8_t *d_sym, const uint64_t *
                      const uint8_t *d_len, const uint64_t *d_code, const uint64_t *d_payload_off, const uint64_t *d_z,
                      uint8_t *d_payload, bool any_long, uint32_t *d_err)
 {
-    static int max_ctas_per_sm = 0;
+    int &max_ctas_per_sm = ctx->occ[OCC_SF_ENCODE];
     const size_t smem = sizeof(EncShared);
     if (!max_ctas_per_sm) {
         SHAFA_CUDA_TRY(ctx, cudaFuncSetAttribute(k_sf_encode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -72,3 +72,30 @@ def test_c5_mixed_decode_only(shafa, pkg):
     out, _ = shafa.rle_decode_host(sym, offs, data.size + 64)                    # -d r
     assert np.array_equal(out, data)
     assert np.array_equal(shafa.decode(enc), data)                               # -m d
+
+
+def test_pipelined_host_calls_match_serial(shafa, pkg):
+    """With caller-provided output buffers the host-buffer calls run chunked on worker streams
+    (csrc/host_pipeline.cu); the result must be identical to the serial path."""
+    for gen, n, bs in (("textlike", 200 * MIB + 12345, pkg.datagen.BLOCK_m), ("zipf", 96 * MIB, pkg.datagen.BLOCK_K)):
+        data = pkg.datagen.GENERATORS[gen](n, seed=21)
+        serial = shafa.encode(data, bs)                                          # library-owned buffers: serial path
+        rle_buf = np.empty(2 * n + 4096, dtype=np.uint8)
+        pay_buf = np.empty(n + n // 4 + 65536, dtype=np.uint8)
+        c = shafa.encode_raw(data, bs, rle_buf=rle_buf, payload_buf=pay_buf)     # pipelined path
+        try:
+            piped = pkg.Encoded(c)
+        finally:
+            shafa.encoded_free(c)
+        assert piped.rle_mode == serial.rle_mode and piped.n_blocks == serial.n_blocks
+        assert piped.rle_bytes() == serial.rle_bytes()
+        assert piped.freq_text() == serial.freq_text() and piped.cod_text() == serial.cod_text()
+        assert piped.shaf_bytes() == serial.shaf_bytes()
+        assert np.array_equal(shafa.decode(piped), data)                         # decode_host is pipelined for >= 8 blocks
+        if piped.rle_mode:
+            assert np.array_equal(shafa.decode(piped, rle_expand=False), piped.rle)
+        # too small an output buffer: the needed size is still reported (error 2), nothing is written past the end
+        with pytest.raises(pkg.ShafaError) as e:
+            shafa.decode_tables(piped.payload, piped.payload_offsets, piped.z, piped.sym_sizes, piped.code_len, piped.code_bits,
+                                piped.rle_mode, 1 << 20)
+        assert e.value.code == 2
