@@ -247,29 +247,21 @@ k_rle_decode(const uint8_t *__restrict__ in, const uint64_t *__restrict__ off, c
                 uint8_t *sb = sh.stage - w0;  // sb[x] is span-space position x
                 uint32_t o = a;
                 if (full && single) {
+                    // literals: one uniform, fully predicated pass -- the offset of position q is
+                    // (literals before q) + (bytes of the runs before q), kept as a running sum
 #pragma unroll
                     for (int c = 0; c < RLD_VECS; c++) {
                         const uint32_t l16 = (uint32_t)(m.lit >> (16 * c)) & 0xffffu, r16 = (uint32_t)(m.run >> (16 * c)) & 0xffffu;
-                        if (r16 == 0 && l16 == 0xffffu) {  // sixteen literals: straight from registers
+                        if (__all_sync(__activemask(), r16 == 0 && l16 == 0xffffu)) {  // whole warp: sixteen literals each
 #pragma unroll
                             for (int j = 0; j < 16; j++) sb[o + j] = (uint8_t)byte_of(v[c], j);
                             o += 16;
-                        } else {  // compact loop over the emitting positions (kept small: the I-cache matters here)
-                            uint32_t eb = l16 | r16;
-#pragma unroll 1
-                            while (eb) {
-                                const int j = ctz32(eb);
-                                eb &= eb - 1;
-                                const uint32_t q = 16 * c + j;
-                                const uint32_t cur = in[pos + q];
-                                if ((r16 >> j) & 1u) {
-                                    const uint32_t sym = q ? (uint32_t)in[pos + q - 1] : prevb;
-                                    const uint32_t len = cur ? cur : 1u;
-                                    rld_fill(sb + o, sym, len);
-                                    o += len;
-                                } else {
-                                    sb[o++] = (uint8_t)cur;
-                                }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 16; j++) {
+                                const uint32_t cur = byte_of(v[c], j);
+                                if ((l16 >> j) & 1u) sb[o] = (uint8_t)cur;
+                                o += ((l16 >> j) & 1u) + (((r16 >> j) & 1u) ? (cur ? cur : 1u) : 0u);
                             }
                         }
                     }
@@ -290,6 +282,54 @@ k_rle_decode(const uint8_t *__restrict__ in, const uint64_t *__restrict__ off, c
                             rld_emit<true>(sb, w0, w1, o, 1u, cur);
                             o += 1;
                         }
+                    }
+                }
+            }
+            if (single) {
+                // runs.  Short ones (<= 16 bytes: the common case in text) are written by their own lane, all
+                // lanes in parallel; long ones are filled by the whole warp, one run at a time.
+                uint64_t long_runs = 0;
+                if (full) {
+                    uint64_t rb = m.run;
+                    uint32_t cum = 0;
+#pragma unroll 1
+                    while (rb) {
+                        const int q = ctz64(rb);
+                        rb &= rb - 1;
+                        const uint32_t cnt = in[pos + q];  // L1 hit: the line was just loaded
+                        const uint32_t len = cnt ? cnt : 1u;
+                        if (len <= 16) {
+                            const uint32_t sym = q ? (uint32_t)in[pos + q - 1] : prevb;
+                            uint8_t *d = sh.stage + shift + my_out + (uint32_t)__popcll(m.lit & ((1ull << q) - 1ull)) + cum;
+                            for (uint32_t k = 0; k < len; k++) d[k] = (uint8_t)sym;
+                        } else {
+                            long_runs |= 1ull << q;
+                        }
+                        cum += len;
+                    }
+                }
+                unsigned has = __ballot_sync(FULL, long_runs != 0);
+                while (has) {
+                    const int src = __ffs(has) - 1;
+                    has &= has - 1;
+                    uint64_t rb = __shfl_sync(FULL, m.run, src);  // that lane's count-byte positions
+                    const uint64_t lr = __shfl_sync(FULL, long_runs, src);
+                    const uint64_t lt = __shfl_sync(FULL, m.lit, src);
+                    const uint32_t a_src = __shfl_sync(FULL, shift + my_out, src);
+                    const uint32_t prev_src = __shfl_sync(FULL, prevb, src);
+                    const uint64_t pos_src = pos - ((uint64_t)lane - (uint64_t)src) * RLD_PER_THREAD;
+                    uint32_t cum = 0;  // bytes of the runs before the current one
+                    while (rb) {
+                        const int q = ctz64(rb);
+                        rb &= rb - 1;
+                        const uint32_t cnt = in[pos_src + q];  // every lane reads the same byte (broadcast)
+                        const uint32_t len = cnt ? cnt : 1u;
+                        if ((lr >> q) & 1ull) {
+                            const uint32_t sym = q ? (uint32_t)in[pos_src + q - 1] : prev_src;
+                            const uint32_t o = a_src + (uint32_t)__popcll(lt & ((1ull << q) - 1ull)) + cum;
+                            for (uint32_t k = lane; k < len; k += 32) sh.stage[o + k] = (uint8_t)sym;
+                        }
+                        cum += len;
                     }
                 }
             }

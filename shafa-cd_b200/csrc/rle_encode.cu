@@ -237,31 +237,35 @@ k_rle_encode(const uint8_t *__restrict__ in, uint64_t n, uint64_t block_size, ui
         // ---- 5. stage + copy out + fused histogram ----
         const uint32_t shift = (uint32_t)(out0 & 15u);  // co-align staging with the destination
         {
-            uint8_t *dst = sh.stage + shift + excl;
+            // literals: one uniform, fully predicated pass with a running offset; a triple just reserves 3 bytes
+            uint8_t *const dst0 = sh.stage + shift + excl;
+            uint32_t o = 0;
 #pragma unroll
             for (int c = 0; c < RLE_VECS; c++) {
                 const uint32_t l16 = (uint32_t)(lit >> (16 * c)) & 0xffffu, t16 = (uint32_t)(tri >> (16 * c)) & 0xffffu;
-                if (t16 == 0 && l16 == 0xffffu) {  // sixteen literals: straight from registers
+                if (__all_sync(__activemask(), t16 == 0 && l16 == 0xffffu)) {  // whole warp: sixteen literals each
 #pragma unroll
-                    for (int j = 0; j < 16; j++) dst[j] = (uint8_t)byte_of(v[c], j);
-                    dst += 16;
-                } else {  // compact loop over the emitting positions (kept small: the I-cache matters here)
-                    uint32_t eb = l16 | t16;
-#pragma unroll 1
-                    while (eb) {
-                        const int j = ctz32(eb);
-                        eb &= eb - 1;
-                        const uint32_t s = in[pos + 16 * c + j];  // L1 hit: the line was just loaded
-                        if ((t16 >> j) & 1u) {
-                            dst[0] = 0;
-                            dst[1] = (uint8_t)s;
-                            dst[2] = (uint8_t)rle_run_remaining(sh.heads, p0 + 16 * c + j);
-                            dst += 3;
-                        } else {
-                            *dst++ = (uint8_t)s;
-                        }
+                    for (int j = 0; j < 16; j++) dst0[o + j] = (uint8_t)byte_of(v[c], j);
+                    o += 16;
+                } else if (__any_sync(__activemask(), (l16 | t16) != 0)) {
+#pragma unroll
+                    for (int j = 0; j < 16; j++) {
+                        if ((l16 >> j) & 1u) dst0[o] = (uint8_t)byte_of(v[c], j);
+                        o += ((l16 >> j) & 1u) + 3u * ((t16 >> j) & 1u);
                     }
                 }
+            }
+            // triples: sparse loop over their positions (the count needs a look-ahead in the head bitmask)
+            uint64_t tb = tri;
+#pragma unroll 1
+            while (tb) {
+                const int q = ctz64(tb);
+                tb &= tb - 1;
+                const uint64_t below = (1ull << q) - 1ull;
+                uint8_t *d = dst0 + (uint32_t)__popcll(lit & below) + 3u * (uint32_t)__popcll(tri & below);
+                d[0] = 0;
+                d[1] = in[pos + q];  // L1 hit: the line was just loaded
+                d[2] = (uint8_t)rle_run_remaining(sh.heads, p0 + (uint32_t)q);
             }
         }
         __syncthreads();

@@ -124,28 +124,45 @@ __device__ __forceinline__ uint4 ld_nc16(const void *p)
     return v;
 }
 
+// Shared memory through explicit 32-bit shared addresses: one ADD per access instead of the
+// generic->shared window arithmetic the compiler emits for dynamic shared memory, and the
+// conditional OR as ONE predicated instruction instead of a branch around an atomic.
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t lds32(uint32_t saddr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr));
+    return v;
+}
+__device__ __forceinline__ void red_or_if(uint32_t saddr, uint32_t value, bool cond)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p red.shared.or.b32 [%0], %1;\n\t}" ::"r"(saddr), "r"(value),
+                 "r"((uint32_t)cond)
+                 : "memory");
+}
+
 // Place the thread's codes into the (zeroed) staging window, branch-free: a code of l bits at bit
 // offset o lands in word o>>5 (and spills into the next word when it straddles); both pieces are
-// OR-ed in with shared-memory atomics, so no data-dependent "a word is full" branch diverges the warp.
+// OR-ed in with shared-memory reductions, so no data-dependent "a word is full" branch diverges the warp.
 // orel = bit offset of the thread's first bit relative to the window start (negative if before it).
 template <bool ALL_VALID>
-__device__ __forceinline__ void enc_pack_thread(EncShared &sh, const uint4 (&v)[ENC_VECS], uint64_t vmask, int32_t orel,
-                                                uint32_t nw, unsigned lane)
+__device__ __forceinline__ void enc_pack_thread(uint32_t lut_lane, uint32_t stage_s, const uint4 (&v)[ENC_VECS], uint64_t vmask,
+                                                int32_t orel, uint32_t nw)
 {
     int32_t o = orel;
 #pragma unroll
     for (int c = 0; c < ENC_VECS; c++) {
 #pragma unroll
         for (int j = 0; j < 16; j++) {
-            uint32_t ee = sh.lut[byte_of(v[c], j) * ENC_COPIES + lane];
+            uint32_t ee = lds32(lut_lane + byte_of(v[c], j) * (ENC_COPIES * 4));
             if (!ALL_VALID) ee = ((vmask >> (c * 16 + j)) & 1ull) ? ee : 0u;
             const uint32_t l = ee & 31u;
             const uint32_t q = (uint32_t)o & 31u;
-            const uint32_t w = (uint32_t)(o >> 5);                      // arithmetic shift: before the window -> huge
+            const uint32_t w = (uint32_t)(o >> 5);                             // arithmetic shift: before the window -> huge
             const uint64_t v64 = (uint64_t)(ee >> 5) << ((64u - q - l) & 63u);  // q + l <= 57; l = 0 carries no bits
             const uint32_t hi = (uint32_t)(v64 >> 32), lo = (uint32_t)v64;
-            if (hi && w < nw) atomicOr(&sh.stage[w], hi);
-            if (lo && w + 1u < nw) atomicOr(&sh.stage[w + 1u], lo);
+            red_or_if(stage_s + w * 4u, hi, hi != 0 && w < nw);
+            red_or_if(stage_s + w * 4u + 4u, lo, lo != 0 && w + 1u < nw);
             o += (int32_t)l;
         }
     }
@@ -209,13 +226,14 @@ k_sf_encode(const uint8_t *__restrict__ in, const uint64_t *__restrict__ off, co
             v[c] = make_uint4(0, 0, 0, 0);
             if (pc + 16 > lo && pc < hi) v[c] = ld_nc16(in + pc);
         }
+        const uint32_t lut_lane = smem_u32(sh.lut) + lane * 4u;  // this lane's private LUT column
         uint32_t bits = 0;
         if (all_valid) {
             vmask = ~0ull;
 #pragma unroll
             for (int c = 0; c < ENC_VECS; c++)
 #pragma unroll
-                for (int j = 0; j < 16; j++) bits += sh.lut[byte_of(v[c], j) * ENC_COPIES + lane] & 31u;
+                for (int j = 0; j < 16; j++) bits += lds32(lut_lane + byte_of(v[c], j) * (ENC_COPIES * 4)) & 31u;
         } else {
 #pragma unroll
             for (int c = 0; c < ENC_VECS; c++)
@@ -224,10 +242,14 @@ k_sf_encode(const uint8_t *__restrict__ in, const uint64_t *__restrict__ off, co
                     const uint64_t q = pos + 16 * c + j;
                     if (q >= lo && q < hi) {
                         vmask |= 1ull << (c * 16 + j);
-                        bits += sh.lut[byte_of(v[c], j) * ENC_COPIES + lane] & 31u;
+                        bits += lds32(lut_lane + byte_of(v[c], j) * (ENC_COPIES * 4)) & 31u;
                     }
                 }
         }
+        // keep the compiler from carrying 64 precomputed table addresses from this pass to the packing pass
+        // (they do not fit in registers and were spilled to local memory)
+#pragma unroll
+        for (int c = 0; c < ENC_VECS; c++) asm volatile("" : "+r"(v[c].x), "+r"(v[c].y), "+r"(v[c].z), "+r"(v[c].w));
         uint32_t tile_bits;
         const uint32_t excl = block_excl_scan<ENC_THREADS>(bits, sh.scan, &tile_bits);
         if (warp == 0) {
@@ -252,9 +274,9 @@ k_sf_encode(const uint8_t *__restrict__ in, const uint64_t *__restrict__ off, co
             if (bits && wl > win && wf < win + nw) {
                 const int32_t orel = (int32_t)((int64_t)p - (int64_t)(win << 5));  // |orel| < 2^31: a tile holds < 2^19 bits
                 if (all_valid)
-                    enc_pack_thread<true>(sh, v, vmask, orel, nw, lane);
+                    enc_pack_thread<true>(lut_lane, smem_u32(sh.stage), v, vmask, orel, nw);
                 else
-                    enc_pack_thread<false>(sh, v, vmask, orel, nw, lane);
+                    enc_pack_thread<false>(lut_lane, smem_u32(sh.stage), v, vmask, orel, nw);
             }
             // leading partial word: bits of the symbols just before this tile
             if (warp == 1 && win == W0 && !is_first && (P & 31u)) {
