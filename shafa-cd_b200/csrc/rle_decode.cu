@@ -83,7 +83,7 @@ __device__ __forceinline__ void rld_emit(uint8_t *stage_base, uint32_t wlo, uint
     }
 }
 
-__global__ void __launch_bounds__(RLD_THREADS, 3)
+__global__ void __launch_bounds__(RLD_THREADS, 4)
 k_rle_decode(const uint8_t *__restrict__ in, const uint64_t *__restrict__ off, const uint64_t *__restrict__ tile0,
              uint32_t nb, uint8_t *__restrict__ out, uint64_t out_capacity, uint64_t *__restrict__ blk_end,
              uint64_t *__restrict__ desc_state_chain, uint64_t *__restrict__ desc_out, uint32_t *__restrict__ counter,
