@@ -469,10 +469,12 @@ SHAFA_HD uint64_t dec_window64(const uint64_t *pairs, uint32_t q)
 // Tables of one block as seen by a decoding thread (shared memory on the GPU).
 //   lut1[4096]  (sym << 8) | len, len 1..12; 0 = no code; 0xFF = longer than 12 bits
 //   lut2[4096]  (nsym << 8) | bits: how many whole codes fit in the 12-bit window and their total length; 0 = use lut1
+//   lut3[4096]  (bits << 24) | (nsym << 16) | (sym1 << 8) | sym0: the first one or two whole codes of the window; 0 = use lut1
 struct DecView {
     const uint64_t *pairs;
     const uint16_t *lut1;
     const uint16_t *lut2;
+    const uint32_t *lut3;
     const uint64_t *sleft;
     const uint8_t *slen;
     const uint8_t *ssym;
@@ -529,7 +531,8 @@ SHAFA_HD DecSub dec_count_subsequence(const V &t, uint32_t start, uint32_t stop)
     return r;
 }
 
-// Decode the symbols that start in [start, stop); emit(i, sym) for the i-th one.
+// Decode the symbols that start in [start, stop); emit(i, sym) for the i-th one.  While a whole 12-bit
+// window lies before `stop`, the first two codes inside it are taken at once (lut3).
 template <typename V, typename Emit>
 SHAFA_HD DecSub dec_emit_subsequence(const V &t, uint32_t start, uint32_t stop, Emit emit)
 {
@@ -537,6 +540,22 @@ SHAFA_HD DecSub dec_emit_subsequence(const V &t, uint32_t start, uint32_t stop, 
     r.count = 0;
     r.bad = 0;
     uint32_t q = start;
+    if (t.lut3) {
+        while (q + (uint32_t)DEC_LUT_BITS <= stop) {
+            const uint32_t e3 = t.lut3[dec_window32(t.pairs, q) >> (32 - DEC_LUT_BITS)];
+            if (e3) {
+                emit(r.count, e3 & 0xFFu);
+                if (e3 & 0x20000u) emit(r.count + 1, (e3 >> 8) & 0xFFu);
+                r.count += (e3 >> 16) & 0xFFu;
+                q += e3 >> 24;
+            } else {
+                uint32_t sym;
+                q += dec_one(t, q, &sym, &r.bad);
+                emit(r.count, sym);
+                r.count++;
+            }
+        }
+    }
     while (q < stop) {
         uint32_t sym;
         q += dec_one(t, q, &sym, &r.bad);
@@ -562,6 +581,19 @@ SHAFA_HD uint16_t dec_lut2_entry(const uint16_t *lut1, uint32_t e)
         n++;
     }
     return (uint16_t)(n ? ((n << 8) | pos) : 0);
+}
+
+// lut3 entry for the 12-bit window value e: its first one or two whole codes
+SHAFA_HD uint32_t dec_lut3_entry(const uint16_t *lut1, uint32_t e)
+{
+    const uint32_t e0 = lut1[e];
+    const uint32_t l0 = e0 & 0xFFu;
+    if (l0 - 1u >= (uint32_t)DEC_LUT_BITS) return 0;
+    const uint32_t e1 = lut1[(e << l0) & (DEC_LUT_SIZE - 1)];
+    const uint32_t l1 = e1 & 0xFFu;
+    if (l1 - 1u < (uint32_t)DEC_LUT_BITS && l0 + l1 <= (uint32_t)DEC_LUT_BITS)
+        return ((l0 + l1) << 24) | (2u << 16) | ((e1 >> 8) << 8) | (e0 >> 8);
+    return (l0 << 24) | (1u << 16) | (e0 >> 8);
 }
 
 }  // namespace shafa

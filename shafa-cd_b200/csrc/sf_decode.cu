@@ -25,6 +25,7 @@ namespace shafa {
 struct DecTablesGlobal {
     uint16_t *lut;    // [nb][4096]  first-level: (sym << 8) | len
     uint16_t *lut2;   // [nb][4096]  (nsym << 8) | bits of all whole codes in the window
+    uint32_t *lut3;   // [nb][4096]  first one or two codes of the window with their symbols
     uint64_t *sleft;  // [nb][256]
     uint8_t *slen;    // [nb][256]
     uint8_t *ssym;    // [nb][256]
@@ -85,7 +86,10 @@ k_dec_tables(const uint8_t *__restrict__ lens, const uint64_t *__restrict__ code
         g.lut[b * DEC_LUT_SIZE + e] = entry;
     }
     __syncthreads();
-    for (int e = s; e < DEC_LUT_SIZE; e += 256) g.lut2[b * DEC_LUT_SIZE + e] = dec_lut2_entry(lut1, (uint32_t)e);
+    for (int e = s; e < DEC_LUT_SIZE; e += 256) {
+        g.lut2[b * DEC_LUT_SIZE + e] = dec_lut2_entry(lut1, (uint32_t)e);
+        g.lut3[b * DEC_LUT_SIZE + e] = dec_lut3_entry(lut1, (uint32_t)e);
+    }
 }
 
 // ---- shared helpers -----------------------------------------------------------------------
@@ -166,6 +170,7 @@ __device__ __forceinline__ DecView dec_view_of(const DecShared &sh)
     t.pairs = sh.pairs;
     t.lut1 = sh.lut1;
     t.lut2 = sh.lut2;
+    t.lut3 = nullptr;
     t.sleft = sh.sleft;
     t.slen = sh.slen;
     t.ssym = sh.ssym;
@@ -339,7 +344,8 @@ k_dec_scan(DecPlan plan, const uint32_t *__restrict__ seq_count, uint64_t *__res
 // copied out with 16-byte stores; a sequence that decodes to more than DEC_STAGE symbols
 // (codes of 1-2 bits) writes straight to global memory instead.
 struct DecWriteShared {
-    DecShared d;
+    DecShared d;  // d.lut2 is not used by the write kernel
+    alignas(16) uint32_t lut3[DEC_LUT_SIZE];
     alignas(16) uint8_t stage[DEC_STAGE + 32];
 };
 
@@ -366,6 +372,9 @@ k_dec_write(const uint8_t *__restrict__ payload, DecPlan plan, DecTablesGlobal g
         if (b != cur_block) {
             cur_block = b;
             dec_load_tables(sh, g, b, false);
+            const uint4 *src3 = reinterpret_cast<const uint4 *>(g.lut3 + (uint64_t)b * DEC_LUT_SIZE);
+            uint4 *dst3 = reinterpret_cast<uint4 *>(ws.lut3);
+            for (int i = tid; i < DEC_LUT_SIZE * 4 / 16; i += DEC_THREADS) dst3[i] = src3[i];
         }
         dec_load_words(sh, payload, plan.pay_off[b], z, sib);
         const uint16_t rec = sub_info[seq * DEC_THREADS + tid];
@@ -373,7 +382,8 @@ k_dec_write(const uint8_t *__restrict__ payload, DecPlan plan, DecTablesGlobal g
         const uint32_t excl = block_excl_scan<DEC_THREADS>(sub_count(rec), sh.scan, &total);  // also fences the loads above
         dec_build_pairs(sh);
         __syncthreads();
-        const DecView t = dec_view_of(sh);
+        DecView t = dec_view_of(sh);
+        t.lut3 = ws.lut3;
         const uint64_t bits_left = (z - sib * DEC_SEQ_BYTES) * 8;
         const uint32_t limit = bits_left < (uint64_t)DEC_SEQ_BYTES * 8 ? (uint32_t)bits_left : DEC_SEQ_BYTES * 8;
         const uint32_t sub_lo = tid * DEC_SUB_BITS;
@@ -452,14 +462,15 @@ int launch_sf_decode(shafa_cuda_ctx *ctx, const uint8_t *d_payload, const uint64
 
     // tables
     const size_t lut_bytes = nb * DEC_LUT_SIZE * sizeof(uint16_t);
-    const size_t tab_bytes = 2 * lut_bytes + nb * 256 * (sizeof(uint64_t) + 2);
+    const size_t tab_bytes = 4 * lut_bytes + nb * 256 * (sizeof(uint64_t) + 2);
     uint8_t *tab = (uint8_t *)scratch_get(ctx, SCR_DEC_LUT, tab_bytes);
     if (!tab) return SHAFA_LACK_OF_MEMORY;
     DecTablesGlobal g;
     g.sleft = (uint64_t *)tab;
     g.lut = (uint16_t *)(tab + nb * 256 * sizeof(uint64_t));
     g.lut2 = (uint16_t *)(tab + nb * 256 * sizeof(uint64_t) + lut_bytes);
-    g.slen = tab + nb * 256 * sizeof(uint64_t) + 2 * lut_bytes;
+    g.lut3 = (uint32_t *)(tab + nb * 256 * sizeof(uint64_t) + 2 * lut_bytes);
+    g.slen = tab + nb * 256 * sizeof(uint64_t) + 4 * lut_bytes;
     g.ssym = g.slen + nb * 256;
 
     uint16_t *sub_info = (uint16_t *)scratch_get(ctx, SCR_DEC_SUB, nseq * DEC_THREADS * sizeof(uint16_t));

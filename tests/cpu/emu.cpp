@@ -489,6 +489,7 @@ static void codes_to_strings(const uint8_t *len, const uint64_t *code, char (*ou
 // ------------------------------------------------------------------ SF decode emulation (sf_decode.cu)
 struct EmuTables {
     std::vector<uint16_t> lut, lut2;
+    std::vector<uint32_t> lut3;
     uint64_t sleft[256];
     uint8_t slen[256], ssym[256];
     DecView view(const uint64_t *pairs) const
@@ -497,6 +498,7 @@ struct EmuTables {
         t.pairs = pairs;
         t.lut1 = lut.data();
         t.lut2 = lut2.data();
+        t.lut3 = lut3.data();
         t.sleft = sleft;
         t.slen = slen;
         t.ssym = ssym;
@@ -542,7 +544,11 @@ static void emu_dec_tables(const uint8_t *len, const uint64_t *code, EmuTables &
         T.lut[e] = entry;
     }
     T.lut2.assign(DEC_LUT_SIZE, 0);
-    for (int e = 0; e < DEC_LUT_SIZE; e++) T.lut2[e] = dec_lut2_entry(T.lut.data(), (uint32_t)e);
+    T.lut3.assign(DEC_LUT_SIZE, 0);
+    for (int e = 0; e < DEC_LUT_SIZE; e++) {
+        T.lut2[e] = dec_lut2_entry(T.lut.data(), (uint32_t)e);
+        T.lut3[e] = dec_lut3_entry(T.lut.data(), (uint32_t)e);
+    }
 }
 
 static Bytes emu_sf_decode(const Bytes &payload, uint64_t n, const uint8_t *len, const uint64_t *code, bool &bad, int *stitch_passes)
