@@ -177,6 +177,14 @@ __device__ __forceinline__ uint64_t lookback_sum(uint64_t *desc, int64_t tile, i
     return excl;
 }
 
+// bit k (k = 0..3) of the result = (byte k of w == 0).  Exact zero-byte test without the emulated
+// SIMD-video intrinsics: t has 0x80 in every zero byte; the multiply gathers bits 7/15/23/31 into a nibble.
+__device__ __forceinline__ uint32_t zero_nibble(uint32_t w)
+{
+    const uint32_t t = ~(((w & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | w | 0x7F7F7F7Fu);
+    return ((t >> 7) * 0x10204080u) >> 28;
+}
+
 // bit j of the result = (byte j of v equals the byte before it); `prev` is the
 // byte preceding byte 0
 __device__ __forceinline__ uint32_t eq_prev_mask16(const uint4 &v, uint32_t prev)
@@ -185,21 +193,13 @@ __device__ __forceinline__ uint32_t eq_prev_mask16(const uint4 &v, uint32_t prev
     const uint32_t sy = __funnelshift_l(v.x, v.y, 8);
     const uint32_t sz = __funnelshift_l(v.y, v.z, 8);
     const uint32_t sw = __funnelshift_l(v.z, v.w, 8);
-    auto nib = [](uint32_t a, uint32_t b) -> uint32_t {
-        const uint32_t m = __vcmpeq4(a, b) & 0x01010101u;
-        return (m | (m >> 7) | (m >> 14) | (m >> 21)) & 0xFu;
-    };
-    return nib(v.x, sx) | (nib(v.y, sy) << 4) | (nib(v.z, sz) << 8) | (nib(v.w, sw) << 12);
+    return zero_nibble(v.x ^ sx) | (zero_nibble(v.y ^ sy) << 4) | (zero_nibble(v.z ^ sz) << 8) | (zero_nibble(v.w ^ sw) << 12);
 }
 
 // bit j = (byte j of v == 0)
 __device__ __forceinline__ uint32_t zero_mask16(const uint4 &v)
 {
-    auto nib = [](uint32_t a) -> uint32_t {
-        const uint32_t m = __vcmpeq4(a, 0u) & 0x01010101u;
-        return (m | (m >> 7) | (m >> 14) | (m >> 21)) & 0xFu;
-    };
-    return nib(v.x) | (nib(v.y) << 4) | (nib(v.z) << 8) | (nib(v.w) << 12);
+    return zero_nibble(v.x) | (zero_nibble(v.y) << 4) | (zero_nibble(v.z) << 8) | (zero_nibble(v.w) << 12);
 }
 
 // Largest b with tile0[b] <= t  (tile0 has nb+1 monotone entries, tile0[nb] = total)

@@ -102,31 +102,30 @@ struct DecPlan {
     uint32_t nb;
 };
 
-constexpr int DEC_STAGE = 16384;  // symbols of one sequence staged in shared memory before the coalesced copy-out
+constexpr int DEC_STAGE = 12288;  // symbols of one sequence staged in shared memory before the coalesced copy-out
 
 struct DecShared {
     uint64_t pairs[DEC_PAIR_SLOTS];  // pair i = (w[i] << 32) | w[i+1] (big-endian words) at slot dec_pair_slot(i)
     uint32_t words[DEC_SEQ_WORDS + DEC_WORDS_PAD + 4];
     uint16_t lut1[DEC_LUT_SIZE];
-    uint16_t lut2[DEC_LUT_SIZE];
     uint64_t sleft[256];
     uint8_t slen[256];
     uint8_t ssym[256];
-    uint32_t ends[DEC_THREADS];
     uint32_t scan[DEC_THREADS / 32 + 1];
     uint32_t block;
 };
 
-__device__ __forceinline__ void dec_load_tables(DecShared &sh, const DecTablesGlobal &g, uint32_t b, bool want_lut2)
+// lut2_dst: shared-memory copy of the multi-symbol count table (sync kernel only), or nullptr
+__device__ __forceinline__ void dec_load_tables(DecShared &sh, const DecTablesGlobal &g, uint32_t b, uint16_t *lut2_dst)
 {
     const unsigned tid = threadIdx.x;
     const uint4 *src1 = reinterpret_cast<const uint4 *>(g.lut + (uint64_t)b * DEC_LUT_SIZE);
     const uint4 *src2 = reinterpret_cast<const uint4 *>(g.lut2 + (uint64_t)b * DEC_LUT_SIZE);
     uint4 *dst1 = reinterpret_cast<uint4 *>(sh.lut1);
-    uint4 *dst2 = reinterpret_cast<uint4 *>(sh.lut2);
+    uint4 *dst2 = reinterpret_cast<uint4 *>(lut2_dst);
     for (int i = tid; i < DEC_LUT_SIZE * 2 / 16; i += DEC_THREADS) {
         dst1[i] = src1[i];
-        if (want_lut2) dst2[i] = src2[i];
+        if (lut2_dst) dst2[i] = src2[i];
     }
     sh.sleft[tid] = g.sleft[(uint64_t)b * 256 + tid];
     sh.slen[tid] = g.slen[(uint64_t)b * 256 + tid];
@@ -169,7 +168,7 @@ __device__ __forceinline__ DecView dec_view_of(const DecShared &sh)
     DecView t;
     t.pairs = sh.pairs;
     t.lut1 = sh.lut1;
-    t.lut2 = sh.lut2;
+    t.lut2 = nullptr;
     t.lut3 = nullptr;
     t.sleft = sh.sleft;
     t.slen = sh.slen;
@@ -197,6 +196,8 @@ k_dec_sync(const uint8_t *__restrict__ payload, DecPlan plan, DecTablesGlobal g,
            uint32_t *__restrict__ seq_end, uint64_t nseq)
 {
     __shared__ DecShared sh;
+    __shared__ __align__(16) uint16_t s_lut2[DEC_LUT_SIZE];
+    __shared__ uint32_t s_ends[DEC_THREADS];
     const unsigned tid = threadIdx.x;
     uint64_t seq_first, seq_last;
     dec_chunk(nseq, &seq_first, &seq_last);
@@ -210,13 +211,14 @@ k_dec_sync(const uint8_t *__restrict__ payload, DecPlan plan, DecTablesGlobal g,
         const uint64_t z = plan.z[b];
         if (b != cur_block) {
             cur_block = b;
-            dec_load_tables(sh, g, b, true);
+            dec_load_tables(sh, g, b, s_lut2);
         }
         dec_load_words(sh, payload, plan.pay_off[b], z, sib);
         __syncthreads();
         dec_build_pairs(sh);
         __syncthreads();
-        const DecView t = dec_view_of(sh);
+        DecView t = dec_view_of(sh);
+        t.lut2 = s_lut2;
         // bits of this sequence that exist in the payload
         const uint64_t bits_left = (z - sib * DEC_SEQ_BYTES) * 8;
         const uint32_t limit = bits_left < (uint64_t)DEC_SEQ_BYTES * 8 ? (uint32_t)bits_left : DEC_SEQ_BYTES * 8;
@@ -228,9 +230,9 @@ k_dec_sync(const uint8_t *__restrict__ payload, DecPlan plan, DecTablesGlobal g,
         DecSub r = dec_count_subsequence(t, sub_lo + start, stop);
         uint32_t my_end = r.end > sub_hi ? r.end - sub_hi : 0;  // overshoot into the next sub-sequence
         for (;;) {
-            sh.ends[tid] = my_end;
+            s_ends[tid] = my_end;
             __syncthreads();
-            const uint32_t want = tid ? sh.ends[tid - 1] : 0u;
+            const uint32_t want = tid ? s_ends[tid - 1] : 0u;
             const int changed = (want != start);
             if (!__syncthreads_or(changed)) break;
             if (changed) {
@@ -344,7 +346,7 @@ k_dec_scan(DecPlan plan, const uint32_t *__restrict__ seq_count, uint64_t *__res
 // copied out with 16-byte stores; a sequence that decodes to more than DEC_STAGE symbols
 // (codes of 1-2 bits) writes straight to global memory instead.
 struct DecWriteShared {
-    DecShared d;  // d.lut2 is not used by the write kernel
+    DecShared d;
     alignas(16) uint32_t lut3[DEC_LUT_SIZE];
     alignas(16) uint8_t stage[DEC_STAGE + 32];
 };
@@ -371,7 +373,7 @@ k_dec_write(const uint8_t *__restrict__ payload, DecPlan plan, DecTablesGlobal g
         const uint64_t z = plan.z[b];
         if (b != cur_block) {
             cur_block = b;
-            dec_load_tables(sh, g, b, false);
+            dec_load_tables(sh, g, b, nullptr);
             const uint4 *src3 = reinterpret_cast<const uint4 *>(g.lut3 + (uint64_t)b * DEC_LUT_SIZE);
             uint4 *dst3 = reinterpret_cast<uint4 *>(ws.lut3);
             for (int i = tid; i < DEC_LUT_SIZE * 4 / 16; i += DEC_THREADS) dst3[i] = src3[i];
