@@ -120,13 +120,16 @@ k_rle_decode(const uint8_t *__restrict__ in, const uint64_t *__restrict__ off, c
         }
         const int n = j1 - j0;
         const bool full = (n == RLD_PER_THREAD);
-        uint4 v[RLD_VECS];
+        // The bytes themselves are not kept: the write pass below reads them again (L1 hits), which
+        // keeps the kernel at 64 registers without spilling.
         uint64_t Z = 0;  // bit q = (valid byte q == 0), relative to j0
+        uint32_t last_byte = 0;
 #pragma unroll
         for (int c = 0; c < RLD_VECS; c++) {
-            v[c] = make_uint4(0, 0, 0, 0);
-            if (16 * c < j1 && 16 * c + 16 > j0) v[c] = rld_ld16(in + pos + 16 * c);
-            Z |= (uint64_t)zero_mask16(v[c]) << (16 * c);
+            uint4 x = make_uint4(0, 0, 0, 0);
+            if (16 * c < j1 && 16 * c + 16 > j0) x = rld_ld16(in + pos + 16 * c);
+            Z |= (uint64_t)zero_mask16(x) << (16 * c);
+            if (c == RLD_VECS - 1) last_byte = x.w >> 24;
         }
         Z = (j0 < 64) ? (Z >> j0) : 0ull;
         Z &= (n >= 64) ? ~0ull : ((1ull << n) - 1ull);
@@ -142,7 +145,7 @@ k_rle_decode(const uint8_t *__restrict__ in, const uint64_t *__restrict__ off, c
         uint32_t excl_map = __shfl_up_sync(FULL, incl, 1);
         if (lane == 0) excl_map = FSM_IDENTITY;
         // byte just before this thread's first valid byte (needed when a count byte is my first byte)
-        uint32_t prevb = __shfl_up_sync(FULL, v[RLD_VECS - 1].w >> 24, 1);
+        uint32_t prevb = __shfl_up_sync(FULL, last_byte, 1);
         if ((lane == 0 || !full) && n > 0 && pos + j0 > lo) prevb = in[pos + j0 - 1];
         __syncthreads();
 
@@ -249,17 +252,18 @@ k_rle_decode(const uint8_t *__restrict__ in, const uint64_t *__restrict__ off, c
                 if (full && single) {
                     // literals: one uniform, fully predicated pass -- the offset of position q is
                     // (literals before q) + (bytes of the runs before q), kept as a running sum
-#pragma unroll
+#pragma unroll 1
                     for (int c = 0; c < RLD_VECS; c++) {
+                        const uint4 x = rld_ld16(in + pos + 16 * c);
                         const uint32_t l16 = (uint32_t)(m.lit >> (16 * c)) & 0xffffu, r16 = (uint32_t)(m.run >> (16 * c)) & 0xffffu;
                         if (__all_sync(__activemask(), r16 == 0 && l16 == 0xffffu)) {  // whole warp: sixteen literals each
 #pragma unroll
-                            for (int j = 0; j < 16; j++) sb[o + j] = (uint8_t)byte_of(v[c], j);
+                            for (int j = 0; j < 16; j++) sb[o + j] = (uint8_t)byte_of(x, j);
                             o += 16;
                         } else {
 #pragma unroll
                             for (int j = 0; j < 16; j++) {
-                                const uint32_t cur = byte_of(v[c], j);
+                                const uint32_t cur = byte_of(x, j);
                                 if ((l16 >> j) & 1u) sb[o] = (uint8_t)cur;
                                 o += ((l16 >> j) & 1u) + (((r16 >> j) & 1u) ? (cur ? cur : 1u) : 0u);
                             }
