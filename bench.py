@@ -127,18 +127,40 @@ def cpu_arm(pkg, steps: int, warmup: int):
 # ----------------------------------------------------------------------------------
 
 class ClockSampler:
-    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi in the background (the recipe's clocks line plus a timestamp); only the samples taken
+    inside the marked load windows count.  nvidia-smi needs a moment to start, so it is launched before
+    the warm-up and `wait_ready` blocks until its first line is there."""
+    FIELDS = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index: int):
         self.path = tempfile.NamedTemporaryFile(prefix="clocks_", suffix=".csv", delete=False).name
         self.proc = None
+        self.windows = []
         if shutil.which("nvidia-smi"):
             try:
                 self.proc = subprocess.Popen(["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                                              "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+                                              "-lms", "50"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
             except Exception:
                 self.proc = None
+
+    def wait_ready(self, timeout_s: float = 10.0):
+        t_end = time.time() + timeout_s
+        while self.proc and time.time() < t_end:
+            if os.path.getsize(self.path) > 0:
+                return
+            time.sleep(0.02)
+
+    def window(self, t0: float, t1: float):
+        self.windows.append((t0, t1))
+
+    @staticmethod
+    def _ts(text: str):
+        import datetime
+        try:
+            return datetime.datetime.strptime(text.strip(), "%Y/%m/%d %H:%M:%S.%f").timestamp()
+        except ValueError:
+            return None
 
     def stop(self) -> dict:
         if not self.proc:
@@ -148,22 +170,26 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        rows = []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for line in Path(self.path).read_text().splitlines():
             f = [x.strip() for x in line.split(",")]
             if len(f) < 9:
                 continue
             try:
-                sm.append(float(f[1])); mx.append(float(f[2]))
+                rows.append((self._ts(f[0]), float(f[1]), float(f[2]), [n for n, v in zip(names, f[5:9]) if v.lower().startswith("active")]))
             except ValueError:
                 continue
-            for name, v in zip(names, f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
         os.unlink(self.path)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+        # a sample describes the ~50 ms before its timestamp: accept it up to one period after a window
+        inside = [r for r in rows if r[0] is not None and any(t0 <= r[0] <= t1 + 0.06 for t0, t1 in self.windows)]
+        scope = "load windows"
+        if not inside:
+            inside, scope = rows, "whole run (no sample fell inside a load window)"
+        sm = [r[1] for r in inside]
+        reasons = sorted({n for r in inside for n in r[3]})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max((r[2] for r in rows), default=None),
+                "samples": len(sm), "scope": scope, "reasons": reasons}
 
 
 # ----------------------------------------------------------------------------------
@@ -195,6 +221,7 @@ def run_ours(args):
     data = pkg.datagen.textlike(n, seed=2024 + rank)      # this rank's shard of blocks
     B = (n + bs - 1) // bs
 
+    clocks = ClockSampler(local_rank)   # started early: nvidia-smi takes a while to deliver its first line
     sh = pkg.Shafa(device=local_rank)
     stream = torch.cuda.current_stream(dev)
     sh.set_stream(stream.cuda_stream)
@@ -253,23 +280,24 @@ def run_ours(args):
         raise RuntimeError("round trip mismatch on the GPU path")
 
     sh.profile(True); sh.profile_reset()
-    clocks = ClockSampler(local_rank)
+    clocks.wait_ready()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     mids = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     launches0 = sh.launch_count()
     barrier()
+    w0 = time.time()
     ev0.record(stream)
     for i in range(args.steps):
         starts[i].record(stream)
         step(mids[i])
     ev1.record(stream)
     barrier()
+    clocks.window(w0, time.time())
     total_ms = ev0.elapsed_time(ev1)
     launches = sh.launch_count() - launches0
     kstats = sh.profile_read()
     sh.profile(False)
-    clk = clocks.stop()
     enc_ms = sum(starts[i].elapsed_time(mids[i]) for i in range(args.steps)) / args.steps
     dec_ms = total_ms / args.steps - enc_ms
 
@@ -293,6 +321,7 @@ def run_ours(args):
     e2e_times, h2d, d2h = [], 0, 0
     for i in range(1 + e2e_steps):
         barrier()
+        w0 = time.time()
         t0 = time.perf_counter()
         c = sh.encode_raw(pin_in, bs, rle_buf=pin_rle, payload_buf=pin_pay)
         enc_view = pkg.Encoded.__new__(pkg.Encoded)   # no copies: read the struct's arrays in place
@@ -307,11 +336,13 @@ def run_ours(args):
                 raise RuntimeError("e2e round trip mismatch")
         else:
             e2e_times.append(t1 - t0)
+            clocks.window(w0, time.time())
         h2d = n + int(c.payload_total) + Bc * 256 * 9
         d2h = int(c.rle_total) + int(c.payload_total) + Bc * 256 * (8 + 9) + n
         sh.encoded_free(c)
         del enc_view
     e2e_s = sum(e2e_times) / len(e2e_times)
+    clk = clocks.stop()
 
     # ---- reduce over ranks (max time) ----
     t = torch.tensor([total_ms, e2e_s * 1e3, enc_ms, dec_ms], dtype=torch.float64, device=dev)
@@ -399,7 +430,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--bytes", type=int, default=GIB, help="bytes per GPU (default: the 1 GiB of configs[1])")
