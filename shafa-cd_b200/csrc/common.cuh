@@ -11,6 +11,8 @@ namespace shafa {
 
 constexpr unsigned FULL = 0xffffffffu;
 
+// 32-bit shared-window address of a shared-memory object (operand of explicit ld/st/red.shared)
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }
 __device__ __forceinline__ unsigned warp_id() { return threadIdx.x >> 5; }
 

@@ -435,35 +435,43 @@ constexpr int DEC_SUB_BITS = 128;                      // sub-sequence (one thre
 constexpr int DEC_THREADS = 256;                       // sub-sequences per sequence (one CTA)
 constexpr int DEC_SEQ_BYTES = DEC_SUB_BITS * DEC_THREADS / 8;  // 4096
 constexpr int DEC_SEQ_WORDS = DEC_SEQ_BYTES / 4;       // 1024
-constexpr int DEC_WORDS_PAD = 4;                       // look-ahead words after the sequence
 
 struct DecSub {
-    uint32_t end;    // bit position (relative to the sequence) where decoding stopped
+    uint32_t end;    // bit position (relative to the sub-sequence) where decoding stopped; may pass DEC_SUB_BITS
     uint32_t count;  // symbols that START inside [start, stop)
     uint32_t bad;    // a window matched no code
 };
 
 // ---- sequence-level decoding -------------------------------------------------------------------
-// The sequence's payload is kept as an array of overlapping pairs: pairs[i] = (w[i] << 32) | w[i+1]
-// (big-endian words), so the 32 bits starting at any bit q are one 64-bit load and a funnel shift and
-// there is no refill branch to diverge a warp.
-// The pair array is stored transposed: thread t of a CTA walks words 4t .. 4t+5 of the sequence, so
-// word i lives at (i & 3) * 257 + (i >> 2): the 32 lanes of a warp then read 32 consecutive 64-bit
-// slots (no shared-memory bank conflicts) instead of slots 16 bytes apart.
-constexpr int DEC_PAIR_ROW = DEC_THREADS + 1;            // 257
-constexpr int DEC_PAIR_SLOTS = 4 * DEC_PAIR_ROW;         // 1028 >= DEC_SEQ_WORDS + DEC_WORDS_PAD
-SHAFA_HD uint32_t dec_pair_slot(uint32_t i) { return (i & 3u) * (uint32_t)DEC_PAIR_ROW + (i >> 2); }
+// Bit positions are relative to the sub-sequence.  A window is only ever read at a position < 128 and
+// the longest code has 64 bits, so a sub-sequence needs the six big-endian words w[0..5] that start at
+// its first bit.  They are kept as a ROW of five overlapping pairs, row[k] = (w[k] << 32) | w[k+1]:
+// the 32 bits starting at any bit q are one 64-bit load and a funnel shift, with no refill branch to
+// diverge a warp and no address arithmetic beyond row + (q >> 5).  Rows are 40 bytes apart, so the 32
+// lanes of a warp reading their own rows do not collide on shared-memory banks more than chance.
+constexpr int DEC_ROW = 5;                               // pairs per row
+constexpr int DEC_ROW_WORDS = DEC_ROW + 1;               // words per row
+constexpr int DEC_PAIR_SLOTS = DEC_ROW * DEC_THREADS;    // 1280 slots of 8 bytes per sequence
 
-SHAFA_HD uint32_t dec_window32(const uint64_t *pairs, uint32_t q)
+SHAFA_HD void dec_row_from_words(const uint32_t *w, uint64_t *row)
 {
-    const uint64_t pr = pairs[dec_pair_slot(q >> 5)];
+    for (int k = 0; k < DEC_ROW; k++) row[k] = ((uint64_t)w[k] << 32) | (uint64_t)w[k + 1];
+}
+
+// V is a view of the tables (DecView below, or the kernels' shared-memory view with the same accessors);
+// `row` is the slot of the sub-sequence's first pair (sub-sequence index * DEC_ROW)
+template <typename V>
+SHAFA_HD uint32_t dec_window32(const V &t, uint32_t row, uint32_t q)
+{
+    const uint64_t pr = t.pair(row + (q >> 5));
     return (uint32_t)((pr << (q & 31u)) >> 32);
 }
-SHAFA_HD uint64_t dec_window64(const uint64_t *pairs, uint32_t q)
+template <typename V>
+SHAFA_HD uint64_t dec_window64(const V &t, uint32_t row, uint32_t q)
 {
     const uint32_t i = q >> 5, sh = q & 31u;
-    const uint64_t hi = pairs[dec_pair_slot(i)];
-    return sh ? ((hi << sh) | ((pairs[dec_pair_slot(i + 1)] & 0xffffffffull) >> (32 - sh))) : hi;  // low word of pair i+1 is w[i+2]
+    const uint64_t hi = t.pair(row + i);
+    return sh ? ((hi << sh) | ((t.pair(row + i + 1) & 0xffffffffull) >> (32 - sh))) : hi;  // low word of pair i+1 is w[i+2]
 }
 
 // Tables of one block as seen by a decoding thread (shared memory on the GPU).
@@ -478,13 +486,18 @@ struct DecView {
     const uint64_t *sleft;
     const uint8_t *slen;
     const uint8_t *ssym;
+    SHAFA_HD uint64_t pair(uint32_t slot) const { return pairs[slot]; }
+    SHAFA_HD uint32_t l1(uint32_t i) const { return lut1[i]; }
+    SHAFA_HD uint32_t l2(uint32_t i) const { return lut2[i]; }
+    SHAFA_HD uint32_t l3(uint32_t i) const { return lut3[i]; }
+    SHAFA_HD bool has_l3() const { return lut3 != nullptr; }
 };
 
 // one symbol at bit q: returns its length (>= 1), *sym; *bad is set if the bits are no code
 template <typename V>
-SHAFA_HD uint32_t dec_one(const V &t, uint32_t q, uint32_t *sym, uint32_t *bad)
+SHAFA_HD uint32_t dec_one(const V &t, uint32_t row, uint32_t q, uint32_t *sym, uint32_t *bad)
 {
-    const uint32_t e = t.lut1[dec_window32(t.pairs, q) >> (32 - DEC_LUT_BITS)];
+    const uint32_t e = t.l1(dec_window32(t, row, q) >> (32 - DEC_LUT_BITS));
     uint32_t l = e & 0xFFu;
     *sym = e >> 8;
     if (l - 1u >= (uint32_t)DEC_LUT_BITS) {  // long code or no code: exact 64-bit window + sorted search
@@ -493,7 +506,7 @@ SHAFA_HD uint32_t dec_one(const V &t, uint32_t q, uint32_t *sym, uint32_t *bad)
         dt.sleft = t.sleft;
         dt.slen = t.slen;
         dt.ssym = t.ssym;
-        l = dec_symbol(dt, dec_window64(t.pairs, q), sym);
+        l = dec_symbol(dt, dec_window64(t, row, q), sym);
         if (l == 0) {
             *bad = 1;
             l = 1;
@@ -502,68 +515,82 @@ SHAFA_HD uint32_t dec_one(const V &t, uint32_t q, uint32_t *sym, uint32_t *bad)
     return l;
 }
 
-// Count the symbols that START in [start, stop) and find where decoding leaves the range.
-// While a whole 12-bit window lies before `stop`, all codes inside it are taken at once (lut2).
+// Count the symbols that START in [start, stop) of the sub-sequence whose row is `row` (stop <= 128)
+// and find where decoding leaves the range.  While a whole 12-bit window lies before `stop`, all codes
+// inside it are taken at once (lut2).
 template <typename V>
-SHAFA_HD DecSub dec_count_subsequence(const V &t, uint32_t start, uint32_t stop)
+SHAFA_HD DecSub dec_count_subsequence(const V &t, uint32_t row, uint32_t start, uint32_t stop)
 {
     DecSub r;
     r.count = 0;
     r.bad = 0;
-    uint32_t q = start;
-    while (q + (uint32_t)DEC_LUT_BITS <= stop) {
-        const uint32_t e2 = t.lut2[dec_window32(t.pairs, q) >> (32 - DEC_LUT_BITS)];
-        if (e2) {
-            q += e2 & 0xFFu;
+    int32_t q = (int32_t)start;
+    const int32_t stop12 = (int32_t)stop - DEC_LUT_BITS;
+    for (;;) {
+        while (q <= stop12) {
+            const uint32_t e2 = t.l2(dec_window32(t, row, (uint32_t)q) >> (32 - DEC_LUT_BITS));
+            if (e2 == 0) break;
+            q += (int32_t)(e2 & 0xFFu);
             r.count += e2 >> 8;
-        } else {
-            uint32_t sym;
-            q += dec_one(t, q, &sym, &r.bad);
-            r.count++;
         }
-    }
-    while (q < stop) {
-        uint32_t sym;
-        q += dec_one(t, q, &sym, &r.bad);
+        if (q >= (int32_t)stop) break;
+        uint32_t sym;  // a code longer than the window, or the last few bits of the range: one code
+        q += (int32_t)dec_one(t, row, (uint32_t)q, &sym, &r.bad);
         r.count++;
     }
-    r.end = q;
+    r.end = (uint32_t)q;
     return r;
 }
 
-// Decode the symbols that start in [start, stop); emit(i, sym) for the i-th one.  While a whole 12-bit
-// window lies before `stop`, the first two codes inside it are taken at once (lut3).
-template <typename V, typename Emit>
-SHAFA_HD DecSub dec_emit_subsequence(const V &t, uint32_t start, uint32_t stop, Emit emit)
+// Decode the symbols that start in [start, stop).  While a whole 12-bit window lies before `stop`, the
+// first two codes inside it are taken at once (lut3).  The sink gets em.one(i, sym) for the i-th symbol,
+// or em.two(i, e3) for a lut3 entry: symbol i is e3 & 0xFF and, if e3 & 0x20000, symbol i+1 is (e3 >> 8) & 0xFF.
+template <typename V, typename Sink>
+SHAFA_HD DecSub dec_emit_to(const V &t, uint32_t row, uint32_t start, uint32_t stop, Sink &em)
 {
     DecSub r;
     r.count = 0;
     r.bad = 0;
-    uint32_t q = start;
-    if (t.lut3) {
-        while (q + (uint32_t)DEC_LUT_BITS <= stop) {
-            const uint32_t e3 = t.lut3[dec_window32(t.pairs, q) >> (32 - DEC_LUT_BITS)];
-            if (e3) {
-                emit(r.count, e3 & 0xFFu);
-                if (e3 & 0x20000u) emit(r.count + 1, (e3 >> 8) & 0xFFu);
-                r.count += (e3 >> 16) & 0xFFu;
-                q += e3 >> 24;
-            } else {
-                uint32_t sym;
-                q += dec_one(t, q, &sym, &r.bad);
-                emit(r.count, sym);
-                r.count++;
-            }
+    int32_t q = (int32_t)start;
+    const int32_t stop12 = t.has_l3() ? (int32_t)stop - DEC_LUT_BITS : -1;
+    for (;;) {
+        while (q <= stop12) {
+            const uint32_t e3 = t.l3(dec_window32(t, row, (uint32_t)q) >> (32 - DEC_LUT_BITS));
+            if (e3 == 0) break;
+            em.two(r.count, e3);
+#ifdef __CUDA_ARCH__
+            r.count += __byte_perm(e3, 0, 0x4442);  // byte 2: one PRMT
+#else
+            r.count += (e3 >> 16) & 0xFFu;
+#endif
+            q += (int32_t)(e3 >> 24);
         }
-    }
-    while (q < stop) {
+        if (q >= (int32_t)stop) break;
         uint32_t sym;
-        q += dec_one(t, q, &sym, &r.bad);
-        emit(r.count, sym);
+        q += (int32_t)dec_one(t, row, (uint32_t)q, &sym, &r.bad);
+        em.one(r.count, sym);
         r.count++;
     }
-    r.end = q;
+    r.end = (uint32_t)q;
     return r;
+}
+
+// the same with a plain callable emit(i, sym)
+template <typename F>
+struct DecFnSink {
+    F f;
+    SHAFA_HD void one(uint32_t i, uint32_t sym) { f(i, sym); }
+    SHAFA_HD void two(uint32_t i, uint32_t e3)
+    {
+        f(i, e3 & 0xFFu);
+        if (e3 & 0x20000u) f(i + 1, (e3 >> 8) & 0xFFu);
+    }
+};
+template <typename V, typename Emit>
+SHAFA_HD DecSub dec_emit_subsequence(const V &t, uint32_t row, uint32_t start, uint32_t stop, Emit emit)
+{
+    DecFnSink<Emit> sink{emit};
+    return dec_emit_to(t, row, start, stop, sink);
 }
 
 struct DecNoEmit {

@@ -105,8 +105,7 @@ struct DecPlan {
 constexpr int DEC_STAGE = 12288;  // symbols of one sequence staged in shared memory before the coalesced copy-out
 
 struct DecShared {
-    uint64_t pairs[DEC_PAIR_SLOTS];  // pair i = (w[i] << 32) | w[i+1] (big-endian words) at slot dec_pair_slot(i)
-    uint32_t words[DEC_SEQ_WORDS + DEC_WORDS_PAD + 4];
+    uint64_t pairs[DEC_PAIR_SLOTS];  // row of sub-sequence s at [s * DEC_ROW, (s + 1) * DEC_ROW) (core.h)
     uint16_t lut1[DEC_LUT_SIZE];
     uint64_t sleft[256];
     uint8_t slen[256];
@@ -132,44 +131,87 @@ __device__ __forceinline__ void dec_load_tables(DecShared &sh, const DecTablesGl
     sh.ssym[tid] = g.ssym[(uint64_t)b * 256 + tid];
 }
 
-// load the sequence's payload as big-endian words, then as overlapping pairs (call between barriers)
-__device__ __forceinline__ void dec_load_words(DecShared &sh, const uint8_t *payload, uint64_t pay_off, uint64_t z,
-                                               uint64_t seq_in_block)
+// Thread s builds the row of sub-sequence s straight from global memory: payload bytes [16 s, 16 s + 24)
+// of the sequence as six big-endian words; bytes at or past z read as zero.  (Call between barriers.)
+__device__ __forceinline__ void dec_load_rows(DecShared &sh, const uint8_t *payload, uint64_t pay_off, uint64_t z,
+                                              uint64_t seq_in_block)
 {
     const unsigned tid = threadIdx.x;
-    const uint64_t byte0 = seq_in_block * DEC_SEQ_BYTES;  // offset of this sequence in the block's payload
-    const uint64_t slot = (z + 15) & ~15ull;              // readable bytes of the block's slot
+    const uint64_t o = seq_in_block * DEC_SEQ_BYTES + (uint64_t)tid * 16;  // offset in the block's payload
+    const uint64_t slot = (z + 15) & ~15ull;                               // readable bytes of the block's slot
     const uint8_t *base = payload + pay_off;
-    for (int i = tid; i < (DEC_SEQ_WORDS + DEC_WORDS_PAD + 4) / 4; i += DEC_THREADS) {
-        const uint64_t o = byte0 + (uint64_t)i * 16;
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (o < slot) v = ld_stream16(base + o);
-        uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    uint32_t w[DEC_ROW_WORDS] = {0, 0, 0, 0, 0, 0};
+    if (o < slot) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4 *>(base + o));
+        w[0] = v.x, w[1] = v.y, w[2] = v.z, w[3] = v.w;
+    }
+    if (o + 16 < slot) {  // the first half of the next thread's vector: the same cache line, or the next one
+        const uint2 u = __ldg(reinterpret_cast<const uint2 *>(base + o + 16));
+        w[4] = u.x, w[5] = u.y;
+    }
+    if (o + 4 * DEC_ROW_WORDS > z) {  // only at the end of a block
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const uint64_t bo = o + 4 * k;  // bytes at or past z read as zero
-            uint32_t x = w[k];
+        for (int k = 0; k < DEC_ROW_WORDS; k++) {
+            const uint64_t bo = o + 4 * k;
             if (bo >= z)
-                x = 0;
+                w[k] = 0;
             else if (bo + 4 > z)
-                x &= (0xffffffffu >> (8 * (uint32_t)(bo + 4 - z)));
-            sh.words[i * 4 + k] = bswap32(x);
+                w[k] &= (0xffffffffu >> (8 * (uint32_t)(bo + 4 - z)));
         }
     }
-}
-__device__ __forceinline__ void dec_build_pairs(DecShared &sh)
-{
-    for (int i = threadIdx.x; i < DEC_SEQ_WORDS + DEC_WORDS_PAD; i += DEC_THREADS)
-        sh.pairs[dec_pair_slot((uint32_t)i)] = ((uint64_t)sh.words[i] << 32) | (uint64_t)sh.words[i + 1];
+#pragma unroll
+    for (int k = 0; k < DEC_ROW_WORDS; k++) w[k] = bswap32(w[k]);
+    uint64_t row[DEC_ROW];
+    dec_row_from_words(w, row);
+#pragma unroll
+    for (int k = 0; k < DEC_ROW; k++) sh.pairs[tid * DEC_ROW + k] = row[k];
 }
 
-__device__ __forceinline__ DecView dec_view_of(const DecShared &sh)
+// The decode loops read the tables through 32-bit shared-memory addresses computed once per sequence
+// (explicit ld.shared), so that no generic-to-shared address arithmetic is left inside them.
+struct DecViewS {
+    uint32_t pairs_s, lut1_s, lut2_s, lut3_s;  // shared-window addresses; 0 = table not loaded
+    const uint16_t *lut1;                      // the same tables as pointers for the rare long-code search
+    const uint64_t *sleft;
+    const uint8_t *slen;
+    const uint8_t *ssym;
+    __device__ __forceinline__ uint64_t pair(uint32_t slot) const
+    {
+        uint64_t v;
+        asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(pairs_s + slot * 8u));
+        return v;
+    }
+    __device__ __forceinline__ uint32_t l1(uint32_t i) const
+    {
+        uint32_t v;
+        asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(lut1_s + i * 2u));
+        return v;
+    }
+    __device__ __forceinline__ uint32_t l2(uint32_t i) const
+    {
+        uint32_t v;
+        asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(lut2_s + i * 2u));
+        return v;
+    }
+    __device__ __forceinline__ uint32_t l3(uint32_t i) const
+    {
+        uint32_t v;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(lut3_s + i * 4u));
+        return v;
+    }
+    __device__ __forceinline__ bool has_l3() const { return lut3_s != 0; }
+};
+
+__device__ __forceinline__ DecViewS dec_view_of(const DecShared &sh, const uint16_t *lut2, const uint32_t *lut3)
 {
-    DecView t;
-    t.pairs = sh.pairs;
+    DecViewS t;
+    t.pairs_s = smem_u32(sh.pairs);
+    t.lut1_s = smem_u32(sh.lut1);
+    t.lut2_s = lut2 ? smem_u32(lut2) : 0u;
+    t.lut3_s = lut3 ? smem_u32(lut3) : 0u;
+    // opaque to the optimiser: otherwise the addresses are rebuilt from the CTA's shared window inside the loops
+    asm volatile("" : "+r"(t.pairs_s), "+r"(t.lut1_s), "+r"(t.lut2_s), "+r"(t.lut3_s));
     t.lut1 = sh.lut1;
-    t.lut2 = nullptr;
-    t.lut3 = nullptr;
     t.sleft = sh.sleft;
     t.slen = sh.slen;
     t.ssym = sh.ssym;
@@ -197,8 +239,12 @@ k_dec_sync(const uint8_t *__restrict__ payload, DecPlan plan, DecTablesGlobal g,
 {
     __shared__ DecShared sh;
     __shared__ __align__(16) uint16_t s_lut2[DEC_LUT_SIZE];
-    __shared__ uint32_t s_ends[DEC_THREADS];
-    const unsigned tid = threadIdx.x;
+    __shared__ uint32_t s_ends[DEC_THREADS];    // overshoot of sub-sequence i into sub-sequence i+1
+    __shared__ uint16_t s_start[DEC_THREADS];   // start offset the current record of sub-sequence i was decoded from
+    __shared__ uint16_t s_count[DEC_THREADS];
+    __shared__ uint32_t s_list[DEC_THREADS];    // compacted work list of a sparse round: sub-sequence | start << 16
+    __shared__ uint32_t s_wcnt[DEC_THREADS / 32];
+    const unsigned tid = threadIdx.x, lane = lane_id(), warp = warp_id();
     uint64_t seq_first, seq_last;
     dec_chunk(nseq, &seq_first, &seq_last);
     uint32_t cur_block = 0xffffffffu;
@@ -213,36 +259,54 @@ k_dec_sync(const uint8_t *__restrict__ payload, DecPlan plan, DecTablesGlobal g,
             cur_block = b;
             dec_load_tables(sh, g, b, s_lut2);
         }
-        dec_load_words(sh, payload, plan.pay_off[b], z, sib);
+        dec_load_rows(sh, payload, plan.pay_off[b], z, sib);
         __syncthreads();
-        dec_build_pairs(sh);
-        __syncthreads();
-        DecView t = dec_view_of(sh);
-        t.lut2 = s_lut2;
+        const DecViewS t = dec_view_of(sh, s_lut2, nullptr);
         // bits of this sequence that exist in the payload
         const uint64_t bits_left = (z - sib * DEC_SEQ_BYTES) * 8;
         const uint32_t limit = bits_left < (uint64_t)DEC_SEQ_BYTES * 8 ? (uint32_t)bits_left : DEC_SEQ_BYTES * 8;
-        const uint32_t sub_lo = tid * DEC_SUB_BITS;
-        const uint32_t sub_hi = sub_lo + DEC_SUB_BITS;
-        const uint32_t stop = sub_hi < limit ? sub_hi : limit;
 
-        uint32_t start = 0;
-        DecSub r = dec_count_subsequence(t, sub_lo + start, stop);
-        uint32_t my_end = r.end > sub_hi ? r.end - sub_hi : 0;  // overshoot into the next sub-sequence
+        // decode sub-sequence `sid` from offset `st` and record where it leaves it
+        auto run = [&](uint32_t sid, uint32_t st) {
+            const uint32_t sub_lo = sid * DEC_SUB_BITS;
+            const uint32_t stop = limit > sub_lo ? (limit - sub_lo < (uint32_t)DEC_SUB_BITS ? limit - sub_lo : (uint32_t)DEC_SUB_BITS) : 0u;
+            const DecSub r = dec_count_subsequence(t, sid * DEC_ROW, st, stop);
+            s_start[sid] = (uint16_t)st;
+            s_count[sid] = (uint16_t)r.count;
+            s_ends[sid] = r.end > (uint32_t)DEC_SUB_BITS ? r.end - DEC_SUB_BITS : 0;  // overshoot into the next sub-sequence
+        };
+        run(tid, 0);
+        // Rounds until every sub-sequence starts where its predecessor ended.  Round 2 moves almost every
+        // start; later rounds touch only the few sub-sequences whose predecessor had not synchronised yet,
+        // so their work is compacted into the first warps instead of costing every warp a full pass.
         for (;;) {
-            s_ends[tid] = my_end;
             __syncthreads();
             const uint32_t want = tid ? s_ends[tid - 1] : 0u;
-            const int changed = (want != start);
-            if (!__syncthreads_or(changed)) break;
-            if (changed) {
-                start = want;
-                r = dec_count_subsequence(t, sub_lo + start, stop);
-                my_end = r.end > sub_hi ? r.end - sub_hi : 0;
+            const bool changed = (want != s_start[tid]);
+            const unsigned bal = __ballot_sync(FULL, changed);
+            if (lane == 0) s_wcnt[warp] = (uint32_t)__popc(bal);
+            __syncthreads();
+            uint32_t total = 0, before = 0;
+#pragma unroll
+            for (int w = 0; w < DEC_THREADS / 32; w++) {
+                const uint32_t c = s_wcnt[w];
+                before += (w < (int)warp) ? c : 0u;
+                total += c;
+            }
+            if (total == 0) break;
+            if (total > DEC_THREADS / 4) {
+                if (changed) run(tid, want);
+            } else {
+                if (changed) s_list[before + (uint32_t)__popc(bal & ((1u << lane) - 1u))] = tid | (want << 16);
+                __syncthreads();
+                if (tid < total) {
+                    const uint32_t e = s_list[tid];
+                    run(e & 0xffffu, e >> 16);
+                }
             }
         }
-        sub_info[seq * DEC_THREADS + tid] = sub_pack(start, r.count);
-        if (tid == DEC_THREADS - 1) seq_end[seq] = my_end;
+        sub_info[seq * DEC_THREADS + tid] = sub_pack(s_start[tid], s_count[tid]);
+        if (tid == DEC_THREADS - 1) seq_end[seq] = s_ends[tid];
         // a speculative start may hit garbage; errors are judged in k_dec_write
     }
 }
@@ -351,6 +415,35 @@ struct DecWriteShared {
     alignas(16) uint8_t stage[DEC_STAGE + 32];
 };
 
+// Sink of the write pass: symbol i of the thread goes to shared byte address base + i.  CHECKED drops
+// the symbols at or past `room` (padding bits after a block's last symbol decode to garbage).
+template <bool CHECKED>
+struct StageSink {
+    uint32_t base, room;
+    __device__ __forceinline__ void put_if(uint32_t addr, uint32_t sym, uint32_t p) const  // store if p != 0
+    {
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p st.shared.u8 [%0], %1;\n\t}" ::"r"(addr), "r"(sym), "r"(p) : "memory");
+    }
+    __device__ __forceinline__ void one(uint32_t i, uint32_t sym) const
+    {
+        if (CHECKED)
+            put_if(base + i, sym, i < room);
+        else
+            asm volatile("st.shared.u8 [%0], %1;" ::"r"(base + i), "r"(sym) : "memory");
+    }
+    __device__ __forceinline__ void two(uint32_t i, uint32_t e3) const
+    {
+        const uint32_t second = e3 & 0x20000u;
+        if (CHECKED) {
+            put_if(base + i, e3, i < room);
+            put_if(base + i + 1, e3 >> 8, (i + 1 < room) ? second : 0u);
+        } else {
+            asm volatile("st.shared.u8 [%0], %1;" ::"r"(base + i), "r"(e3) : "memory");
+            put_if(base + i + 1, e3 >> 8, second);
+        }
+    }
+};
+
 __global__ void __launch_bounds__(DEC_THREADS)
 k_dec_write(const uint8_t *__restrict__ payload, DecPlan plan, DecTablesGlobal g,
             const uint16_t *__restrict__ sub_info, const uint64_t *__restrict__ seq_excl, uint8_t *__restrict__ out,
@@ -378,19 +471,15 @@ k_dec_write(const uint8_t *__restrict__ payload, DecPlan plan, DecTablesGlobal g
             uint4 *dst3 = reinterpret_cast<uint4 *>(ws.lut3);
             for (int i = tid; i < DEC_LUT_SIZE * 4 / 16; i += DEC_THREADS) dst3[i] = src3[i];
         }
-        dec_load_words(sh, payload, plan.pay_off[b], z, sib);
+        dec_load_rows(sh, payload, plan.pay_off[b], z, sib);
         const uint16_t rec = sub_info[seq * DEC_THREADS + tid];
         uint32_t total;
-        const uint32_t excl = block_excl_scan<DEC_THREADS>(sub_count(rec), sh.scan, &total);  // also fences the loads above
-        dec_build_pairs(sh);
-        __syncthreads();
-        DecView t = dec_view_of(sh);
-        t.lut3 = ws.lut3;
+        const uint32_t excl = block_excl_scan<DEC_THREADS>(sub_count(rec), sh.scan, &total);  // also fences the table loads above
+        const DecViewS t = dec_view_of(sh, nullptr, ws.lut3);
         const uint64_t bits_left = (z - sib * DEC_SEQ_BYTES) * 8;
         const uint32_t limit = bits_left < (uint64_t)DEC_SEQ_BYTES * 8 ? (uint32_t)bits_left : DEC_SEQ_BYTES * 8;
         const uint32_t sub_lo = tid * DEC_SUB_BITS;
-        const uint32_t sub_hi = sub_lo + DEC_SUB_BITS;
-        const uint32_t stop = sub_hi < limit ? sub_hi : limit;
+        const uint32_t stop = limit > sub_lo ? (limit - sub_lo < (uint32_t)DEC_SUB_BITS ? limit - sub_lo : (uint32_t)DEC_SUB_BITS) : 0u;
         const uint64_t n = plan.n[b];
         const uint64_t sfirst = seq_excl[seq];   // index of this sequence's first symbol inside the block
         if (sfirst >= n) continue;               // only padding garbage from here on (uniform for the CTA)
@@ -400,10 +489,16 @@ k_dec_write(const uint8_t *__restrict__ payload, DecPlan plan, DecTablesGlobal g
         const uint32_t room = excl < seq_syms ? seq_syms - excl : 0u;
         if (seq_syms <= (uint32_t)DEC_STAGE) {
             const uint32_t shift = (uint32_t)((uintptr_t)gdst & 15u);
-            uint8_t *dst = ws.stage + shift + excl;
-            const DecSub r = dec_emit_subsequence(t, sub_lo + sub_start(rec), stop, [&](uint32_t i, uint32_t sym) {
-                if (i < room) dst[i] = (uint8_t)sym;
-            });
+            uint32_t dst_s = smem_u32(ws.stage) + shift + excl;  // explicit st.shared: no generic address in the loop
+            asm volatile("" : "+r"(dst_s));
+            DecSub r;
+            if (seq_room >= total) {  // every symbol of this sequence is real (all but a block's last sequences)
+                StageSink<false> sink{dst_s, room};
+                r = dec_emit_to(t, tid * DEC_ROW, sub_start(rec), stop, sink);
+            } else {
+                StageSink<true> sink{dst_s, room};
+                r = dec_emit_to(t, tid * DEC_ROW, sub_start(rec), stop, sink);
+            }
             bad |= r.bad && room;
             __syncthreads();
             uint8_t *ga = gdst - shift;  // 16-byte aligned
@@ -417,7 +512,7 @@ k_dec_write(const uint8_t *__restrict__ payload, DecPlan plan, DecTablesGlobal g
             }
         } else {
             uint8_t *dst = gdst + excl;
-            const DecSub r = dec_emit_subsequence(t, sub_lo + sub_start(rec), stop, [&](uint32_t i, uint32_t sym) {
+            const DecSub r = dec_emit_subsequence(t, tid * DEC_ROW, sub_start(rec), stop, [&](uint32_t i, uint32_t sym) {
                 if (i < room) dst[i] = (uint8_t)sym;
             });
             bad |= r.bad && room;

@@ -127,7 +127,6 @@ __device__ __forceinline__ uint4 ld_nc16(const void *p)
 // Shared memory through explicit 32-bit shared addresses: one ADD per access instead of the
 // generic->shared window arithmetic the compiler emits for dynamic shared memory, and the
 // conditional OR as ONE predicated instruction instead of a branch around an atomic.
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ uint32_t lds32(uint32_t saddr)
 {
     uint32_t v;

@@ -559,18 +559,23 @@ static Bytes emu_sf_decode(const Bytes &payload, uint64_t n, const uint8_t *len,
     const uint64_t nseq = (z + DEC_SEQ_BYTES - 1) / DEC_SEQ_BYTES;
     std::vector<uint16_t> start(nseq * DEC_THREADS), count(nseq * DEC_THREADS);
     std::vector<uint32_t> seq_end(nseq);
-    auto load_pairs = [&](uint64_t seq, std::vector<uint64_t> &pairs) {
-        std::vector<uint32_t> words(DEC_SEQ_WORDS + DEC_WORDS_PAD + 4, 0);
-        for (size_t i = 0; i < words.size(); i++) {
-            uint32_t w = 0;
-            for (int k = 0; k < 4; k++) {
-                const uint64_t bo = seq * DEC_SEQ_BYTES + (uint64_t)i * 4 + k;
-                w = (w << 8) | (bo < z ? payload[bo] : 0);
-            }
-            words[i] = w;
-        }
+    auto load_pairs = [&](uint64_t seq, std::vector<uint64_t> &pairs) {  // dec_load_rows: one row per sub-sequence
         pairs.assign(DEC_PAIR_SLOTS, 0);
-        for (size_t i = 0; i < (size_t)(DEC_SEQ_WORDS + DEC_WORDS_PAD); i++) pairs[dec_pair_slot((uint32_t)i)] = ((uint64_t)words[i] << 32) | words[i + 1];
+        for (int sid = 0; sid < DEC_THREADS; sid++) {
+            uint32_t words[DEC_ROW_WORDS];
+            for (int i = 0; i < DEC_ROW_WORDS; i++) {
+                uint32_t w = 0;
+                for (int k = 0; k < 4; k++) {
+                    const uint64_t bo = seq * DEC_SEQ_BYTES + (uint64_t)sid * 16 + (uint64_t)i * 4 + k;
+                    w = (w << 8) | (bo < z ? payload[bo] : 0);
+                }
+                words[i] = w;
+            }
+            dec_row_from_words(words, pairs.data() + (size_t)sid * DEC_ROW);
+        }
+    };
+    auto sub_stop = [](uint32_t limit, uint32_t sub_lo) -> uint32_t {
+        return limit > sub_lo ? std::min<uint32_t>(limit - sub_lo, DEC_SUB_BITS) : 0u;
     };
     // phase 1
     for (uint64_t seq = 0; seq < nseq; seq++) {
@@ -581,12 +586,11 @@ static Bytes emu_sf_decode(const Bytes &payload, uint64_t n, const uint8_t *len,
         const uint32_t limit = (uint32_t)std::min<uint64_t>(bits_left, DEC_SEQ_BYTES * 8);
         uint32_t st[DEC_THREADS] = {0}, en[DEC_THREADS], cn[DEC_THREADS];
         auto run = [&](int tid) {
-            const uint32_t sub_lo = tid * DEC_SUB_BITS, sub_hi = sub_lo + DEC_SUB_BITS;
-            const uint32_t stop = std::min(sub_hi, limit);
-            DecSub r = dec_count_subsequence(t, sub_lo + st[tid], stop);
-            DecSub r1 = dec_emit_subsequence(t, sub_lo + st[tid], stop, DecNoEmit());
+            const uint32_t stop = sub_stop(limit, tid * DEC_SUB_BITS);
+            DecSub r = dec_count_subsequence(t, tid * DEC_ROW, st[tid], stop);
+            DecSub r1 = dec_emit_subsequence(t, tid * DEC_ROW, st[tid], stop, DecNoEmit());
             CHECK(r.end == r1.end && r.count == r1.count, "multi-symbol and single-symbol walks disagree");
-            en[tid] = r.end > sub_hi ? r.end - sub_hi : 0;
+            en[tid] = r.end > (uint32_t)DEC_SUB_BITS ? r.end - DEC_SUB_BITS : 0;
             cn[tid] = r.count;
         };
         for (int tid = 0; tid < DEC_THREADS; tid++) run(tid);
@@ -624,12 +628,11 @@ static Bytes emu_sf_decode(const Bytes &payload, uint64_t n, const uint8_t *len,
             for (int k = 0; k < DEC_THREADS; k++) {
                 const uint64_t gi = seq * DEC_THREADS + k;
                 if (start[gi] == cur) break;
-                const uint32_t sub_lo = k * DEC_SUB_BITS, sub_hi = sub_lo + DEC_SUB_BITS;
-                DecSub r = dec_count_subsequence(t, sub_lo + cur, std::min(sub_hi, limit));
+                DecSub r = dec_count_subsequence(t, k * DEC_ROW, cur, sub_stop(limit, k * DEC_SUB_BITS));
                 start[gi] = (uint16_t)cur;
                 count[gi] = (uint16_t)r.count;
                 touched = true;
-                cur = r.end > sub_hi ? r.end - sub_hi : 0;
+                cur = r.end > (uint32_t)DEC_SUB_BITS ? r.end - DEC_SUB_BITS : 0;
                 if (k == DEC_THREADS - 1) seq_end[seq] = cur;
             }
         }
@@ -650,10 +653,9 @@ static Bytes emu_sf_decode(const Bytes &payload, uint64_t n, const uint8_t *len,
         for (int tid = 0; tid < DEC_THREADS; tid++) {
             const uint64_t gi = seq * DEC_THREADS + tid;
             if (first < n) {
-                const uint32_t sub_lo = tid * DEC_SUB_BITS, sub_hi = sub_lo + DEC_SUB_BITS;
                 const uint64_t room = n - first;
                 uint8_t *dst = out.data() + first;
-                DecSub r = dec_emit_subsequence(t, sub_lo + start[gi], std::min(sub_hi, limit),
+                DecSub r = dec_emit_subsequence(t, tid * DEC_ROW, start[gi], sub_stop(limit, tid * DEC_SUB_BITS),
                                                 [&](uint32_t i, uint32_t sym) { if (i < room) dst[i] = (uint8_t)sym; });
                 CHECK(r.count == count[gi], "final decode count differs from the recorded count");
                 if (r.bad) bad = true;
