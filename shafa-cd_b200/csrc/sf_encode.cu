@@ -144,6 +144,51 @@ __device__ __forceinline__ void red_or_if(uint32_t saddr, uint32_t value, bool c
 // offset o lands in word o>>5 (and spills into the next word when it straddles); both pieces are
 // OR-ed in with shared-memory reductions, so no data-dependent "a word is full" branch diverges the warp.
 // orel = bit offset of the thread's first bit relative to the window start (negative if before it).
+__device__ __forceinline__ void st_shared_if(uint32_t saddr, uint32_t value, uint32_t cond)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p st.shared.b32 [%0], %1;\n\t}" ::"r"(saddr), "r"(value), "r"(cond) : "memory");
+}
+
+// Common case: all 64 symbols valid and every bit of the thread inside the staging window.  The codes
+// are shifted into a 64-bit accumulator and leave it one whole 32-bit word at a time, as plain stores:
+// a word the thread completes holds no bits of later threads, and the bits of EARLIER threads in its
+// first word (zeros here) are OR-ed in afterwards -- every thread's last, partial word is returned and
+// merged with a reduction only after a barrier (see the kernel).
+// PAIR: no code of the block is longer than 16 bits, so two codes are joined before they enter the
+// accumulator (31 pending bits + 32 <= 63) and the flush test runs once per two symbols.
+template <bool PAIR>
+__device__ __forceinline__ void enc_pack_fast(uint32_t lut_lane, uint32_t stage_s, uint4 (&v)[ENC_VECS], uint32_t orel,
+                                              uint32_t *tail_addr, uint32_t *tail_word)
+{
+    uint32_t nbits = orel & 31u;                  // bits of the open word that belong to earlier threads
+    uint32_t waddr = stage_s + (orel >> 5) * 4u;  // the open word
+    uint64_t acc = 0;
+#pragma unroll
+    for (int c = 0; c < ENC_VECS; c++) {
+        // opaque: the table addresses of later vectors must not be precomputed (they would be spilled)
+        asm volatile("" : "+r"(v[c].x), "+r"(v[c].y), "+r"(v[c].z), "+r"(v[c].w));
+#pragma unroll
+        for (int j = 0; j < 16; j += (PAIR ? 2 : 1)) {
+            const uint32_t e0 = lds32(lut_lane + byte_of(v[c], j) * (ENC_COPIES * 4));
+            uint32_t code = e0 >> 5, l = e0 & 31u;
+            if (PAIR) {
+                const uint32_t e1 = lds32(lut_lane + byte_of(v[c], j + 1) * (ENC_COPIES * 4));
+                const uint32_t l1 = e1 & 31u;
+                code = (code << l1) | (e1 >> 5);
+                l += l1;
+            }
+            acc = (acc << l) | code;
+            nbits += l;
+            const uint32_t full = nbits >> 5;  // 0 or 1
+            st_shared_if(waddr, (uint32_t)(acc >> ((nbits - 32u) & 31u)), full);
+            waddr += full * 4u;
+            nbits &= 31u;
+        }
+    }
+    *tail_addr = waddr;
+    *tail_word = nbits ? (uint32_t)(acc << (32u - nbits)) : 0u;
+}
+
 template <bool ALL_VALID>
 __device__ __forceinline__ void enc_pack_thread(uint32_t lut_lane, uint32_t stage_s, const uint4 (&v)[ENC_VECS], uint64_t vmask,
                                                 int32_t orel, uint32_t nw)
@@ -178,7 +223,7 @@ k_sf_encode(const uint8_t *__restrict__ in, const uint64_t *__restrict__ off, co
     const unsigned tid = threadIdx.x, lane = lane_id(), warp = warp_id();
     const uint64_t total_tiles = tile0[nb];
     uint32_t cur_block = 0xffffffffu;
-    bool cur_long = false;
+    bool cur_long = false, cur_pair = false;
 
     for (;;) {
         __syncthreads();  // everyone is done with the previous tile's shared state
@@ -196,6 +241,7 @@ k_sf_encode(const uint8_t *__restrict__ in, const uint64_t *__restrict__ off, co
             const uint32_t l = lens[(uint64_t)b * 256 + tid];
             const uint64_t c = codes[(uint64_t)b * 256 + tid];
             cur_long = __syncthreads_or(l > (uint32_t)ENC_SHORT_MAX) != 0;
+            cur_pair = __syncthreads_or(l > 16u) == 0;
             if (!cur_long) {
                 sh.entry[tid] = enc_entry(c, l);
                 __syncthreads();
@@ -270,8 +316,20 @@ k_sf_encode(const uint8_t *__restrict__ in, const uint64_t *__restrict__ off, co
             const uint32_t nw = (uint32_t)((Wtouch - win < (uint64_t)ENC_STAGE_WORDS) ? (Wtouch - win) : ENC_STAGE_WORDS);
             for (uint32_t k = tid; k < nw; k += ENC_THREADS) sh.stage[k] = 0;
             __syncthreads();
-            if (bits && wl > win && wf < win + nw) {
-                const int32_t orel = (int32_t)((int64_t)p - (int64_t)(win << 5));  // |orel| < 2^31: a tile holds < 2^19 bits
+            const bool mine = bits && wl > win && wf < win + nw;
+            const bool fast = mine && all_valid && wf >= win && wl <= win + nw;
+            const int32_t orel = (int32_t)((int64_t)p - (int64_t)(win << 5));  // |orel| < 2^31: a tile holds < 2^19 bits
+            uint32_t tail_addr = 0, tail_word = 0;
+            if (fast) {
+                if (cur_pair)
+                    enc_pack_fast<true>(lut_lane, smem_u32(sh.stage), v, (uint32_t)orel, &tail_addr, &tail_word);
+                else
+                    enc_pack_fast<false>(lut_lane, smem_u32(sh.stage), v, (uint32_t)orel, &tail_addr, &tail_word);
+            }
+            __syncthreads();  // plain stores of whole words first, then every OR into a shared word
+            if (fast) {
+                red_or_if(tail_addr, tail_word, tail_word != 0);
+            } else if (mine) {
                 if (all_valid)
                     enc_pack_thread<true>(lut_lane, smem_u32(sh.stage), v, vmask, orel, nw);
                 else
