@@ -179,6 +179,62 @@ __device__ __forceinline__ uint64_t lookback_sum(uint64_t *desc, int64_t tile, i
     return excl;
 }
 
+// The same in two steps, so that work which does not need the prefix can run in between: publish the
+// aggregate (one thread) as soon as it is known, resolve (one warp) when the prefix is needed.
+__device__ __forceinline__ void lookback_publish(uint64_t *desc, int64_t tile, int64_t first, uint64_t aggregate)
+{
+    desc_store(desc + tile, desc_pack(tile == first ? DESC_PREFIX : DESC_AGG, aggregate));
+}
+__device__ __forceinline__ uint64_t lookback_resolve(uint64_t *desc, int64_t tile, int64_t first, uint64_t aggregate)
+{
+    if (tile == first) return 0;
+    const uint64_t excl = lookback_read(desc, tile, first);
+    if (lane_id() == 0) desc_store(desc + tile, desc_pack(DESC_PREFIX, excl + aggregate));
+    return excl;
+}
+
+// Copy n bytes of shared memory (src 16-byte aligned, readable up to src + n + 32) to global memory at
+// dst (ANY alignment) with 16-byte stores, by all NT threads of the CTA.  The tile is staged at
+// tile-relative offsets -- before its place in the output is known -- so the two are not co-aligned:
+// each 16-byte destination chunk is cut out of two aligned 16-byte shared loads with funnel shifts.
+// The misalignment is the same for every chunk, so the word selection is a uniform branch.
+template <int NT>
+__device__ __forceinline__ void copy_out_unaligned(uint8_t *dst, const uint8_t *src, uint32_t n)
+{
+    const uint32_t tid = threadIdx.x;
+    const uint32_t r = (16u - (uint32_t)((uintptr_t)dst & 15u)) & 15u;  // bytes before dst's first 16-byte boundary
+    const uint32_t head = r < n ? r : n;
+    if (tid < head) dst[tid] = src[tid];
+    const uint32_t body = (n - head) >> 4;  // whole 16-byte chunks; chunk k = src bytes [r + 16k, r + 16k + 16)
+    uint8_t *const d16 = dst + head;
+    if (r == 0) {
+        for (uint32_t k = tid; k < body; k += NT) st_stream16(d16 + 16 * k, *reinterpret_cast<const uint4 *>(src + 16 * k));
+    } else {
+        const uint32_t wr = r >> 2, sh8 = (r & 3u) * 8u;
+        for (uint32_t k = tid; k < body; k += NT) {
+            const uint4 a = *reinterpret_cast<const uint4 *>(src + 16 * k);
+            const uint4 b = *reinterpret_cast<const uint4 *>(src + 16 * k + 16);
+            uint32_t w0, w1, w2, w3, w4;  // the five words that hold the chunk
+            if (wr == 0)
+                w0 = a.x, w1 = a.y, w2 = a.z, w3 = a.w, w4 = b.x;
+            else if (wr == 1)
+                w0 = a.y, w1 = a.z, w2 = a.w, w3 = b.x, w4 = b.y;
+            else if (wr == 2)
+                w0 = a.z, w1 = a.w, w2 = b.x, w3 = b.y, w4 = b.z;
+            else
+                w0 = a.w, w1 = b.x, w2 = b.y, w3 = b.z, w4 = b.w;
+            uint4 o;
+            o.x = __funnelshift_r(w0, w1, sh8);
+            o.y = __funnelshift_r(w1, w2, sh8);
+            o.z = __funnelshift_r(w2, w3, sh8);
+            o.w = __funnelshift_r(w3, w4, sh8);
+            st_stream16(d16 + 16 * k, o);
+        }
+    }
+    const uint32_t done = head + 16 * body;
+    if (tid < n - done) dst[done + tid] = src[done + tid];
+}
+
 // bit k (k = 0..3) of the result = (byte k of w == 0).  Exact zero-byte test without the emulated
 // SIMD-video intrinsics: t has 0x80 in every zero byte; the multiply gathers bits 7/15/23/31 into a nibble.
 __device__ __forceinline__ uint32_t zero_nibble(uint32_t w)

@@ -30,7 +30,7 @@ constexpr int RLD_STAGE = 32768;                          // staging window (byt
 constexpr uint64_t RLE_BLOCK_CAP = 67108864ull + 1024ull;  // d.c:135,163
 
 struct RleDecShared {
-    alignas(16) uint8_t stage[RLD_STAGE + 16];
+    alignas(16) uint8_t stage[RLD_STAGE + 32];  // + the read-ahead of copy_out_unaligned
     uint8_t compose[64 * 64];  // compose[a*64+b] = first a, then b
     uint32_t scan[RLD_WARPS + 1];
     uint32_t wmap[RLD_WARPS];
@@ -221,33 +221,18 @@ k_rle_decode(const uint8_t *__restrict__ in, const uint64_t *__restrict__ off, c
         }
         uint32_t tile_out;
         const uint32_t my_out = block_excl_scan<RLD_THREADS>(obytes, sh.scan, &tile_out);
-        if (warp == 0) {
-            const uint64_t pfx = lookback_sum(desc_out, (int64_t)t, 0, tile_out);
-            if (lane == 0) sh.out_prefix = pfx;
-        }
-        __syncthreads();
-        const uint64_t out0 = sh.out_prefix;
-        if (is_last && tid == 0) {
-            blk_end[b] = out0 + tile_out;
-            if (fsm_apply(sh.tile_map, tile_entry) != 0) atomicOr(err, (uint32_t)ERR_RLE_TRUNCATED);  // block ends inside a triple
-        }
-        if (out0 + tile_out > out_capacity) {
-            if (tid == 0) atomicOr(err, (uint32_t)ERR_CAPACITY);
-            continue;
-        }
-        if (tile_out == 0) continue;
+        if (tid == 0) lookback_publish(desc_out, (int64_t)t, 0, tile_out);  // the size now, the place after the staging
 
-        // ---- materialise the tile's output, one staging window at a time ----
-        const uint32_t shift = (uint32_t)(out0 & 15u);
-        uint8_t *const gbase = out + (out0 - shift);  // 16-byte aligned; stage index s <-> gbase[s] in window 0
-        const uint32_t span = shift + tile_out;       // window k covers stage-space [k*RLD_STAGE, (k+1)*RLD_STAGE) of this span
-        const bool single = span <= (uint32_t)RLD_STAGE;
-        for (uint32_t w0 = 0; w0 < span; w0 += RLD_STAGE) {
-            const uint32_t w1 = (span - w0 < (uint32_t)RLD_STAGE) ? span : (w0 + RLD_STAGE);
-            // my output occupies span-space [a, a+obytes)
-            const uint32_t a = shift + my_out;
+        // ---- materialise the tile's output at tile-relative offsets, one staging window at a time ----
+        const bool single = tile_out <= (uint32_t)RLD_STAGE;
+        bool placed = false;
+        uint64_t out0 = 0;
+        for (uint32_t w0 = 0; w0 < tile_out || !placed; w0 += RLD_STAGE) {
+            const uint32_t w1 = (tile_out - w0 < (uint32_t)RLD_STAGE) ? tile_out : (w0 + RLD_STAGE);
+            // my output occupies tile-space [a, a+obytes)
+            const uint32_t a = my_out;
             if (obytes && a < w1 && a + obytes > w0) {
-                uint8_t *sb = sh.stage - w0;  // sb[x] is span-space position x
+                uint8_t *sb = sh.stage - w0;  // sb[x] is tile-space position x
                 uint32_t o = a;
                 if (full && single) {
                     // literals: one uniform, fully predicated pass -- the offset of position q is
@@ -304,7 +289,7 @@ k_rle_decode(const uint8_t *__restrict__ in, const uint64_t *__restrict__ off, c
                         const uint32_t len = cnt ? cnt : 1u;
                         if (len <= 16) {
                             const uint32_t sym = q ? (uint32_t)in[pos + q - 1] : prevb;
-                            uint8_t *d = sh.stage + shift + my_out + (uint32_t)__popcll(m.lit & ((1ull << q) - 1ull)) + cum;
+                            uint8_t *d = sh.stage + my_out + (uint32_t)__popcll(m.lit & ((1ull << q) - 1ull)) + cum;
                             for (uint32_t k = 0; k < len; k++) d[k] = (uint8_t)sym;
                         } else {
                             long_runs |= 1ull << q;
@@ -319,7 +304,7 @@ k_rle_decode(const uint8_t *__restrict__ in, const uint64_t *__restrict__ off, c
                     uint64_t rb = __shfl_sync(FULL, m.run, src);  // that lane's count-byte positions
                     const uint64_t lr = __shfl_sync(FULL, long_runs, src);
                     const uint64_t lt = __shfl_sync(FULL, m.lit, src);
-                    const uint32_t a_src = __shfl_sync(FULL, shift + my_out, src);
+                    const uint32_t a_src = __shfl_sync(FULL, my_out, src);
                     const uint32_t prev_src = __shfl_sync(FULL, prevb, src);
                     const uint64_t pos_src = pos - ((uint64_t)lane - (uint64_t)src) * RLD_PER_THREAD;
                     uint32_t cum = 0;  // bytes of the runs before the current one
@@ -337,16 +322,27 @@ k_rle_decode(const uint8_t *__restrict__ in, const uint64_t *__restrict__ off, c
                     }
                 }
             }
-            __syncthreads();
-            // copy the window out: stage[s - w0] -> gbase[s] for s in [max(w0, shift), w1)
-            for (uint32_t c = w0 + tid * 16; c < w1; c += RLD_THREADS * 16) {
-                if (c >= shift && c + 16 <= w1) {
-                    st_stream16(gbase + c, *reinterpret_cast<const uint4 *>(sh.stage + (c - w0)));
-                } else {
-                    for (uint32_t k = (c > shift ? c : shift); k < c + 16 && k < w1; k++) gbase[k] = sh.stage[k - w0];
+            if (!placed) {  // first window: the tile's place in the output, looked up behind the staging work
+                if (warp == 0) {
+                    const uint64_t pfx = lookback_resolve(desc_out, (int64_t)t, 0, tile_out);
+                    if (lane == 0) sh.out_prefix = pfx;
                 }
+                __syncthreads();
+                placed = true;
+                out0 = sh.out_prefix;
+                if (is_last && tid == 0) {
+                    blk_end[b] = out0 + tile_out;
+                    if (fsm_apply(sh.tile_map, tile_entry) != 0) atomicOr(err, (uint32_t)ERR_RLE_TRUNCATED);  // block ends inside a triple
+                }
+                if (out0 + tile_out > out_capacity) {
+                    if (tid == 0) atomicOr(err, (uint32_t)ERR_CAPACITY);
+                    break;
+                }
+            } else {
+                __syncthreads();
             }
-            if (w1 < span) __syncthreads();  // the next window overwrites the stage
+            if (w1 > w0) copy_out_unaligned<RLD_THREADS>(out + out0 + w0, sh.stage, w1 - w0);
+            if (w1 < tile_out) __syncthreads();  // the next window overwrites the stage
         }
     }
 }

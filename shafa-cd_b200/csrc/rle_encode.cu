@@ -30,7 +30,7 @@ namespace shafa {
 
 constexpr int RLE_WARPS = RLE_THREADS / 32;
 constexpr int RLE_PER_THREAD = RLE_ITEMS * RLE_VECS;     // 64
-constexpr int RLE_STAGE = 2 * RLE_TILE + 3 + 16 + 13;    // worst case 2n+3 (f.c:244) + alignment slack, multiple of 16
+constexpr int RLE_STAGE = 2 * RLE_TILE + 48;             // worst case 2n+3 (f.c:244) + the read-ahead of copy_out_unaligned
 constexpr int RLE_HIST_COPIES = 8;
 
 struct RleEncShared {
@@ -222,23 +222,24 @@ k_rle_encode(const uint8_t *__restrict__ in, uint64_t n, uint64_t block_size, ui
         }
         const uint32_t my_bytes = (uint32_t)__popcll(lit) + 3u * (uint32_t)__popcll(tri);
 
-        // ---- 4. offsets ----
+        // ---- 4. offsets: publish the tile's size at once, resolve its place only after the staging ----
         uint32_t tile_bytes;
         const uint32_t excl = block_excl_scan<RLE_THREADS>(my_bytes, sh.scan, &tile_bytes);
-        if (warp == 0) {
-            const uint64_t pfx = lookback_sum(desc_out, (int64_t)t, 0, tile_bytes);
-            if (lane == 0) sh.out_prefix = pfx;
+        if (tid == 0) lookback_publish(desc_out, (int64_t)t, 0, tile_bytes);
+        if (!WRITE && !HIST) {
+            if (warp == 0 && last_tile) {
+                const uint64_t pfx = lookback_resolve(desc_out, (int64_t)t, 0, tile_bytes);
+                if (lane == 0) blk_end[b] = pfx + tile_bytes;
+            } else if (warp == 0) {
+                lookback_resolve(desc_out, (int64_t)t, 0, tile_bytes);
+            }
+            continue;
         }
-        __syncthreads();
-        const uint64_t out0 = sh.out_prefix;
-        if (last_tile && tid == 0) blk_end[b] = out0 + tile_bytes;
-        if (!WRITE && !HIST) continue;
 
-        // ---- 5. stage + copy out + fused histogram ----
-        const uint32_t shift = (uint32_t)(out0 & 15u);  // co-align staging with the destination
+        // ---- 5. stage at tile-relative offsets (needs no prefix: the look-back latency hides behind it) ----
         {
             // literals: one uniform, fully predicated pass with a running offset; a triple just reserves 3 bytes
-            uint8_t *const dst0 = sh.stage + shift + excl;
+            uint8_t *const dst0 = sh.stage + excl;
             uint32_t o = 0;
 #pragma unroll
             for (int c = 0; c < RLE_VECS; c++) {
@@ -268,40 +269,34 @@ k_rle_encode(const uint8_t *__restrict__ in, uint64_t n, uint64_t block_size, ui
                 d[2] = (uint8_t)rle_run_remaining(sh.heads, p0 + (uint32_t)q);
             }
         }
+        if (warp == 0) {
+            const uint64_t pfx = lookback_resolve(desc_out, (int64_t)t, 0, tile_bytes);
+            if (lane == 0) sh.out_prefix = pfx;
+        }
         __syncthreads();
+        const uint64_t out0 = sh.out_prefix;
+        if (last_tile && tid == 0) blk_end[b] = out0 + tile_bytes;
+
+        // ---- 6. copy out + fused histogram ----
         if (WRITE) {
             if (out0 + tile_bytes > out_capacity) {
                 if (tid == 0) atomicOr(err, (uint32_t)ERR_CAPACITY);
             } else {
-                uint8_t *dst = out + (out0 - shift);  // 16-byte aligned
-                const uint32_t end = shift + tile_bytes;
-                for (uint32_t c = tid * 16; c < end; c += RLE_THREADS * 16) {
-                    if (c >= shift && c + 16 <= end) {
-                        st_stream16(dst + c, *reinterpret_cast<const uint4 *>(sh.stage + c));
-                    } else {
-                        for (uint32_t k = (c > shift ? c : shift); k < c + 16 && k < end; k++) dst[k] = sh.stage[k];
-                    }
-                }
+                copy_out_unaligned<RLE_THREADS>(out + out0, sh.stage, tile_bytes);
             }
         }
         if (HIST) {
             uint32_t *mine = sh.hist + (lane & (RLE_HIST_COPIES - 1));
-            const uint32_t end = shift + tile_bytes;
             const uint32_t *stage32 = reinterpret_cast<const uint32_t *>(sh.stage);
-            for (uint32_t w = tid; w * 4 < end; w += RLE_THREADS) {
+            const uint32_t whole = tile_bytes >> 2;
+            for (uint32_t w = tid; w < whole; w += RLE_THREADS) {
                 const uint32_t word = stage32[w];
-                const uint32_t c = w * 4;
-                if (c >= shift && c + 4 <= end) {
-                    atomicAdd(&mine[(word & 0xffu) * RLE_HIST_COPIES], 1u);
-                    atomicAdd(&mine[((word >> 8) & 0xffu) * RLE_HIST_COPIES], 1u);
-                    atomicAdd(&mine[((word >> 16) & 0xffu) * RLE_HIST_COPIES], 1u);
-                    atomicAdd(&mine[(word >> 24) * RLE_HIST_COPIES], 1u);
-                } else {
-#pragma unroll
-                    for (int k = 0; k < 4; k++)
-                        if (c + k >= shift && c + k < end) atomicAdd(&mine[((word >> (8 * k)) & 0xffu) * RLE_HIST_COPIES], 1u);
-                }
+                atomicAdd(&mine[(word & 0xffu) * RLE_HIST_COPIES], 1u);
+                atomicAdd(&mine[((word >> 8) & 0xffu) * RLE_HIST_COPIES], 1u);
+                atomicAdd(&mine[((word >> 16) & 0xffu) * RLE_HIST_COPIES], 1u);
+                atomicAdd(&mine[(word >> 24) * RLE_HIST_COPIES], 1u);
             }
+            if (tid < (tile_bytes & 3u)) atomicAdd(&mine[(uint32_t)sh.stage[whole * 4 + tid] * RLE_HIST_COPIES], 1u);
             __syncthreads();
             uint32_t sum = 0;
 #pragma unroll

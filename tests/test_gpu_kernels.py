@@ -206,6 +206,19 @@ def test_sf_encode_tile_with_long_codes_everywhere(shafa, orc):
     _check_sf_encode_decode(shafa, orc, body, offs, False)
 
 
+def test_sf_encode_codes_between_17_and_26_bits(shafa, orc):
+    """Halving counts give a deep code (max 17..26 bits): the accumulator path that takes one code at a time,
+    with rare long codes sprinkled through otherwise ordinary tiles and ragged block edges."""
+    rng = np.random.default_rng(17)
+    counts = [max(1, 600_000 >> i) for i in range(24)]
+    body = np.repeat((np.arange(24, dtype=np.uint8) * 7 + 3), counts)
+    rng.shuffle(body)
+    offs = np.array([0, 5, 400_001, body.size], dtype=np.uint64)
+    ln, _, _ = _codes_for(orc, body, offs)
+    assert 16 < ln[1].max() <= 26 and 16 < ln[2].max() <= 26
+    _check_sf_encode_decode(shafa, orc, body, offs, True)
+
+
 def test_sf_encode_symbol_without_code(shafa, orc, pkg):
     data = pkg.datagen.zipf(50_000, seed=1)
     offs = np.array([0, data.size], dtype=np.uint64)
