@@ -297,64 +297,101 @@ k_sf_encode(const uint8_t *__restrict__ in, const uint64_t *__restrict__ off, co
         for (int c = 0; c < ENC_VECS; c++) asm volatile("" : "+r"(v[c].x), "+r"(v[c].y), "+r"(v[c].z), "+r"(v[c].w));
         uint32_t tile_bits;
         const uint32_t excl = block_excl_scan<ENC_THREADS>(bits, sh.scan, &tile_bits);
-        if (warp == 0) {
-            const uint64_t pfx = lookback_sum(desc, (int64_t)t, (int64_t)first_tile, tile_bits);
-            if (lane == 0) sh.prefix = pfx;
-        }
-        __syncthreads();
-        const uint64_t P = sh.prefix;  // bits of this block before this tile
-        const uint64_t E = P + tile_bits;
-        const uint64_t W0 = P >> 5;
-        const uint64_t Wtouch = (E + 31) >> 5;                  // words holding bits of this tile: [W0, Wtouch)
-        const uint64_t Wown = is_last ? Wtouch : (E >> 5);      // words whose last bit lies in [P, E) (all, for the last tile)
-        const uint64_t p = P + excl;                            // my first bit
-        const uint64_t wf = p >> 5, wl = (p + bits + 31) >> 5;  // my words: [wf, wl)
+        // The tile's size is published at once; its place in the block's bit stream (P) is resolved behind
+        // the packing, which works in tile-relative bit positions.  stage[1 + j] is word j of the tile's own
+        // bit string; stage[0] holds the 32 bits just before it, so that output word k of the tile -- bits
+        // [32k - r, 32k - r + 32) of the tile with r = P mod 32 -- is one funnel shift of stage[k], stage[k+1].
+        if (tid == 0) lookback_publish(desc, (int64_t)t, (int64_t)first_tile, tile_bits);
+        const uint32_t Tw = (tile_bits + 31u) >> 5;                           // words of the tile's own bit string
+        const uint32_t wf = excl >> 5, wl = (excl + bits + 31u) >> 5;         // my words: [wf, wl)
         uint32_t *out32 = reinterpret_cast<uint32_t *>(payload + pay_off[b]);
+        const uint32_t stage_s = smem_u32(sh.stage) + 4u;                     // shared address of stage[1]
+        uint64_t P = 0, W0 = 0;
+        uint32_t r = 0, Kown = 0;
 
-        // the tile's bit range is materialised window by window (one window unless codes are very long here)
-        for (uint64_t win = W0; win < Wtouch; win += ENC_STAGE_WORDS) {
-            const uint32_t nw = (uint32_t)((Wtouch - win < (uint64_t)ENC_STAGE_WORDS) ? (Wtouch - win) : ENC_STAGE_WORDS);
-            for (uint32_t k = tid; k < nw; k += ENC_THREADS) sh.stage[k] = 0;
+        // the bit string is materialised window by window (one window unless codes are very long here)
+        for (uint32_t jw = 0; jw < Tw || jw == 0; jw += ENC_STAGE_WORDS) {
+            const uint32_t nw = (Tw - jw < (uint32_t)ENC_STAGE_WORDS) ? (Tw - jw) : (uint32_t)ENC_STAGE_WORDS;
+            if (jw) {  // the word just before this window
+                if (tid == 0) sh.stage[0] = sh.stage[ENC_STAGE_WORDS];
+                __syncthreads();
+            }
+            for (uint32_t k = tid; k <= nw; k += ENC_THREADS) sh.stage[1 + k] = 0;  // one more: read as the word after the end
             __syncthreads();
-            const bool mine = bits && wl > win && wf < win + nw;
-            const bool fast = mine && all_valid && wf >= win && wl <= win + nw;
-            const int32_t orel = (int32_t)((int64_t)p - (int64_t)(win << 5));  // |orel| < 2^31: a tile holds < 2^19 bits
+            const bool mine = bits && wl > jw && wf < jw + nw;
+            const bool fast = mine && all_valid && wf >= jw && wl <= jw + nw;
+            const int32_t orel = (int32_t)excl - (int32_t)(jw << 5);  // a tile holds < 2^19 bits
             uint32_t tail_addr = 0, tail_word = 0;
             if (fast) {
                 if (cur_pair)
-                    enc_pack_fast<true>(lut_lane, smem_u32(sh.stage), v, (uint32_t)orel, &tail_addr, &tail_word);
+                    enc_pack_fast<true>(lut_lane, stage_s, v, (uint32_t)orel, &tail_addr, &tail_word);
                 else
-                    enc_pack_fast<false>(lut_lane, smem_u32(sh.stage), v, (uint32_t)orel, &tail_addr, &tail_word);
+                    enc_pack_fast<false>(lut_lane, stage_s, v, (uint32_t)orel, &tail_addr, &tail_word);
             }
             __syncthreads();  // plain stores of whole words first, then every OR into a shared word
             if (fast) {
                 red_or_if(tail_addr, tail_word, tail_word != 0);
             } else if (mine) {
                 if (all_valid)
-                    enc_pack_thread<true>(lut_lane, smem_u32(sh.stage), v, vmask, orel, nw);
+                    enc_pack_thread<true>(lut_lane, stage_s, v, vmask, orel, nw);
                 else
-                    enc_pack_thread<false>(lut_lane, smem_u32(sh.stage), v, vmask, orel, nw);
+                    enc_pack_thread<false>(lut_lane, stage_s, v, vmask, orel, nw);
             }
-            // leading partial word: bits of the symbols just before this tile
-            if (warp == 1 && win == W0 && !is_first && (P & 31u)) {
-                const uint32_t r = (uint32_t)(P & 31u);
-                uint32_t ee = 0;  // not the first tile => base > lo
-                if (base >= lo + 1 + lane) ee = sh.lut[(uint32_t)in[base - 1 - lane] * ENC_COPIES + lane];
-                const uint32_t l = ee & 31u;
-                const uint32_t s_incl = warp_incl_scan(l);
-                const uint32_t s_prev = s_incl - l;  // bits of nearer symbols
-                uint32_t w = 0;
-                if (l && s_prev < r) {
-                    const uint32_t room = r - s_prev;  // 1..31 bits of the word still free towards the MSB side
-                    w = ((ee >> 5) & ((1u << room) - 1u)) << (32 - r + s_prev);
+            if (jw == 0) {
+                if (warp == 1) {
+                    // stage[0]: the last 32 bits of the block's stream before this tile = the codes of the
+                    // (up to) 32 symbols just before it, right-aligned (what lies further back is shifted out)
+                    uint32_t ee = 0;
+                    if (base >= lo + 1 + lane) ee = sh.lut[(uint32_t)in[base - 1 - lane] * ENC_COPIES + lane];
+                    const uint32_t l = ee & 31u;
+                    const uint32_t s_prev = warp_incl_scan(l) - l;  // bits of nearer symbols
+                    uint32_t w = (l && s_prev < 32u) ? ((ee >> 5) << s_prev) : 0u;
+                    w = __reduce_or_sync(FULL, w);
+                    if (lane == 0) sh.stage[0] = w;
                 }
-                w = __reduce_or_sync(FULL, w);
-                if (lane == 0 && w) atomicOr(&sh.stage[0], w);
+                if (warp == 0) {
+                    const uint64_t pfx = lookback_resolve(desc, (int64_t)t, (int64_t)first_tile, tile_bits);
+                    if (lane == 0) sh.prefix = pfx;
+                }
             }
             __syncthreads();
-            const uint64_t cend = (Wown < win + nw) ? Wown : (win + nw);
-            for (uint64_t w = win + tid; w < cend; w += ENC_THREADS) st_stream4(out32 + w, bswap32(sh.stage[w - win]));
-            if (win + ENC_STAGE_WORDS < Wtouch) __syncthreads();  // the next window re-zeroes the stage
+            if (jw == 0) {
+                P = sh.prefix;  // bits of this block before this tile
+                const uint64_t E = P + tile_bits;
+                W0 = P >> 5;
+                r = (uint32_t)(P & 31u);
+                const uint64_t Wown = is_last ? ((E + 31) >> 5) : (E >> 5);  // words whose last bit lies in [P, E) (all, for the last tile)
+                Kown = (uint32_t)(Wown - W0);
+            }
+            // output words k in [jw, kend): word k = stage[k - jw], stage[k - jw + 1] shifted by r
+            const bool last_win = (jw + nw >= Tw);
+            uint32_t kend = last_win ? Kown : (jw + nw);
+            if (kend > jw + nw + 1) kend = jw + nw + 1;
+            if (kend > Kown) kend = Kown;
+            if (kend > jw) {
+                const uint64_t gfirst = W0 + jw, glast = W0 + kend;  // global words of the block's payload
+                for (uint64_t Q = (gfirst >> 2) + tid; Q * 4 < glast; Q += ENC_THREADS) {
+                    const int64_t s0 = (int64_t)(Q * 4) - (int64_t)gfirst;  // stage index of the quad's first "previous" word
+                    if (Q * 4 >= gfirst && Q * 4 + 4 <= glast) {
+                        const uint32_t a0 = sh.stage[s0], a1 = sh.stage[s0 + 1], a2 = sh.stage[s0 + 2], a3 = sh.stage[s0 + 3],
+                                       a4 = sh.stage[s0 + 4];
+                        uint4 o;
+                        o.x = bswap32(__funnelshift_r(a1, a0, r));
+                        o.y = bswap32(__funnelshift_r(a2, a1, r));
+                        o.z = bswap32(__funnelshift_r(a3, a2, r));
+                        o.w = bswap32(__funnelshift_r(a4, a3, r));
+                        st_stream16(out32 + Q * 4, o);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 4; i++) {
+                            const uint64_t g = Q * 4 + i;
+                            if (g >= gfirst && g < glast)
+                                st_stream4(out32 + g, bswap32(__funnelshift_r(sh.stage[s0 + i + 1], sh.stage[s0 + i], r)));
+                        }
+                    }
+                }
+            }
+            if (!last_win) __syncthreads();  // the next window re-zeroes the stage
         }
     }
     (void)err;  // a symbol without a code is caught by k_sf_block_bits (histogram x length) before this kernel runs
