@@ -3,17 +3,21 @@
 //
 // The .shaf format has no sync points, so this is self-synchronising
 // sub-sequence decoding (Weissenberger & Schmidt, ICPP'18):
-//   k_dec_tables   per block: codes sorted by left-aligned bits + 12-bit LUT
-//   k_dec_sync     one CTA per 4 KiB "sequence" of a block's payload, one thread
-//                  per 128-bit sub-sequence: decode speculatively from the
-//                  sub-sequence start, then repeatedly restart from where the
-//                  left neighbour really ended until nothing changes
-//   k_dec_stitch   across sequence boundaries: feed each sequence the true end
-//                  of its predecessor and re-walk until it meets the recorded
-//                  state; repeated while anything changed
-//   k_dec_count / k_dec_scan   symbols per sequence -> output offsets
-//   k_dec_write    final decode from the agreed start points, symbols written
-//                  at their scanned offsets, clipped at the block's symbol count
+//   k_dec_tables   per block: codes sorted by left-aligned bits, 12-bit LUT (one code),
+//                  lut2 (all whole codes of a window: count + bits), lut3 (first two codes)
+//   k_dec_sync     persistent CTAs, each owning a contiguous chunk of 4 KiB "sequences";
+//                  one thread per 128-bit sub-sequence: decode speculatively from the
+//                  sub-sequence start, then restart from where the left neighbour
+//                  really ended until nothing changes (later rounds are compacted).
+//                  A sequence's first sub-sequence starts where the chunk's previous
+//                  sequence ended; per-sequence symbol counts are produced here
+//   k_dec_stitch   across chunk boundaries: feed each sequence the true end of its
+//                  predecessor and re-walk until it meets the recorded state;
+//                  repeated while a sequence end moved
+//   k_dec_scan     symbols per sequence -> output offsets
+//   k_dec_write    final decode from the agreed start points (two codes per lookup),
+//                  symbols staged and written at their scanned offsets, clipped at
+//                  the block's symbol count
 // Algorithmic bytes: Z (payload in) + S (symbols out).
 #include "common.cuh"
 #include "core.h"
@@ -235,7 +239,7 @@ __device__ __forceinline__ void dec_chunk(uint64_t nseq, uint64_t *first, uint64
 // ---- phase 1: synchronise inside each sequence ----------------------------------------------
 __global__ void __launch_bounds__(DEC_THREADS)
 k_dec_sync(const uint8_t *__restrict__ payload, DecPlan plan, DecTablesGlobal g, uint16_t *__restrict__ sub_info,
-           uint32_t *__restrict__ seq_end, uint64_t nseq)
+           uint32_t *__restrict__ seq_end, uint32_t *__restrict__ seq_count, uint64_t nseq)
 {
     __shared__ DecShared sh;
     __shared__ __align__(16) uint16_t s_lut2[DEC_LUT_SIZE];
@@ -244,10 +248,12 @@ k_dec_sync(const uint8_t *__restrict__ payload, DecPlan plan, DecTablesGlobal g,
     __shared__ uint16_t s_count[DEC_THREADS];
     __shared__ uint32_t s_list[DEC_THREADS];    // compacted work list of a sparse round: sub-sequence | start << 16
     __shared__ uint32_t s_wcnt[DEC_THREADS / 32];
+    __shared__ uint32_t s_wsum[DEC_THREADS / 32];
     const unsigned tid = threadIdx.x, lane = lane_id(), warp = warp_id();
     uint64_t seq_first, seq_last;
     dec_chunk(nseq, &seq_first, &seq_last);
     uint32_t cur_block = 0xffffffffu;
+    uint32_t carry = 0;  // where the previous sequence of this CTA's chunk left its last sub-sequence
     for (uint64_t seq = seq_first; seq < seq_last; seq++) {
         __syncthreads();  // previous sequence fully consumed
         if (tid == 0) sh.block = find_block(plan.seq0, plan.nb, seq);
@@ -259,6 +265,9 @@ k_dec_sync(const uint8_t *__restrict__ payload, DecPlan plan, DecTablesGlobal g,
             cur_block = b;
             dec_load_tables(sh, g, b, s_lut2);
         }
+        // The first sub-sequence starts where the previous sequence ended.  Inside a chunk that is known;
+        // the first sequence of a chunk assumes 0 and k_dec_stitch repairs it (a block's first sequence IS 0).
+        if (sib == 0 || seq == seq_first) carry = 0;
         dec_load_rows(sh, payload, plan.pay_off[b], z, sib);
         __syncthreads();
         const DecViewS t = dec_view_of(sh, s_lut2, nullptr);
@@ -275,13 +284,13 @@ k_dec_sync(const uint8_t *__restrict__ payload, DecPlan plan, DecTablesGlobal g,
             s_count[sid] = (uint16_t)r.count;
             s_ends[sid] = r.end > (uint32_t)DEC_SUB_BITS ? r.end - DEC_SUB_BITS : 0;  // overshoot into the next sub-sequence
         };
-        run(tid, 0);
+        run(tid, tid ? 0u : carry);
         // Rounds until every sub-sequence starts where its predecessor ended.  Round 2 moves almost every
         // start; later rounds touch only the few sub-sequences whose predecessor had not synchronised yet,
         // so their work is compacted into the first warps instead of costing every warp a full pass.
         for (;;) {
             __syncthreads();
-            const uint32_t want = tid ? s_ends[tid - 1] : 0u;
+            const uint32_t want = tid ? s_ends[tid - 1] : carry;
             const bool changed = (want != s_start[tid]);
             const unsigned bal = __ballot_sync(FULL, changed);
             if (lane == 0) s_wcnt[warp] = (uint32_t)__popc(bal);
@@ -305,8 +314,20 @@ k_dec_sync(const uint8_t *__restrict__ payload, DecPlan plan, DecTablesGlobal g,
                 }
             }
         }
-        sub_info[seq * DEC_THREADS + tid] = sub_pack(s_start[tid], s_count[tid]);
-        if (tid == DEC_THREADS - 1) seq_end[seq] = s_ends[tid];
+        const uint32_t my_count = s_count[tid];
+        sub_info[seq * DEC_THREADS + tid] = sub_pack(s_start[tid], my_count);
+        carry = s_ends[DEC_THREADS - 1];
+        if (tid == DEC_THREADS - 1) seq_end[seq] = carry;
+        // symbols of the sequence (k_dec_stitch adjusts it when it re-decodes a sub-sequence)
+        const uint32_t wsum = __reduce_add_sync(FULL, my_count);
+        if (lane == 0) s_wsum[warp] = wsum;
+        __syncthreads();
+        if (tid == 0) {
+            uint32_t tot = 0;
+#pragma unroll
+            for (int w = 0; w < DEC_THREADS / 32; w++) tot += s_wsum[w];
+            seq_count[seq] = tot;
+        }
         // a speculative start may hit garbage; errors are judged in k_dec_write
     }
 }
@@ -328,7 +349,8 @@ __device__ __forceinline__ uint64_t window_global(const uint8_t *base, uint64_t 
 
 __global__ void __launch_bounds__(128)
 k_dec_stitch(const uint8_t *__restrict__ payload, DecPlan plan, DecTablesGlobal g, uint16_t *__restrict__ sub_info,
-             uint32_t *__restrict__ seq_end, uint64_t nseq, uint32_t *__restrict__ changed_flag)
+             uint32_t *__restrict__ seq_end, uint32_t *__restrict__ seq_count, uint64_t nseq,
+             uint32_t *__restrict__ changed_flag)
 {
     const uint64_t seq = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (seq >= nseq) return;
@@ -345,7 +367,8 @@ k_dec_stitch(const uint8_t *__restrict__ payload, DecPlan plan, DecTablesGlobal 
     t.ssym = g.ssym + (uint64_t)b * 256;
     const uint64_t seq_bit0 = sib * DEC_SEQ_BYTES * 8;
     const uint64_t total_bits = z * 8;
-    bool touched = false;
+    bool end_moved = false;
+    int32_t delta = 0;  // change of this sequence's symbol count
     for (uint32_t k = 0; k < DEC_THREADS; k++) {
         const uint64_t gi = seq * DEC_THREADS + k;
         const uint16_t rec = sub_info[gi];
@@ -363,24 +386,20 @@ k_dec_stitch(const uint8_t *__restrict__ payload, DecPlan plan, DecTablesGlobal 
             count++;
         }
         sub_info[gi] = sub_pack(cur, count);
-        touched = true;
+        delta += (int32_t)count - (int32_t)sub_count(rec);
         cur = q > hi ? (uint32_t)(q - hi) : 0u;
-        if (k == DEC_THREADS - 1 && seq_end[seq] != cur) seq_end[seq] = cur;
+        if (k == DEC_THREADS - 1 && seq_end[seq] != cur) {
+            seq_end[seq] = cur;
+            end_moved = true;
+        }
     }
-    if (touched) atomicOr(changed_flag, 1u);
+    if (delta) seq_count[seq] = (uint32_t)((int32_t)seq_count[seq] + delta);
+    // Only a moved sequence end can invalidate what another thread of this pass decided: a pass in which
+    // no end moved leaves every sequence consistent with its predecessor, and nothing is left to do.
+    if (end_moved) atomicOr(changed_flag, 1u);
 }
 
-// ---- phase 3: symbols per sequence, offsets ---------------------------------------------------
-__global__ void __launch_bounds__(DEC_THREADS)
-k_dec_count(const uint16_t *__restrict__ sub_info, uint32_t *__restrict__ seq_count)
-{
-    __shared__ uint32_t scan[DEC_THREADS / 32 + 1];
-    const uint64_t seq = blockIdx.x;
-    uint32_t total;
-    block_excl_scan<DEC_THREADS>(sub_count(sub_info[seq * DEC_THREADS + threadIdx.x]), scan, &total);
-    if (threadIdx.x == 0) seq_count[seq] = total;
-}
-
+// ---- phase 3: output offsets ---------------------------------------------------------------------
 // one CTA per block: exclusive scan of its sequences' counts; checks the block holds >= n symbols
 __global__ void __launch_bounds__(256)
 k_dec_scan(DecPlan plan, const uint32_t *__restrict__ seq_count, uint64_t *__restrict__ seq_excl,
@@ -594,22 +613,21 @@ int launch_sf_decode(shafa_cuda_ctx *ctx, const uint8_t *d_payload, const uint64
     if (grid_write > nseq) grid_write = nseq;
     SHAFA_LAUNCH(ctx, "dec_tables", k_dec_tables, dim3((unsigned)nb), dim3(256), 0, d_len, d_code, g);
     SHAFA_LAUNCH(ctx, "dec_sync", k_dec_sync, dim3((unsigned)grid_sync), dim3(DEC_THREADS), 0, d_payload, plan, g, sub_info,
-                 seq_end, nseq);
+                 seq_end, seq_count, nseq);
     SHAFA_CHECK_LAUNCH(ctx);
-    // stitch until a pass changes nothing (normally 1-2 passes)
+    // stitch across chunk boundaries until a pass moves no sequence end (normally the first pass)
     uint32_t *h_flag = (uint32_t *)pinned_get(ctx, 64);
     if (!h_flag) return SHAFA_LACK_OF_MEMORY;
     for (uint64_t pass = 0;; pass++) {
         SHAFA_CUDA_TRY(ctx, cudaMemsetAsync(flag, 0, 4, ctx->stream));
         SHAFA_LAUNCH(ctx, "dec_stitch", k_dec_stitch, dim3((unsigned)((nseq + 127) / 128)), dim3(128), 0, d_payload,
-                     plan, g, sub_info, seq_end, nseq, flag);
+                     plan, g, sub_info, seq_end, seq_count, nseq, flag);
         SHAFA_CHECK_LAUNCH(ctx);
         SHAFA_CUDA_TRY(ctx, cudaMemcpyAsync(h_flag, flag, 4, cudaMemcpyDeviceToHost, ctx->stream));
         SHAFA_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
         if (*h_flag == 0) break;
         if (pass > nseq + 2) return set_error(ctx, SHAFA_FILE_UNRECOGNIZABLE, "sf_decode: stitching did not converge");
     }
-    SHAFA_LAUNCH(ctx, "dec_count", k_dec_count, dim3((unsigned)nseq), dim3(DEC_THREADS), 0, sub_info, seq_count);
     SHAFA_LAUNCH(ctx, "dec_scan", k_dec_scan, dim3((unsigned)nb), dim3(256), 0, plan, seq_count, seq_excl, d_err);
     SHAFA_LAUNCH(ctx, "dec_write", k_dec_write, dim3((unsigned)grid_write), dim3(DEC_THREADS), smem_w, d_payload, plan, g,
                  sub_info, seq_excl, d_sym, nseq, d_err);
