@@ -115,7 +115,6 @@ struct DecShared {
     uint8_t slen[256];
     uint8_t ssym[256];
     uint32_t scan[DEC_THREADS / 32 + 1];
-    uint32_t block;
 };
 
 // lut2_dst: shared-memory copy of the multi-symbol count table (sync kernel only), or nullptr
@@ -136,23 +135,30 @@ __device__ __forceinline__ void dec_load_tables(DecShared &sh, const DecTablesGl
 }
 
 // Thread s builds the row of sub-sequence s straight from global memory: payload bytes [16 s, 16 s + 24)
-// of the sequence as six big-endian words; bytes at or past z read as zero.  (Call between barriers.)
-__device__ __forceinline__ void dec_load_rows(DecShared &sh, const uint8_t *payload, uint64_t pay_off, uint64_t z,
-                                              uint64_t seq_in_block)
+// of the sequence as six big-endian words; bytes at or past z read as zero.  The loads are issued one
+// sequence ahead (dec_fetch_row) and only turned into a row when that sequence's turn comes.
+struct RowRegs {
+    uint4 v;
+    uint2 u;
+};
+__device__ __forceinline__ RowRegs dec_fetch_row(const uint8_t *payload, uint64_t pay_off, uint64_t z, uint64_t seq_in_block)
+{
+    const uint64_t o = seq_in_block * DEC_SEQ_BYTES + (uint64_t)threadIdx.x * 16;  // offset in the block's payload
+    const uint64_t slot = (z + 15) & ~15ull;                                       // readable bytes of the block's slot
+    const uint8_t *base = payload + pay_off;
+    RowRegs r;
+    r.v = make_uint4(0, 0, 0, 0);
+    r.u = make_uint2(0, 0);
+    if (o < slot) r.v = __ldg(reinterpret_cast<const uint4 *>(base + o));
+    // the first half of the next thread's vector: the same cache line, or the next one
+    if (o + 16 < slot) r.u = __ldg(reinterpret_cast<const uint2 *>(base + o + 16));
+    return r;
+}
+__device__ __forceinline__ void dec_store_row(DecShared &sh, const RowRegs &r, uint64_t z, uint64_t seq_in_block)
 {
     const unsigned tid = threadIdx.x;
-    const uint64_t o = seq_in_block * DEC_SEQ_BYTES + (uint64_t)tid * 16;  // offset in the block's payload
-    const uint64_t slot = (z + 15) & ~15ull;                               // readable bytes of the block's slot
-    const uint8_t *base = payload + pay_off;
-    uint32_t w[DEC_ROW_WORDS] = {0, 0, 0, 0, 0, 0};
-    if (o < slot) {
-        const uint4 v = __ldg(reinterpret_cast<const uint4 *>(base + o));
-        w[0] = v.x, w[1] = v.y, w[2] = v.z, w[3] = v.w;
-    }
-    if (o + 16 < slot) {  // the first half of the next thread's vector: the same cache line, or the next one
-        const uint2 u = __ldg(reinterpret_cast<const uint2 *>(base + o + 16));
-        w[4] = u.x, w[5] = u.y;
-    }
+    const uint64_t o = seq_in_block * DEC_SEQ_BYTES + (uint64_t)tid * 16;
+    uint32_t w[DEC_ROW_WORDS] = {r.v.x, r.v.y, r.v.z, r.v.w, r.u.x, r.u.y};
     if (o + 4 * DEC_ROW_WORDS > z) {  // only at the end of a block
 #pragma unroll
         for (int k = 0; k < DEC_ROW_WORDS; k++) {
@@ -169,6 +175,44 @@ __device__ __forceinline__ void dec_load_rows(DecShared &sh, const uint8_t *payl
     dec_row_from_words(w, row);
 #pragma unroll
     for (int k = 0; k < DEC_ROW; k++) sh.pairs[tid * DEC_ROW + k] = row[k];
+}
+
+// Which block a sequence belongs to, tracked incrementally while a CTA walks its chunk (every thread
+// keeps the same copy: no broadcast through shared memory, no barrier).
+struct SeqCursor {
+    uint32_t b;
+    uint64_t first, next;  // block b holds sequences [first, next)
+    __device__ __forceinline__ void init(const DecPlan &plan, uint64_t seq)
+    {
+        b = find_block(plan.seq0, plan.nb, seq);
+        first = plan.seq0[b];
+        next = plan.seq0[b + 1];
+    }
+    __device__ __forceinline__ void advance_to(const DecPlan &plan, uint64_t seq)
+    {
+        while (seq >= next) {  // skips blocks without payload
+            b++;
+            first = next;
+            next = plan.seq0[b + 1];
+        }
+    }
+};
+
+// what a sequence needs from global memory, fetched one sequence ahead
+struct SeqFetch {
+    uint32_t b;
+    uint64_t sib, z;
+    RowRegs row;
+};
+__device__ __forceinline__ SeqFetch dec_fetch_seq(const uint8_t *payload, const DecPlan &plan, SeqCursor &c, uint64_t seq)
+{
+    c.advance_to(plan, seq);
+    SeqFetch f;
+    f.b = c.b;
+    f.sib = seq - c.first;
+    f.z = plan.z[c.b];
+    f.row = dec_fetch_row(payload, plan.pay_off[c.b], f.z, f.sib);
+    return f;
 }
 
 // The decode loops read the tables through 32-bit shared-memory addresses computed once per sequence
@@ -254,13 +298,16 @@ k_dec_sync(const uint8_t *__restrict__ payload, DecPlan plan, DecTablesGlobal g,
     dec_chunk(nseq, &seq_first, &seq_last);
     uint32_t cur_block = 0xffffffffu;
     uint32_t carry = 0;  // where the previous sequence of this CTA's chunk left its last sub-sequence
+    if (seq_first >= seq_last) return;
+    SeqCursor cursor;
+    cursor.init(plan, seq_first);
+    SeqFetch cur = dec_fetch_seq(payload, plan, cursor, seq_first);
     for (uint64_t seq = seq_first; seq < seq_last; seq++) {
+        SeqFetch nxt = cur;
+        if (seq + 1 < seq_last) nxt = dec_fetch_seq(payload, plan, cursor, seq + 1);  // in flight during this sequence
+        const uint32_t b = cur.b;
+        const uint64_t sib = cur.sib, z = cur.z;
         __syncthreads();  // previous sequence fully consumed
-        if (tid == 0) sh.block = find_block(plan.seq0, plan.nb, seq);
-        __syncthreads();
-        const uint32_t b = sh.block;
-        const uint64_t sib = seq - plan.seq0[b];
-        const uint64_t z = plan.z[b];
         if (b != cur_block) {
             cur_block = b;
             dec_load_tables(sh, g, b, s_lut2);
@@ -268,7 +315,8 @@ k_dec_sync(const uint8_t *__restrict__ payload, DecPlan plan, DecTablesGlobal g,
         // The first sub-sequence starts where the previous sequence ended.  Inside a chunk that is known;
         // the first sequence of a chunk assumes 0 and k_dec_stitch repairs it (a block's first sequence IS 0).
         if (sib == 0 || seq == seq_first) carry = 0;
-        dec_load_rows(sh, payload, plan.pay_off[b], z, sib);
+        dec_store_row(sh, cur.row, z, sib);
+        cur = nxt;
         __syncthreads();
         const DecViewS t = dec_view_of(sh, s_lut2, nullptr);
         // bits of this sequence that exist in the payload
@@ -476,66 +524,72 @@ k_dec_write(const uint8_t *__restrict__ payload, DecPlan plan, DecTablesGlobal g
     dec_chunk(nseq, &seq_first, &seq_last);
     uint32_t cur_block = 0xffffffffu;
     uint32_t bad = 0;
+    if (seq_first >= seq_last) return;
+    SeqCursor cursor;
+    cursor.init(plan, seq_first);
+    SeqFetch cur = dec_fetch_seq(payload, plan, cursor, seq_first);
+    uint16_t rec = sub_info[seq_first * DEC_THREADS + tid];
+    uint64_t sfirst = seq_excl[seq_first];  // index of the sequence's first symbol inside the block
     for (uint64_t seq = seq_first; seq < seq_last; seq++) {
-        __syncthreads();
-        if (tid == 0) sh.block = find_block(plan.seq0, plan.nb, seq);
-        __syncthreads();
-        const uint32_t b = sh.block;
-        const uint64_t sib = seq - plan.seq0[b];
-        const uint64_t z = plan.z[b];
+        // the next sequence's global loads are in flight while this one is decoded
+        SeqFetch nxt = cur;
+        uint16_t rec_nxt = 0;
+        uint64_t sfirst_nxt = 0;
+        if (seq + 1 < seq_last) {
+            nxt = dec_fetch_seq(payload, plan, cursor, seq + 1);
+            rec_nxt = sub_info[(seq + 1) * DEC_THREADS + tid];
+            sfirst_nxt = seq_excl[seq + 1];
+        }
+        const uint32_t b = cur.b;
+        const uint64_t sib = cur.sib, z = cur.z;
         if (b != cur_block) {
             cur_block = b;
+            __syncthreads();  // nobody decodes with the old tables any more
             dec_load_tables(sh, g, b, nullptr);
             const uint4 *src3 = reinterpret_cast<const uint4 *>(g.lut3 + (uint64_t)b * DEC_LUT_SIZE);
             uint4 *dst3 = reinterpret_cast<uint4 *>(ws.lut3);
             for (int i = tid; i < DEC_LUT_SIZE * 4 / 16; i += DEC_THREADS) dst3[i] = src3[i];
         }
-        dec_load_rows(sh, payload, plan.pay_off[b], z, sib);
-        const uint16_t rec = sub_info[seq * DEC_THREADS + tid];
+        dec_store_row(sh, cur.row, z, sib);  // read back by this thread only
         uint32_t total;
-        const uint32_t excl = block_excl_scan<DEC_THREADS>(sub_count(rec), sh.scan, &total);  // also fences the table loads above
+        // the scan's barriers also fence the table loads above and the previous sequence's copy-out
+        const uint32_t excl = block_excl_scan<DEC_THREADS>(sub_count(rec), sh.scan, &total);
         const DecViewS t = dec_view_of(sh, nullptr, ws.lut3);
         const uint64_t bits_left = (z - sib * DEC_SEQ_BYTES) * 8;
         const uint32_t limit = bits_left < (uint64_t)DEC_SEQ_BYTES * 8 ? (uint32_t)bits_left : DEC_SEQ_BYTES * 8;
         const uint32_t sub_lo = tid * DEC_SUB_BITS;
         const uint32_t stop = limit > sub_lo ? (limit - sub_lo < (uint32_t)DEC_SUB_BITS ? limit - sub_lo : (uint32_t)DEC_SUB_BITS) : 0u;
         const uint64_t n = plan.n[b];
-        const uint64_t sfirst = seq_excl[seq];   // index of this sequence's first symbol inside the block
-        if (sfirst >= n) continue;               // only padding garbage from here on (uniform for the CTA)
-        const uint64_t seq_room = n - sfirst;    // symbols of this sequence that are real
-        const uint32_t seq_syms = seq_room < total ? (uint32_t)seq_room : total;
-        uint8_t *gdst = out + plan.out_off[b] + sfirst;
-        const uint32_t room = excl < seq_syms ? seq_syms - excl : 0u;
-        if (seq_syms <= (uint32_t)DEC_STAGE) {
-            const uint32_t shift = (uint32_t)((uintptr_t)gdst & 15u);
-            uint32_t dst_s = smem_u32(ws.stage) + shift + excl;  // explicit st.shared: no generic address in the loop
-            asm volatile("" : "+r"(dst_s));
-            DecSub r;
-            if (seq_room >= total) {  // every symbol of this sequence is real (all but a block's last sequences)
-                StageSink<false> sink{dst_s, room};
-                r = dec_emit_to(t, tid * DEC_ROW, sub_start(rec), stop, sink);
-            } else {
-                StageSink<true> sink{dst_s, room};
-                r = dec_emit_to(t, tid * DEC_ROW, sub_start(rec), stop, sink);
-            }
-            bad |= r.bad && room;
-            __syncthreads();
-            uint8_t *ga = gdst - shift;  // 16-byte aligned
-            const uint32_t end = shift + seq_syms;
-            for (uint32_t c = tid * 16; c < end; c += DEC_THREADS * 16) {
-                if (c >= shift && c + 16 <= end) {
-                    st_stream16(ga + c, *reinterpret_cast<const uint4 *>(ws.stage + c));
+        if (sfirst < n) {  // else: only padding garbage from here on (uniform for the CTA)
+            const uint64_t seq_room = n - sfirst;  // symbols of this sequence that are real
+            const uint32_t seq_syms = seq_room < total ? (uint32_t)seq_room : total;
+            uint8_t *gdst = out + plan.out_off[b] + sfirst;
+            const uint32_t room = excl < seq_syms ? seq_syms - excl : 0u;
+            if (seq_syms <= (uint32_t)DEC_STAGE) {
+                uint32_t dst_s = smem_u32(ws.stage) + excl;  // explicit st.shared: no generic address in the loop
+                asm volatile("" : "+r"(dst_s));
+                DecSub r;
+                if (seq_room >= total) {  // every symbol of this sequence is real (all but a block's last sequences)
+                    StageSink<false> sink{dst_s, room};
+                    r = dec_emit_to(t, tid * DEC_ROW, sub_start(rec), stop, sink);
                 } else {
-                    for (uint32_t k = (c > shift ? c : shift); k < c + 16 && k < end; k++) ga[k] = ws.stage[k];
+                    StageSink<true> sink{dst_s, room};
+                    r = dec_emit_to(t, tid * DEC_ROW, sub_start(rec), stop, sink);
                 }
+                bad |= r.bad && room;
+                __syncthreads();
+                copy_out_unaligned<DEC_THREADS>(gdst, ws.stage, seq_syms);
+            } else {
+                uint8_t *dst = gdst + excl;
+                const DecSub r = dec_emit_subsequence(t, tid * DEC_ROW, sub_start(rec), stop, [&](uint32_t i, uint32_t sym) {
+                    if (i < room) dst[i] = (uint8_t)sym;
+                });
+                bad |= r.bad && room;
             }
-        } else {
-            uint8_t *dst = gdst + excl;
-            const DecSub r = dec_emit_subsequence(t, tid * DEC_ROW, sub_start(rec), stop, [&](uint32_t i, uint32_t sym) {
-                if (i < room) dst[i] = (uint8_t)sym;
-            });
-            bad |= r.bad && room;
         }
+        cur = nxt;
+        rec = rec_nxt;
+        sfirst = sfirst_nxt;
     }
     // a bad window only matters if it produced one of the n real symbols
     if (bad) atomicOr(err, (uint32_t)ERR_BAD_WINDOW);
