@@ -26,7 +26,7 @@ constexpr int RLD_WARPS = RLD_THREADS / 32;
 constexpr int RLD_VECS = 4;
 constexpr int RLD_PER_THREAD = 16 * RLD_VECS;             // 64 RLE bytes per thread
 constexpr int RLD_TILE = RLD_THREADS * RLD_PER_THREAD;    // 16 KiB of RLE bytes per tile
-constexpr int RLD_STAGE = 32768;                          // staging window (bytes of output)
+constexpr int RLD_STAGE = 24576;                          // staging window (bytes of output)
 constexpr uint64_t RLE_BLOCK_CAP = 67108864ull + 1024ull;  // d.c:135,163
 
 struct RleDecShared {
@@ -83,7 +83,7 @@ __device__ __forceinline__ void rld_emit(uint8_t *stage_base, uint32_t wlo, uint
     }
 }
 
-__global__ void __launch_bounds__(RLD_THREADS, 4)
+__global__ void __launch_bounds__(RLD_THREADS, 6)
 k_rle_decode(const uint8_t *__restrict__ in, const uint64_t *__restrict__ off, const uint64_t *__restrict__ tile0,
              uint32_t nb, uint8_t *__restrict__ out, uint64_t out_capacity, uint64_t *__restrict__ blk_end,
              uint64_t *__restrict__ desc_state_chain, uint64_t *__restrict__ desc_out, uint32_t *__restrict__ counter,

@@ -52,7 +52,7 @@ __device__ __forceinline__ uint4 rle_ld16(const void *p)
 }
 
 template <bool WRITE, bool HIST>
-__global__ void __launch_bounds__(RLE_THREADS, 4)
+__global__ void __launch_bounds__(RLE_THREADS, 5)
 k_rle_encode(const uint8_t *__restrict__ in, uint64_t n, uint64_t block_size, uint32_t tiles_per_block,
              uint64_t total_tiles, uint8_t *__restrict__ out, uint64_t out_capacity,
              unsigned long long *__restrict__ hist, uint64_t *__restrict__ blk_end, uint64_t *__restrict__ desc_run,
