@@ -202,6 +202,15 @@ ALGO_BYTES_DOC = {
 }
 
 
+# the metric is quoted on C2; the other BASELINE.json configs can be timed with the same harness (--workload)
+WORKLOADS = {
+    "C2": lambda pkg: ("textlike", pkg.datagen.BLOCK_m, "C2: {gib} text-like synthetic (seed 2024), -b m (8 MiB blocks), F->T->C->D round trip"),
+    "C1": lambda pkg: ("zipf", pkg.datagen.BLOCK_K, "C1-shaped: {gib} zipf synthetic (seed 12345), -b K (640 KiB blocks), N mode"),
+    "C3": lambda pkg: ("runheavy", pkg.datagen.BLOCK_M, "C3-shaped: {gib} run-heavy synthetic (seed 99), -b M (64 MiB blocks), R mode"),
+    "C4": lambda pkg: ("uniform", pkg.datagen.BLOCK_m, "C4-shaped: {gib} uniform synthetic (seed 7), -b m (8 MiB blocks), N mode"),
+}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -217,8 +226,9 @@ def run_ours(args):
     dev = torch.device("cuda", local_rank)
 
     n = args.bytes
-    bs = pkg.datagen.BLOCK_m
-    data = pkg.datagen.textlike(n, seed=2024 + rank)      # this rank's shard of blocks
+    gen_name, bs, wl_desc = WORKLOADS[args.workload](pkg)
+    seed0 = {"textlike": 2024, "zipf": 12345, "runheavy": 99, "uniform": 7}[gen_name]
+    data = pkg.datagen.GENERATORS[gen_name](n, seed=seed0 + rank)      # this rank's shard of blocks
     B = (n + bs - 1) // bs
 
     clocks = ClockSampler(local_rank)   # started early: nvidia-smi takes a while to deliver its first line
@@ -378,7 +388,7 @@ def run_ours(args):
             "metric": METRIC, "value": round(value, 3), "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "bytes_per_gpu": n, "block_size": bs, "blocks_per_gpu": B, "mode": "R" if info["rle_mode"] else "N",
+            "config": {"workload": WORKLOAD if (args.workload == "C2" and n == GIB) else wl_desc.format(gib=f"{n / GIB:g} GiB"), "bytes_per_gpu": n, "block_size": bs, "blocks_per_gpu": B, "mode": "R" if info["rle_mode"] else "N",
                        "S_rle_bytes": S, "Z_payload_bytes": Z, "l2": "inputs (1 GiB per pass) larger than the 126 MB L2",
                        "sharding": f"{world} x independent block shards, no collective"},
             "encode_gbs": round(world * n / (enc_ms * 1e-3) / 1e9, 3), "decode_gbs": round(world * n / (dec_ms * 1e-3) / 1e9, 3),
@@ -434,6 +444,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--bytes", type=int, default=GIB, help="bytes per GPU (default: the 1 GiB of configs[1])")
+    ap.add_argument("--workload", choices=sorted(WORKLOADS), default="C2", help="input shape (default C2, the one the metric is quoted on)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -104,7 +104,7 @@ enum ErrBits : uint32_t {
     ERR_CAPACITY = 32,       // output buffer too small
     ERR_RLE_TRUNCATED = 64   // RLE block ends inside a triple
 };
-enum OccId { OCC_SF_ENCODE = 0, OCC_RLE_ENC = 1 /* +variant 0..3 */, OCC_RLE_DEC = 5, OCC_DEC_SYNC = 6, OCC_DEC_WRITE = 7 };
+enum OccId { OCC_SF_ENCODE = 0, OCC_RLE_ENC = 1 /* +variant 0..3 */, OCC_RLE_DEC = 5, OCC_DEC_SYNC = 6, OCC_DEC_WRITE = 7, OCC_HIST = 8 };
 enum MiscSlot { MISC_COUNTER = 0, MISC_FLAG = 16, MISC_ERR = 32, MISC_WORDS = 64 };  // uint32 indices into SCR_MISC
 uint32_t *misc_ptr(shafa_cuda_ctx *ctx, int which);
 shafa_cuda_ctx *worker_ctx(shafa_cuda_ctx *ctx, int i);  // lazily created child context i (0..3) on the same device
