@@ -106,6 +106,8 @@ struct DecPlan {
     uint32_t nb;
 };
 
+constexpr int DEC_MAP_MAX = 16;     // longest code for which the all-starts fallback of k_dec_sync is used
+constexpr int DEC_MAX_ROUNDS = 12;  // sync rounds before that fallback is taken in any case
 constexpr int DEC_STAGE = 12288;  // symbols of one sequence staged in shared memory before the coalesced copy-out
 
 struct DecShared {
@@ -293,6 +295,10 @@ k_dec_sync(const uint8_t *__restrict__ payload, DecPlan plan, DecTablesGlobal g,
     __shared__ uint32_t s_list[DEC_THREADS];    // compacted work list of a sparse round: sub-sequence | start << 16
     __shared__ uint32_t s_wcnt[DEC_THREADS / 32];
     __shared__ uint32_t s_wsum[DEC_THREADS / 32];
+    __shared__ uint16_t s_map[DEC_THREADS * DEC_MAP_MAX];  // [sub-sequence][start] -> (overshoot << 10) | count
+    __shared__ uint8_t s_path[(DEC_THREADS / 32) * DEC_MAP_MAX * 32];  // [warp][entry offset][i]: start of the warp's i-th sub-sequence
+    __shared__ uint8_t s_path_out[(DEC_THREADS / 32) * DEC_MAP_MAX];   // [warp][entry offset]: offset handed to the next warp
+    __shared__ uint32_t s_maxlen;
     const unsigned tid = threadIdx.x, lane = lane_id(), warp = warp_id();
     uint64_t seq_first, seq_last;
     dec_chunk(nseq, &seq_first, &seq_last);
@@ -311,6 +317,10 @@ k_dec_sync(const uint8_t *__restrict__ payload, DecPlan plan, DecTablesGlobal g,
         if (b != cur_block) {
             cur_block = b;
             dec_load_tables(sh, g, b, s_lut2);
+            if (tid == 0) s_maxlen = 0;
+            __syncthreads();
+            const uint32_t wmax = __reduce_max_sync(FULL, (uint32_t)sh.slen[tid]);
+            if (lane == 0) atomicMax(&s_maxlen, wmax);
         }
         // The first sub-sequence starts where the previous sequence ended.  Inside a chunk that is known;
         // the first sequence of a chunk assumes 0 and k_dec_stitch repairs it (a block's first sequence IS 0).
@@ -333,6 +343,8 @@ k_dec_sync(const uint8_t *__restrict__ payload, DecPlan plan, DecTablesGlobal g,
             s_ends[sid] = r.end > (uint32_t)DEC_SUB_BITS ? r.end - DEC_SUB_BITS : 0;  // overshoot into the next sub-sequence
         };
         run(tid, tid ? 0u : carry);
+        const uint32_t maxlen = s_maxlen;  // (written before the barrier above)
+        uint32_t round = 1;
         // Rounds until every sub-sequence starts where its predecessor ended.  Round 2 moves almost every
         // start; later rounds touch only the few sub-sequences whose predecessor had not synchronised yet,
         // so their work is compacted into the first warps instead of costing every warp a full pass.
@@ -351,6 +363,50 @@ k_dec_sync(const uint8_t *__restrict__ payload, DecPlan plan, DecTablesGlobal g,
                 total += c;
             }
             if (total == 0) break;
+            round++;
+            if (((round > 3 && total > DEC_THREADS / 2) || round > DEC_MAX_ROUNDS) && maxlen <= (uint32_t)DEC_MAP_MAX) {
+                // Codes of (nearly) one length never re-synchronise, and the rounds above would then settle
+                // one sub-sequence at a time.  Instead every thread decodes its sub-sequence from EVERY start
+                // that can occur (an overshoot is shorter than the longest code) and one thread follows the
+                // chain through the resulting tables.
+                for (uint32_t st = 0; st < maxlen; st++) {
+                    const uint32_t sub_lo = tid * DEC_SUB_BITS;
+                    const uint32_t stop = limit > sub_lo ? (limit - sub_lo < (uint32_t)DEC_SUB_BITS ? limit - sub_lo : (uint32_t)DEC_SUB_BITS) : 0u;
+                    const DecSub r = dec_count_subsequence(t, tid * DEC_ROW, st, stop);
+                    const uint32_t over = r.end > (uint32_t)DEC_SUB_BITS ? r.end - DEC_SUB_BITS : 0u;
+                    s_map[tid * DEC_MAP_MAX + st] = (uint16_t)((over << 10) | r.count);
+                }
+                __syncthreads();
+                // the chain, two levels: lane s of every warp follows its warp's 32 sub-sequences from entry
+                // offset s (all offsets and warps in parallel), one thread links the eight warps, and every
+                // thread then picks the path that belongs to its warp's real entry offset
+                if (lane < maxlen) {
+                    uint32_t st = lane;
+                    for (int i = 0; i < 32; i++) {
+                        s_path[(warp * DEC_MAP_MAX + lane) * 32 + i] = (uint8_t)st;
+                        st = s_map[(warp * 32 + i) * DEC_MAP_MAX + st] >> 10;  // < maxlen: shorter than the longest code
+                    }
+                    s_path_out[warp * DEC_MAP_MAX + lane] = (uint8_t)st;
+                }
+                __syncthreads();
+                if (tid == 0) {
+                    uint32_t st = carry < maxlen ? carry : 0u;  // carry >= maxlen cannot happen
+                    for (int w = 0; w < DEC_THREADS / 32; w++) {
+                        s_wcnt[w] = st;
+                        st = s_path_out[w * DEC_MAP_MAX + st];
+                    }
+                }
+                __syncthreads();
+                {
+                    const uint32_t st = s_path[(warp * DEC_MAP_MAX + s_wcnt[warp]) * 32 + lane];
+                    const uint32_t e = s_map[tid * DEC_MAP_MAX + st];
+                    s_start[tid] = (uint16_t)st;
+                    s_count[tid] = (uint16_t)(e & 1023u);
+                    s_ends[tid] = e >> 10;
+                }
+                __syncthreads();
+                break;
+            }
             if (total > DEC_THREADS / 4) {
                 if (changed) run(tid, want);
             } else {
