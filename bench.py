@@ -50,6 +50,19 @@ def measured_peak_hbm():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def profiled_traffic(kernel: str):
+    """DRAM bytes per launch of `kernel` from the newest committed ncu capture (profiles/*_traffic.json, written by
+    tools/summarize_ncu.py from one `ncu --set full` run of this bench on the C2 workload); (None, why) if there is none."""
+    files = sorted((ROOT / "profiles").glob("*_traffic.json"))
+    if not files:
+        return None, "no profiles/*_traffic.json"
+    try:
+        j = json.loads(files[-1].read_text())
+        return int(j["bytes_per_launch"][kernel]), f"profiles/{files[-1].name}"
+    except Exception as e:  # noqa: BLE001
+        return None, f"profiles/{files[-1].name}: {type(e).__name__}"
+
+
 # ----------------------------------------------------------------------------------
 # reference arm / cpu baseline: the unmodified reference binary on host cores
 # ----------------------------------------------------------------------------------
@@ -384,6 +397,7 @@ def run_ours(args):
         value = world * n / (ms_per_step * 1e-3) / 1e9
         # pipeline-level roofline: algorithmic bytes of the staged pipeline: F (N+R) + C (S+Z) + D (Z+S [+ R+N])
         pipe_bytes = (n + R) + (S + Z) + (Z + S) + ((R + n) if info["rle_mode"] else 0)
+        traffic, traffic_src = (profiled_traffic(dom) if (args.workload == "C2" and n == GIB) else (None, "captured on the C2 1 GiB workload only"))
         line = {
             "metric": METRIC, "value": round(value, 3), "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -397,8 +411,8 @@ def run_ours(args):
                              "achieved_gbs": round(pipe_bytes / (ms_per_step * 1e-3) / 1e9, 1),
                              "frac": round(pipe_bytes / (ms_per_step * 1e-3) / 1e9 / peak, 4)},
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["gbs"], "peak": peak, "unit": "GB/s",
-                         "frac": kernels[dom]["frac_of_hbm"], "traffic": None, "peak_source": peak_src,
-                         "algorithmic_bytes": ALGO_BYTES_DOC[dom]},
+                         "frac": kernels[dom]["frac_of_hbm"], "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                         "algorithmic_bytes": ALGO_BYTES_DOC[dom], "algorithmic_bytes_per_launch": algo[dom]},
             "kernels": kernels,
             "e2e": {"value": round(world * n / (e2e_ms * 1e-3) / 1e9, 3), "unit": "GB/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "api": "shafa_cuda_encode_host + shafa_cuda_decode_host on pinned host buffers"},

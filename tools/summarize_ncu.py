@@ -6,6 +6,8 @@ from pathlib import Path
 
 ROOT = Path(__file__).resolve().parents[1]
 tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
+bench_name = sys.argv[2] if len(sys.argv) > 2 else "bench1.json"
+rep_name = sys.argv[3] if len(sys.argv) > 3 else "prof.ncu-rep"
 src = ROOT / "gpurun_out"
 dst = ROOT / "profiles"
 dst.mkdir(exist_ok=True)
@@ -45,7 +47,17 @@ if lp.exists():
     out.append("")
     (dst / f"{tag}_launches.csv").write_bytes(lp.read_bytes())
 
-rep = src / "prof.ncu-rep"
+rep = src / rep_name
+traffic = {}
+
+def bench_key(kernel: str) -> str:
+    """ncu kernel name -> the key bench.py uses for that launch"""
+    k = kernel.replace("shafa::", "")
+    if k.startswith("k_rle_encode<0, 0>"):
+        return "rle_encode_sizes"
+    return k.split("<")[0].replace("k_", "", 1)
+
+UNIT = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
 if rep.exists():
     raw = subprocess.run(["ncu", "-i", str(rep), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
@@ -67,12 +79,16 @@ if rep.exists():
             rd = float(r[hdr.index('dram__bytes_read.sum')]); wr = float(r[hdr.index('dram__bytes_write.sum')])
             u = units[hdr.index('dram__bytes_read.sum')]
             out.append(f"| dram traffic (read+write) | {rd + wr:.4f} | {u} |")
+            traffic[bench_key(name)] = int((rd + wr) * UNIT.get(u, 1))
         except Exception:
             pass
         out.append("")
     (dst / f"{tag}_ncu_raw.csv").write_text(raw)
+    # per-launch DRAM bytes of each hot kernel on the bench workload: bench.py reports the dominant kernel's as roofline.traffic
+    (dst / f"{tag}_traffic.json").write_text(json.dumps({"source": f"profiles/{tag}_ncu_raw.csv (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, one launch)",
+                                                         "workload": "C2, 1 GiB per GPU", "bytes_per_launch": traffic}, indent=1) + "\n")
 
-for name in ("bench1.json",):
+for name in (bench_name,):
     p = src / name
     if p.exists() and p.stat().st_size:
         (dst / f"{tag}_bench.json").write_bytes(p.read_bytes())
