@@ -262,6 +262,29 @@ SHAFA_HD int ctz64(uint64_t x)
     return __builtin_ctzll(x);
 #endif
 }
+
+// Runs longer than 255: the reference counts to 255, emits, and starts over (f.c:38-49; the counter c of
+// rle_emit_thread above), so the first position of every further 255-byte chunk behaves exactly like the
+// head of a new run -- triple if the rest of the run has >= 4 bytes or the byte is 0x00, literals otherwise.
+// Given a thread whose first position continues a run (E bit 0 set) at distance k0 from that run's head,
+// clear the continuation bit of such chunk heads inside the window the bit-parallel rule looks at
+// (positions p0-2 .. p0+66).  At most one falls into it (255 > 69).
+SHAFA_HD void rle_chunk_heads(uint64_t k0, uint64_t *E, uint32_t *before, uint32_t *after)
+{
+    const uint64_t e = *E;
+    const uint32_t lead = (~e) ? (uint32_t)ctz64(~e) : 64u;  // positions 0 .. lead-1 continue the incoming run
+    const uint32_t r = (uint32_t)(k0 % 255u);
+    const uint32_t j = r ? 255u - r : 0u;  // first position >= p0 at a multiple of 255 from the head
+    if (j < lead) {
+        *E = e & ~(1ull << j);
+    } else if (lead == 64 && j < 67) {  // p0+64 .. p0+66 continue the run only through set bits
+        const uint32_t i = j - 64, through = (1u << (i + 1)) - 1u;
+        if ((*after & through) == through) *after &= ~(1u << i);
+    }
+    if (k0 > 1 && (k0 - 1) % 255u == 0) *before &= ~2u;  // p0-1
+    if (k0 > 2 && (k0 - 2) % 255u == 0) *before &= ~1u;  // p0-2
+}
+
 struct FsmWalk {
     uint64_t esc;   // positions of the escape bytes met in state 0
     uint32_t exit;  // state after the n bytes

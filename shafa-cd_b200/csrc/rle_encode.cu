@@ -199,26 +199,13 @@ k_rle_encode(const uint8_t *__restrict__ in, uint64_t n, uint64_t block_size, ui
         uint64_t lit = 0, tri = 0;
         if (nvalid) {
             const uint64_t k0 = (lh >= 0) ? (uint64_t)(p0 - (uint32_t)lh) : (uint64_t)p0 + run_in;  // k at p0 if p0 is no head
-            if ((E & 1ull) && k0 + (RLE_PER_THREAD - 1) >= 255) {
-                // deep inside a long run: general per-position walk, one 16-byte group at a time
-#pragma unroll
-                for (int c = 0; c < RLE_VECS; c++) {
-                    const int nv = nvalid - 16 * c;
-                    if (nv > 0) {
-                        // k at the group's first position: distance to the last head before it
-                        const uint64_t hb = (c == 0) ? 0ull : (my_heads & ((1ull << (16 * c)) - 1ull));
-                        const uint64_t kc = hb ? (uint64_t)(16 * c - (63 - __clzll((long long)hb))) : k0 + 16 * c;
-                        auto symc = [&](int j) -> uint32_t { return byte_of(v[c], j); };
-                        const RleEmit em = rle_emit_thread(sh.heads, p0 + 16 * c, nv > 16 ? 16 : nv, (uint32_t)(kc % 255), symc);
-                        lit |= (uint64_t)em.lit << (16 * c);
-                        tri |= (uint64_t)em.tri << (16 * c);
-                    }
-                }
-            } else {
-                const RleMasks64 m = rle_fast_masks64(E, e_before, e_after, Z & valid64, valid64);
-                lit = m.lit;
-                tri = m.tri;
-            }
+            // deep inside a long run the first position of every further 255-byte chunk acts as a head
+            uint64_t Ev = E;
+            uint32_t bv = e_before, av = e_after;
+            if ((E & 1ull) && k0 + (RLE_PER_THREAD + 2) >= 255) rle_chunk_heads(k0, &Ev, &bv, &av);
+            const RleMasks64 m = rle_fast_masks64(Ev, bv, av, Z & valid64, valid64);
+            lit = m.lit;
+            tri = m.tri;
         }
         const uint32_t my_bytes = (uint32_t)__popcll(lit) + 3u * (uint32_t)__popcll(tri);
 

@@ -140,14 +140,15 @@ static Bytes emu_rle_encode_block(const uint8_t *blk, uint64_t len)
                     glit |= (uint64_t)em.lit << (16 * c);
                     gtri |= (uint64_t)em.tri << (16 * c);
                 }
-                if ((E & 1ull) && k0 + (PT - 1) >= 255) {
-                    lit = glit;
-                    tri = gtri;
-                } else {
-                    const RleMasks64 m = rle_fast_masks64(E, before | (rng_noise & ~3u), after | (rng_noise & ~7u), Z & valid64, valid64);
+                {
+                    uint64_t Ev = E;
+                    uint32_t bv = before, av = after;
+                    if ((E & 1ull) && k0 + (PT + 2) >= 255) rle_chunk_heads(k0, &Ev, &bv, &av);  // as in the kernel
+                    const RleMasks64 m = rle_fast_masks64(Ev, bv | (rng_noise & ~3u), av | (rng_noise & ~7u), Z & valid64, valid64);
                     lit = m.lit;
                     tri = m.tri;
-                    CHECK(lit == glit && tri == gtri, "fast masks differ from the general rule (tile %llu tid %u)", (unsigned long long)ti, tid);
+                    CHECK(lit == glit && tri == gtri, "fast masks differ from the general rule (tile %llu tid %u k0 %llu)",
+                          (unsigned long long)ti, tid, (unsigned long long)k0);
                 }
             }
             for (int j = 0; j < PT; j++) {
