@@ -67,8 +67,8 @@ def profiled_traffic(kernel: str):
 # reference arm / cpu baseline: the unmodified reference binary on host cores
 # ----------------------------------------------------------------------------------
 
-def reference_round_trip(sample: np.ndarray, bflag: str, workdir: Path) -> dict:
-    """F, T, C, D with oracle/_ref/shafa on `sample`; wall seconds per module."""
+def reference_round_trip(sample: np.ndarray, bflag: str, workdir: Path, extra=()) -> dict:
+    """F, T, C, D with oracle/_ref/shafa on `sample`; wall seconds per module.  `extra`: more CLI flags for every call."""
     from oracle import oracle_py as orc
 
     x = workdir / "x"
@@ -77,7 +77,7 @@ def reference_round_trip(sample: np.ndarray, bflag: str, workdir: Path) -> dict:
 
     def run(args, key):
         t0 = time.perf_counter()
-        r = orc.ref_run(args, str(workdir), timeout=3600)
+        r = orc.ref_run(list(args) + list(extra), str(workdir), timeout=3600)
         t[key] = time.perf_counter() - t0
         if r.returncode != 0:
             raise RuntimeError(f"reference failed {args}: {r.stderr.decode(errors='replace')[:300]}")
@@ -109,8 +109,8 @@ def port_round_trip(sample: np.ndarray, block: int) -> dict:
     return {"seconds": t, "ok": out == sample.tobytes(), "rle_mode": f["rle_mode"]}
 
 
-def cpu_arm(pkg, steps: int, warmup: int):
-    """Returns (per-step seconds list, description dict)."""
+def cpu_arm(pkg, steps: int, warmup: int, per_core: bool = False):
+    """Returns (per-step seconds list, description dict).  per_core: also one --no-multithread pass."""
     from oracle import oracle_py as orc
 
     sample = pkg.datagen.textlike(CPU_SAMPLE_BYTES, seed=2024)
@@ -125,6 +125,7 @@ def cpu_arm(pkg, steps: int, warmup: int):
             if i >= warmup:
                 times.append(sum(r["seconds"].values()))
                 last = r
+        single = reference_round_trip(sample, "m", Path(td), extra=("--no-multithread",)) if (use_ref and per_core) else None
     desc = {
         "kind": "reference" if use_ref else "port",
         "cores": os.cpu_count() if use_ref else 1,
@@ -132,6 +133,9 @@ def cpu_arm(pkg, steps: int, warmup: int):
                   f"files on {'tmpfs' if tmp_root else 'tmp'}; F,T single-threaded, C,D one pthread per block (reference design)",
         "module_seconds": {k: round(v, 4) for k, v in last["seconds"].items()},
     }
+    if single:
+        desc["single_thread"] = {"value": round(CPU_SAMPLE_BYTES / sum(single["seconds"].values()) / 1e9, 4), "unit": "GB/s",
+                                 "flag": "--no-multithread", "module_seconds": {k: round(v, 4) for k, v in single["seconds"].items()}}
     return times, desc
 
 
@@ -411,7 +415,7 @@ def run_ours(args):
                              "achieved_gbs": round(pipe_bytes / (ms_per_step * 1e-3) / 1e9, 1),
                              "frac": round(pipe_bytes / (ms_per_step * 1e-3) / 1e9 / peak, 4)},
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["gbs"], "peak": peak, "unit": "GB/s",
-                         "frac": kernels[dom]["frac_of_hbm"], "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                         "frac": kernels[dom]["frac_of_hbm"], "frac_of_nominal_8000": round(kernels[dom]["gbs"] / 8000.0, 4), "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                          "algorithmic_bytes": ALGO_BYTES_DOC[dom], "algorithmic_bytes_per_launch": algo[dom]},
             "kernels": kernels,
             "e2e": {"value": round(world * n / (e2e_ms * 1e-3) / 1e9, 3), "unit": "GB/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -419,7 +423,7 @@ def run_ours(args):
             "gpu_launches": int(launches), "clocks": clk,
         }
         if world == 1 and not args.no_cpu:
-            times, desc = cpu_arm(pkg, 1, 0)
+            times, desc = cpu_arm(pkg, 1, 0, per_core=True)
             desc["value"] = round(CPU_SAMPLE_BYTES / times[0] / 1e9, 4)
             desc["unit"] = "GB/s"
             line["cpu_baseline"] = desc
