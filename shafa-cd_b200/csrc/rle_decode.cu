@@ -49,6 +49,34 @@ __device__ __forceinline__ uint4 rld_ld16(const void *p)
     return v;
 }
 
+// One position of the uniform literal pass, as predicated instructions on a 32-bit shared address:
+// store the byte if the position is a literal (bit `BIT` of l16) and advance by one; if it is a count byte
+// (bit of r16) advance by the run's length, max(count, 1) (d.c:179-184: count 0 -> one copy).
+template <uint32_t BIT>
+__device__ __forceinline__ void rld_lit_step(uint32_t &o_s, uint32_t cur, uint32_t l16, uint32_t r16)
+{
+    asm volatile(
+        "{\n\t.reg .pred pl, pr;\n\t.reg .u32 t;\n\t"
+        "and.b32 t, %2, %4;\n\tsetp.ne.u32 pl, t, 0;\n\t"
+        "and.b32 t, %3, %4;\n\tsetp.ne.u32 pr, t, 0;\n\t"
+        "@pl st.shared.u8 [%0], %1;\n\t"
+        "@pl add.u32 %0, %0, 1;\n\t"
+        "max.u32 t, %1, 1;\n\t"
+        "@pr add.u32 %0, %0, t;\n\t}"
+        : "+r"(o_s)
+        : "r"(cur), "r"(l16), "r"(r16), "n"(BIT)
+        : "memory");
+}
+template <int J>
+__device__ __forceinline__ void rld_lit_steps(uint32_t &o_s, const uint4 &x, uint32_t l16, uint32_t r16)
+{
+    if constexpr (J < 16) {
+        const uint32_t w = (J < 4) ? x.x : (J < 8) ? x.y : (J < 12) ? x.z : x.w;
+        rld_lit_step<(1u << J)>(o_s, __byte_perm(w, 0, 0x4440 | (J & 3)), l16, r16);
+        rld_lit_steps<J + 1>(o_s, x, l16, r16);
+    }
+}
+
 // `len` copies of `sym` at dst (shared memory): bytes up to a 4-byte boundary, words, tail bytes
 __device__ __noinline__ void rld_fill(uint8_t *dst, uint32_t sym, uint32_t len)
 {
@@ -235,6 +263,8 @@ k_rle_decode(const uint8_t *__restrict__ in, const uint64_t *__restrict__ off, c
                 uint8_t *sb = sh.stage - w0;  // sb[x] is tile-space position x
                 uint32_t o = a;
                 if (full && single) {
+                    uint32_t o_s = smem_u32(sh.stage) + a;  // single window: w0 = 0
+                    asm volatile("" : "+r"(o_s));
                     // literals: one uniform, fully predicated pass -- the offset of position q is
                     // (literals before q) + (bytes of the runs before q), kept as a running sum
 #pragma unroll 1
@@ -243,15 +273,11 @@ k_rle_decode(const uint8_t *__restrict__ in, const uint64_t *__restrict__ off, c
                         const uint32_t l16 = (uint32_t)(m.lit >> (16 * c)) & 0xffffu, r16 = (uint32_t)(m.run >> (16 * c)) & 0xffffu;
                         if (__all_sync(__activemask(), r16 == 0 && l16 == 0xffffu)) {  // whole warp: sixteen literals each
 #pragma unroll
-                            for (int j = 0; j < 16; j++) sb[o + j] = (uint8_t)byte_of(x, j);
-                            o += 16;
+                            for (int j = 0; j < 16; j++)
+                                asm volatile("st.shared.u8 [%0], %1;" ::"r"(o_s + j), "r"(byte_of(x, j)) : "memory");
+                            o_s += 16;
                         } else {
-#pragma unroll
-                            for (int j = 0; j < 16; j++) {
-                                const uint32_t cur = byte_of(x, j);
-                                if ((l16 >> j) & 1u) sb[o] = (uint8_t)cur;
-                                o += ((l16 >> j) & 1u) + (((r16 >> j) & 1u) ? (cur ? cur : 1u) : 0u);
-                            }
+                            rld_lit_steps<0>(o_s, x, l16, r16);
                         }
                     }
                 } else {
