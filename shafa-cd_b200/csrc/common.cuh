@@ -13,6 +13,21 @@ constexpr unsigned FULL = 0xffffffffu;
 
 // 32-bit shared-window address of a shared-memory object (operand of explicit ld/st/red.shared)
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// Explicit shared-memory accesses through such addresses.  The compiler otherwise tends to rebuild the CTA's
+// shared window base (S2R SR_CgaCtaId, MOV, LEA, IADD) in front of dynamically indexed or predicated accesses.
+__device__ __forceinline__ uint32_t smem_opaque(const void *p)
+{
+    uint32_t a = smem_u32(p);
+    asm volatile("" : "+r"(a));  // keeps the optimiser from rematerialising the address at every use
+    return a;
+}
+__device__ __forceinline__ uint32_t lds_u8(uint32_t saddr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(saddr));
+    return v;
+}
+__device__ __forceinline__ void sts_u8(uint32_t saddr, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(saddr), "r"(v) : "memory"); }
 __device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }
 __device__ __forceinline__ unsigned warp_id() { return threadIdx.x >> 5; }
 

@@ -121,6 +121,7 @@ k_rle_decode(const uint8_t *__restrict__ in, const uint64_t *__restrict__ off, c
     const unsigned tid = threadIdx.x, lane = lane_id(), warp = warp_id();
     const uint64_t total_tiles = tile0[nb];
     for (int i = tid; i < 64 * 64; i += RLD_THREADS) sh.compose[i] = (uint8_t)fsm_compose((uint32_t)i >> 6, (uint32_t)i & 63u);
+    const uint32_t compose_s = smem_opaque(sh.compose), stage_s = smem_opaque(sh.stage);
 
     for (;;) {
         __syncthreads();
@@ -167,7 +168,7 @@ k_rle_decode(const uint8_t *__restrict__ in, const uint64_t *__restrict__ off, c
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             const uint32_t o = __shfl_up_sync(FULL, incl, d);
-            if (lane >= (unsigned)d) incl = sh.compose[o * 64 + incl];
+            if (lane >= (unsigned)d) incl = lds_u8(compose_s + o * 64 + incl);
         }
         if (lane == 31) sh.wmap[warp] = incl;
         uint32_t excl_map = __shfl_up_sync(FULL, incl, 1);
@@ -184,7 +185,7 @@ k_rle_decode(const uint8_t *__restrict__ in, const uint64_t *__restrict__ off, c
 #pragma unroll
             for (int d = 1; d < RLD_WARPS; d <<= 1) {
                 const uint32_t o = __shfl_up_sync(FULL, wi, d);
-                if (lane >= (unsigned)d) wi = sh.compose[o * 64 + wi];
+                if (lane >= (unsigned)d) wi = lds_u8(compose_s + o * 64 + wi);
             }
             uint32_t we = __shfl_up_sync(FULL, wi, 1);
             if (lane == 0) we = FSM_IDENTITY;
@@ -263,8 +264,7 @@ k_rle_decode(const uint8_t *__restrict__ in, const uint64_t *__restrict__ off, c
                 uint8_t *sb = sh.stage - w0;  // sb[x] is tile-space position x
                 uint32_t o = a;
                 if (full && single) {
-                    uint32_t o_s = smem_u32(sh.stage) + a;  // single window: w0 = 0
-                    asm volatile("" : "+r"(o_s));
+                    uint32_t o_s = stage_s + a;  // single window: w0 = 0
                     // literals: one uniform, fully predicated pass -- the offset of position q is
                     // (literals before q) + (bytes of the runs before q), kept as a running sum
 #pragma unroll 1
@@ -315,8 +315,8 @@ k_rle_decode(const uint8_t *__restrict__ in, const uint64_t *__restrict__ off, c
                         const uint32_t len = cnt ? cnt : 1u;
                         if (len <= 16) {
                             const uint32_t sym = q ? (uint32_t)in[pos + q - 1] : prevb;
-                            uint8_t *d = sh.stage + my_out + (uint32_t)__popcll(m.lit & ((1ull << q) - 1ull)) + cum;
-                            for (uint32_t k = 0; k < len; k++) d[k] = (uint8_t)sym;
+                            const uint32_t d = stage_s + my_out + (uint32_t)__popcll(m.lit & ((1ull << q) - 1ull)) + cum;
+                            for (uint32_t k = 0; k < len; k++) sts_u8(d + k, sym);
                         } else {
                             long_runs |= 1ull << q;
                         }
@@ -342,7 +342,7 @@ k_rle_decode(const uint8_t *__restrict__ in, const uint64_t *__restrict__ off, c
                         if ((lr >> q) & 1ull) {
                             const uint32_t sym = q ? (uint32_t)in[pos_src + q - 1] : prev_src;
                             const uint32_t o = a_src + (uint32_t)__popcll(lt & ((1ull << q) - 1ull)) + cum;
-                            for (uint32_t k = lane; k < len; k += 32) sh.stage[o + k] = (uint8_t)sym;
+                            for (uint32_t k = lane; k < len; k += 32) sts_u8(stage_s + o + k, sym);
                         }
                         cum += len;
                     }

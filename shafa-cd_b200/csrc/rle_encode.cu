@@ -51,6 +51,32 @@ __device__ __forceinline__ uint4 rle_ld16(const void *p)
     return v;
 }
 
+// One position of the uniform literal pass, as predicated instructions on a 32-bit shared address: store the
+// byte and advance by one if the position emits a literal (bit `BIT` of l16); a triple only reserves 3 bytes.
+template <uint32_t BIT>
+__device__ __forceinline__ void rle_lit_step(uint32_t &o_s, uint32_t cur, uint32_t l16, uint32_t t16)
+{
+    asm volatile(
+        "{\n\t.reg .pred pl, pt;\n\t.reg .u32 t;\n\t"
+        "and.b32 t, %2, %4;\n\tsetp.ne.u32 pl, t, 0;\n\t"
+        "and.b32 t, %3, %4;\n\tsetp.ne.u32 pt, t, 0;\n\t"
+        "@pl st.shared.u8 [%0], %1;\n\t"
+        "@pl add.u32 %0, %0, 1;\n\t"
+        "@pt add.u32 %0, %0, 3;\n\t}"
+        : "+r"(o_s)
+        : "r"(cur), "r"(l16), "r"(t16), "n"(BIT)
+        : "memory");
+}
+template <int J>
+__device__ __forceinline__ void rle_lit_steps(uint32_t &o_s, const uint4 &x, uint32_t l16, uint32_t t16)
+{
+    if constexpr (J < 16) {
+        const uint32_t w = (J < 4) ? x.x : (J < 8) ? x.y : (J < 12) ? x.z : x.w;
+        rle_lit_step<(1u << J)>(o_s, __byte_perm(w, 0, 0x4440 | (J & 3)), l16, t16);
+        rle_lit_steps<J + 1>(o_s, x, l16, t16);
+    }
+}
+
 template <bool WRITE, bool HIST>
 __global__ void __launch_bounds__(RLE_THREADS, 5)
 k_rle_encode(const uint8_t *__restrict__ in, uint64_t n, uint64_t block_size, uint32_t tiles_per_block,
@@ -227,20 +253,16 @@ k_rle_encode(const uint8_t *__restrict__ in, uint64_t n, uint64_t block_size, ui
         {
             // literals: one uniform, fully predicated pass with a running offset; a triple just reserves 3 bytes
             uint8_t *const dst0 = sh.stage + excl;
-            uint32_t o = 0;
+            uint32_t o_s = smem_opaque(sh.stage) + excl;
 #pragma unroll
             for (int c = 0; c < RLE_VECS; c++) {
                 const uint32_t l16 = (uint32_t)(lit >> (16 * c)) & 0xffffu, t16 = (uint32_t)(tri >> (16 * c)) & 0xffffu;
                 if (__all_sync(__activemask(), t16 == 0 && l16 == 0xffffu)) {  // whole warp: sixteen literals each
 #pragma unroll
-                    for (int j = 0; j < 16; j++) dst0[o + j] = (uint8_t)byte_of(v[c], j);
-                    o += 16;
+                    for (int j = 0; j < 16; j++) sts_u8(o_s + j, byte_of(v[c], j));
+                    o_s += 16;
                 } else if (__any_sync(__activemask(), (l16 | t16) != 0)) {
-#pragma unroll
-                    for (int j = 0; j < 16; j++) {
-                        if ((l16 >> j) & 1u) dst0[o] = (uint8_t)byte_of(v[c], j);
-                        o += ((l16 >> j) & 1u) + 3u * ((t16 >> j) & 1u);
-                    }
+                    rle_lit_steps<0>(o_s, v[c], l16, t16);
                 }
             }
             // triples: sparse loop over their positions (the count needs a look-ahead in the head bitmask)
