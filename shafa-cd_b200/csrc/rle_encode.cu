@@ -295,17 +295,21 @@ k_rle_encode(const uint8_t *__restrict__ in, uint64_t n, uint64_t block_size, ui
             }
         }
         if (HIST) {
-            uint32_t *mine = sh.hist + (lane & (RLE_HIST_COPIES - 1));
+            // bin address = this lane's sub-histogram + byte * 32: byte extract, multiply-add, reduction
+            const uint32_t mine_s = smem_opaque(sh.hist) + (lane & (RLE_HIST_COPIES - 1)) * 4u;
+            auto bump = [&](uint32_t byte) {
+                asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(mine_s + byte * (RLE_HIST_COPIES * 4u)), "r"(1u) : "memory");
+            };
             const uint32_t *stage32 = reinterpret_cast<const uint32_t *>(sh.stage);
             const uint32_t whole = tile_bytes >> 2;
             for (uint32_t w = tid; w < whole; w += RLE_THREADS) {
                 const uint32_t word = stage32[w];
-                atomicAdd(&mine[(word & 0xffu) * RLE_HIST_COPIES], 1u);
-                atomicAdd(&mine[((word >> 8) & 0xffu) * RLE_HIST_COPIES], 1u);
-                atomicAdd(&mine[((word >> 16) & 0xffu) * RLE_HIST_COPIES], 1u);
-                atomicAdd(&mine[(word >> 24) * RLE_HIST_COPIES], 1u);
+                bump(__byte_perm(word, 0, 0x4440));
+                bump(__byte_perm(word, 0, 0x4441));
+                bump(__byte_perm(word, 0, 0x4442));
+                bump(__byte_perm(word, 0, 0x4443));
             }
-            if (tid < (tile_bytes & 3u)) atomicAdd(&mine[(uint32_t)sh.stage[whole * 4 + tid] * RLE_HIST_COPIES], 1u);
+            if (tid < (tile_bytes & 3u)) bump(sh.stage[whole * 4 + tid]);
             __syncthreads();
             uint32_t sum = 0;
 #pragma unroll

@@ -294,6 +294,7 @@ k_dec_sync(const uint8_t *__restrict__ payload, DecPlan plan, DecTablesGlobal g,
     __shared__ uint16_t s_count[DEC_THREADS];
     __shared__ uint32_t s_list[DEC_THREADS];    // compacted work list of a sparse round: sub-sequence | start << 16
     __shared__ uint32_t s_wcnt[DEC_THREADS / 32];
+    __shared__ uint32_t s_nlist;
     __shared__ uint32_t s_wsum[DEC_THREADS / 32];
     __shared__ uint16_t s_map[DEC_THREADS * DEC_MAP_MAX];  // [sub-sequence][start] -> (overshoot << 10) | count
     __shared__ uint8_t s_path[(DEC_THREADS / 32) * DEC_MAP_MAX * 32];  // [warp][entry offset][i]: start of the warp's i-th sub-sequence
@@ -352,16 +353,8 @@ k_dec_sync(const uint8_t *__restrict__ payload, DecPlan plan, DecTablesGlobal g,
             __syncthreads();
             const uint32_t want = tid ? s_ends[tid - 1] : carry;
             const bool changed = (want != s_start[tid]);
-            const unsigned bal = __ballot_sync(FULL, changed);
-            if (lane == 0) s_wcnt[warp] = (uint32_t)__popc(bal);
-            __syncthreads();
-            uint32_t total = 0, before = 0;
-#pragma unroll
-            for (int w = 0; w < DEC_THREADS / 32; w++) {
-                const uint32_t c = s_wcnt[w];
-                before += (w < (int)warp) ? c : 0u;
-                total += c;
-            }
+            if (tid == 0) s_nlist = 0;
+            const uint32_t total = (uint32_t)__syncthreads_count(changed);
             if (total == 0) break;
             round++;
             if (((round > 3 && total > DEC_THREADS / 2) || round > DEC_MAX_ROUNDS) && maxlen <= (uint32_t)DEC_MAP_MAX) {
@@ -410,7 +403,12 @@ k_dec_sync(const uint8_t *__restrict__ payload, DecPlan plan, DecTablesGlobal g,
             if (total > DEC_THREADS / 4) {
                 if (changed) run(tid, want);
             } else {
-                if (changed) s_list[before + (uint32_t)__popc(bal & ((1u << lane) - 1u))] = tid | (want << 16);
+                // work list in any order: one shared counter, one atomic per warp
+                const unsigned bal = __ballot_sync(FULL, changed);
+                uint32_t base = 0;
+                if (lane == 0 && bal) base = atomicAdd(&s_nlist, (uint32_t)__popc(bal));
+                base = __shfl_sync(FULL, base, 0);
+                if (changed) s_list[base + (uint32_t)__popc(bal & ((1u << lane) - 1u))] = tid | (want << 16);
                 __syncthreads();
                 if (tid < total) {
                     const uint32_t e = s_list[tid];
