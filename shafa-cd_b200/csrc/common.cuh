@@ -250,12 +250,17 @@ __device__ __forceinline__ void copy_out_unaligned(uint8_t *dst, const uint8_t *
     if (tid < n - done) dst[done + tid] = src[done + tid];
 }
 
-// bit k (k = 0..3) of the result = (byte k of w == 0).  Exact zero-byte test without the emulated
-// SIMD-video intrinsics: t has 0x80 in every zero byte; the multiply gathers bits 7/15/23/31 into a nibble.
-__device__ __forceinline__ uint32_t zero_nibble(uint32_t w)
+// 0x80 in every byte of the result whose byte of w is zero (exact, no carries between bytes)
+__device__ __forceinline__ uint32_t zero_flags(uint32_t w) { return ~(((w & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | w | 0x7F7F7F7Fu); }
+
+// bit j (j = 0..15) of the result = (byte j of the 16 bytes x,y,z,w is zero).  The flag bytes (0x80 or 0) are
+// gathered with byte dot products against the bit weights 1,2,4,8 / 16,32,64,128 -- 128 * (the 8-bit mask) per
+// pair of words -- so a vector costs four dp4a, one multiply-add and one shift on top of the flag tests.
+__device__ __forceinline__ uint32_t zero_mask16_words(uint32_t x, uint32_t y, uint32_t z, uint32_t w)
 {
-    const uint32_t t = ~(((w & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | w | 0x7F7F7F7Fu);
-    return ((t >> 7) * 0x10204080u) >> 28;
+    const uint32_t lo = __dp4a(zero_flags(y), 0x80402010u, __dp4a(zero_flags(x), 0x08040201u, 0u));
+    const uint32_t hi = __dp4a(zero_flags(w), 0x80402010u, __dp4a(zero_flags(z), 0x08040201u, 0u));
+    return (hi * 256u + lo) >> 7;
 }
 
 // bit j of the result = (byte j of v equals the byte before it); `prev` is the
@@ -266,14 +271,11 @@ __device__ __forceinline__ uint32_t eq_prev_mask16(const uint4 &v, uint32_t prev
     const uint32_t sy = __funnelshift_l(v.x, v.y, 8);
     const uint32_t sz = __funnelshift_l(v.y, v.z, 8);
     const uint32_t sw = __funnelshift_l(v.z, v.w, 8);
-    return zero_nibble(v.x ^ sx) | (zero_nibble(v.y ^ sy) << 4) | (zero_nibble(v.z ^ sz) << 8) | (zero_nibble(v.w ^ sw) << 12);
+    return zero_mask16_words(v.x ^ sx, v.y ^ sy, v.z ^ sz, v.w ^ sw);
 }
 
 // bit j = (byte j of v == 0)
-__device__ __forceinline__ uint32_t zero_mask16(const uint4 &v)
-{
-    return zero_nibble(v.x) | (zero_nibble(v.y) << 4) | (zero_nibble(v.z) << 8) | (zero_nibble(v.w) << 12);
-}
+__device__ __forceinline__ uint32_t zero_mask16(const uint4 &v) { return zero_mask16_words(v.x, v.y, v.z, v.w); }
 
 // Largest b with tile0[b] <= t  (tile0 has nb+1 monotone entries, tile0[nb] = total)
 __device__ __forceinline__ uint32_t find_block(const uint64_t *__restrict__ tile0, uint32_t nb, uint64_t t)
