@@ -418,6 +418,8 @@ SHAFA_HD uint64_t bit_window(const uint32_t *words, uint32_t q)
 // =============================================================================
 constexpr int DEC_LUT_BITS = 12;
 constexpr int DEC_LUT_SIZE = 1 << DEC_LUT_BITS;
+constexpr int DEC_LUT2_BITS = 13;       // window of the count-only table: one byte per entry, so 8 KiB as well
+constexpr int DEC_LUT2_SIZE = 1 << DEC_LUT2_BITS;
 constexpr uint32_t DEC_LONG = 0xFF;   // lut entry low byte: 1..12 length, 0 invalid, 0xFF -> fallback
 
 struct DecTables {
@@ -499,12 +501,12 @@ SHAFA_HD uint64_t dec_window64(const V &t, uint32_t row, uint32_t q)
 
 // Tables of one block as seen by a decoding thread (shared memory on the GPU).
 //   lut1[4096]  (sym << 8) | len, len 1..12; 0 = no code; 0xFF = longer than 12 bits
-//   lut2[4096]  (nsym << 8) | bits: how many whole codes fit in the 12-bit window and their total length; 0 = use lut1
+//   lut2[8192]  (nsym << 4) | bits, one byte: how many whole codes fit in the 13-bit window and their total length; 0 = use lut1
 //   lut3[4096]  (bits << 24) | (nsym << 16) | (sym1 << 8) | sym0: the first one or two whole codes of the window; 0 = use lut1
 struct DecView {
     const uint64_t *pairs;
     const uint16_t *lut1;
-    const uint16_t *lut2;
+    const uint8_t *lut2;
     const uint32_t *lut3;
     const uint64_t *sleft;
     const uint8_t *slen;
@@ -548,13 +550,13 @@ SHAFA_HD DecSub dec_count_subsequence(const V &t, uint32_t row, uint32_t start, 
     r.count = 0;
     r.bad = 0;
     int32_t q = (int32_t)start;
-    const int32_t stop12 = (int32_t)stop - DEC_LUT_BITS;
+    const int32_t stop13 = (int32_t)stop - DEC_LUT2_BITS;
     for (;;) {
-        while (q <= stop12) {
-            const uint32_t e2 = t.l2(dec_window32(t, row, (uint32_t)q) >> (32 - DEC_LUT_BITS));
+        while (q <= stop13) {
+            const uint32_t e2 = t.l2(dec_window32(t, row, (uint32_t)q) >> (32 - DEC_LUT2_BITS));
             if (e2 == 0) break;
-            q += (int32_t)(e2 & 0xFFu);
-            r.count += e2 >> 8;
+            q += (int32_t)(e2 & 0xFu);
+            r.count += e2 >> 4;
         }
         if (q >= (int32_t)stop) break;
         uint32_t sym;  // a code longer than the window, or the last few bits of the range: one code
@@ -620,17 +622,19 @@ struct DecNoEmit {
     SHAFA_HD void operator()(uint32_t, uint32_t) const {}
 };
 
-// lut2 entry for the 12-bit window value e, derived from lut1
-SHAFA_HD uint16_t dec_lut2_entry(const uint16_t *lut1, uint32_t e)
+// lut2 entry for the 13-bit window value e, derived from lut1 (codes of up to 12 bits): how many whole codes
+// the window holds and their total length
+SHAFA_HD uint8_t dec_lut2_entry(const uint16_t *lut1, uint32_t e)
 {
     uint32_t pos = 0, n = 0;
-    while (pos < (uint32_t)DEC_LUT_BITS) {
-        const uint32_t l = lut1[(e << pos) & (DEC_LUT_SIZE - 1)] & 0xFFu;  // remaining bits, zero padded
-        if (l - 1u >= (uint32_t)DEC_LUT_BITS || pos + l > (uint32_t)DEC_LUT_BITS) break;  // must fit entirely
+    while (pos < (uint32_t)DEC_LUT2_BITS) {
+        // the next 12 bits of the window, zero padded
+        const uint32_t l = lut1[((e << pos) >> (DEC_LUT2_BITS - DEC_LUT_BITS)) & (DEC_LUT_SIZE - 1)] & 0xFFu;
+        if (l - 1u >= (uint32_t)DEC_LUT_BITS || pos + l > (uint32_t)DEC_LUT2_BITS) break;  // must fit entirely
         pos += l;
         n++;
     }
-    return (uint16_t)(n ? ((n << 8) | pos) : 0);
+    return (uint8_t)(n ? ((n << 4) | pos) : 0);  // n, pos <= 13
 }
 
 // lut3 entry for the 12-bit window value e: its first one or two whole codes

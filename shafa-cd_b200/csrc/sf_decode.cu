@@ -28,7 +28,7 @@ namespace shafa {
 // ---- tables -----------------------------------------------------------------------------
 struct DecTablesGlobal {
     uint16_t *lut;    // [nb][4096]  first-level: (sym << 8) | len
-    uint16_t *lut2;   // [nb][4096]  (nsym << 8) | bits of all whole codes in the window
+    uint8_t *lut2;    // [nb][8192]  (nsym << 4) | bits of all whole codes in a 13-bit window
     uint32_t *lut3;   // [nb][4096]  first one or two codes of the window with their symbols
     uint64_t *sleft;  // [nb][256]
     uint8_t *slen;    // [nb][256]
@@ -91,7 +91,8 @@ k_dec_tables(const uint8_t *__restrict__ lens, const uint64_t *__restrict__ code
     }
     __syncthreads();
     for (int e = s; e < DEC_LUT_SIZE; e += 256) {
-        g.lut2[b * DEC_LUT_SIZE + e] = dec_lut2_entry(lut1, (uint32_t)e);
+        g.lut2[b * DEC_LUT2_SIZE + 2 * e] = dec_lut2_entry(lut1, 2u * (uint32_t)e);
+        g.lut2[b * DEC_LUT2_SIZE + 2 * e + 1] = dec_lut2_entry(lut1, 2u * (uint32_t)e + 1u);
         g.lut3[b * DEC_LUT_SIZE + e] = dec_lut3_entry(lut1, (uint32_t)e);
     }
 }
@@ -120,11 +121,11 @@ struct DecShared {
 };
 
 // lut2_dst: shared-memory copy of the multi-symbol count table (sync kernel only), or nullptr
-__device__ __forceinline__ void dec_load_tables(DecShared &sh, const DecTablesGlobal &g, uint32_t b, uint16_t *lut2_dst)
+__device__ __forceinline__ void dec_load_tables(DecShared &sh, const DecTablesGlobal &g, uint32_t b, uint8_t *lut2_dst)
 {
     const unsigned tid = threadIdx.x;
     const uint4 *src1 = reinterpret_cast<const uint4 *>(g.lut + (uint64_t)b * DEC_LUT_SIZE);
-    const uint4 *src2 = reinterpret_cast<const uint4 *>(g.lut2 + (uint64_t)b * DEC_LUT_SIZE);
+    const uint4 *src2 = reinterpret_cast<const uint4 *>(g.lut2 + (uint64_t)b * DEC_LUT2_SIZE);  // 8 KiB, like lut1
     uint4 *dst1 = reinterpret_cast<uint4 *>(sh.lut1);
     uint4 *dst2 = reinterpret_cast<uint4 *>(lut2_dst);
     for (int i = tid; i < DEC_LUT_SIZE * 2 / 16; i += DEC_THREADS) {
@@ -240,7 +241,7 @@ struct DecViewS {
     __device__ __forceinline__ uint32_t l2(uint32_t i) const
     {
         uint32_t v;
-        asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(lut2_s + i * 2u));
+        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(lut2_s + i));
         return v;
     }
     __device__ __forceinline__ uint32_t l3(uint32_t i) const
@@ -252,7 +253,7 @@ struct DecViewS {
     __device__ __forceinline__ bool has_l3() const { return lut3_s != 0; }
 };
 
-__device__ __forceinline__ DecViewS dec_view_of(const DecShared &sh, const uint16_t *lut2, const uint32_t *lut3)
+__device__ __forceinline__ DecViewS dec_view_of(const DecShared &sh, const uint8_t *lut2, const uint32_t *lut3)
 {
     DecViewS t;
     t.pairs_s = smem_u32(sh.pairs);
@@ -288,7 +289,7 @@ k_dec_sync(const uint8_t *__restrict__ payload, DecPlan plan, DecTablesGlobal g,
            uint32_t *__restrict__ seq_end, uint32_t *__restrict__ seq_count, uint64_t nseq)
 {
     __shared__ DecShared sh;
-    __shared__ __align__(16) uint16_t s_lut2[DEC_LUT_SIZE];
+    __shared__ __align__(16) uint8_t s_lut2[DEC_LUT2_SIZE];
     __shared__ uint32_t s_ends[DEC_THREADS];    // overshoot of sub-sequence i into sub-sequence i+1
     __shared__ uint16_t s_start[DEC_THREADS];   // start offset the current record of sub-sequence i was decoded from
     __shared__ uint16_t s_count[DEC_THREADS];
@@ -692,7 +693,7 @@ int launch_sf_decode(shafa_cuda_ctx *ctx, const uint8_t *d_payload, const uint64
     DecTablesGlobal g;
     g.sleft = (uint64_t *)tab;
     g.lut = (uint16_t *)(tab + nb * 256 * sizeof(uint64_t));
-    g.lut2 = (uint16_t *)(tab + nb * 256 * sizeof(uint64_t) + lut_bytes);
+    g.lut2 = (uint8_t *)(tab + nb * 256 * sizeof(uint64_t) + lut_bytes);  // DEC_LUT2_SIZE bytes per block = lut_bytes per block
     g.lut3 = (uint32_t *)(tab + nb * 256 * sizeof(uint64_t) + 2 * lut_bytes);
     g.slen = tab + nb * 256 * sizeof(uint64_t) + 4 * lut_bytes;
     g.ssym = g.slen + nb * 256;

@@ -489,7 +489,8 @@ static void codes_to_strings(const uint8_t *len, const uint64_t *code, char (*ou
 
 // ------------------------------------------------------------------ SF decode emulation (sf_decode.cu)
 struct EmuTables {
-    std::vector<uint16_t> lut, lut2;
+    std::vector<uint16_t> lut;
+    std::vector<uint8_t> lut2;
     std::vector<uint32_t> lut3;
     uint64_t sleft[256];
     uint8_t slen[256], ssym[256];
@@ -544,10 +545,11 @@ static void emu_dec_tables(const uint8_t *len, const uint64_t *code, EmuTables &
         }
         T.lut[e] = entry;
     }
-    T.lut2.assign(DEC_LUT_SIZE, 0);
+    T.lut2.assign(DEC_LUT2_SIZE, 0);
     T.lut3.assign(DEC_LUT_SIZE, 0);
     for (int e = 0; e < DEC_LUT_SIZE; e++) {
-        T.lut2[e] = dec_lut2_entry(T.lut.data(), (uint32_t)e);
+        T.lut2[2 * e] = dec_lut2_entry(T.lut.data(), 2u * (uint32_t)e);
+        T.lut2[2 * e + 1] = dec_lut2_entry(T.lut.data(), 2u * (uint32_t)e + 1u);
         T.lut3[e] = dec_lut3_entry(T.lut.data(), (uint32_t)e);
     }
 }
