@@ -399,7 +399,7 @@ constexpr int ENC_THREADS = 256;
 constexpr int ENC_VECS = 4;                                // 16-byte vectors per thread, contiguous
 constexpr int ENC_ITEMS = 16 * ENC_VECS;                   // 64 symbols per thread
 constexpr int ENC_TILE = ENC_THREADS * ENC_ITEMS;          // 16 KiB of symbols per tile
-constexpr int ENC_STAGE_WORDS = 6144;                      // staging window: 24 KiB of the tile's bit range
+constexpr int ENC_STAGE_WORDS = 5120;                      // staging window: 20 KiB of the tile's bit range (10 bits per symbol)
 SHAFA_HD uint32_t enc_entry(uint64_t code, uint32_t len) { return ((uint32_t)code << 5) | len; }
 
 // 64-bit window starting at bit `q` of a big-endian word array

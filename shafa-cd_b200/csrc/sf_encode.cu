@@ -212,7 +212,7 @@ __device__ __forceinline__ void enc_pack_thread(uint32_t lut_lane, uint32_t stag
     }
 }
 
-__global__ void __launch_bounds__(ENC_THREADS, 3)
+__global__ void __launch_bounds__(ENC_THREADS, 4)
 k_sf_encode(const uint8_t *__restrict__ in, const uint64_t *__restrict__ off, const uint64_t *__restrict__ tile0,
             uint32_t nb, const uint8_t *__restrict__ lens, const uint64_t *__restrict__ codes,
             const uint64_t *__restrict__ pay_off, uint8_t *__restrict__ payload, uint64_t *__restrict__ desc,
