@@ -400,7 +400,11 @@ constexpr int ENC_VECS = 4;                                // 16-byte vectors pe
 constexpr int ENC_ITEMS = 16 * ENC_VECS;                   // 64 symbols per thread
 constexpr int ENC_TILE = ENC_THREADS * ENC_ITEMS;          // 16 KiB of symbols per tile
 constexpr int ENC_STAGE_WORDS = 5120;                      // staging window: 20 KiB of the tile's bit range (10 bits per symbol)
-SHAFA_HD uint32_t enc_entry(uint64_t code, uint32_t len) { return ((uint32_t)code << 5) | len; }
+// Encoder LUT entry of a code of at most ENC_SHORT_MAX (< 28) bits: length in the top five bits -- so that
+// "bits += length" is one shift-add -- and the right-aligned code below.
+SHAFA_HD uint32_t enc_entry(uint64_t code, uint32_t len) { return (len << 27) | (uint32_t)code; }
+SHAFA_HD uint32_t enc_len(uint32_t entry) { return entry >> 27; }
+SHAFA_HD uint32_t enc_code(uint32_t entry) { return entry & 0x07FFFFFFu; }
 
 // 64-bit window starting at bit `q` of a big-endian word array
 SHAFA_HD uint64_t bit_window(const uint32_t *words, uint32_t q)
@@ -568,13 +572,13 @@ SHAFA_HD DecSub dec_count_subsequence(const V &t, uint32_t row, uint32_t start, 
 }
 
 // Decode the symbols that start in [start, stop).  While a whole 12-bit window lies before `stop`, the
-// first two codes inside it are taken at once (lut3).  The sink gets em.one(i, sym) for the i-th symbol,
-// or em.two(i, e3) for a lut3 entry: symbol i is e3 & 0xFF and, if e3 & 0x20000, symbol i+1 is (e3 >> 8) & 0xFF.
+// first two codes inside it are taken at once (lut3).  The sink keeps the running symbol index itself:
+// em.one(sym) appends one symbol, em.two(e3) the one or two symbols of a lut3 entry (e3 & 0xFF, then
+// (e3 >> 8) & 0xFF if e3 & 0x20000; byte 2 of e3 is how many), em.count() is how many were appended.
 template <typename V, typename Sink>
 SHAFA_HD DecSub dec_emit_to(const V &t, uint32_t row, uint32_t start, uint32_t stop, Sink &em)
 {
     DecSub r;
-    r.count = 0;
     r.bad = 0;
     int32_t q = (int32_t)start;
     const int32_t stop12 = t.has_l3() ? (int32_t)stop - DEC_LUT_BITS : -1;
@@ -582,21 +586,16 @@ SHAFA_HD DecSub dec_emit_to(const V &t, uint32_t row, uint32_t start, uint32_t s
         while (q <= stop12) {
             const uint32_t e3 = t.l3(dec_window32(t, row, (uint32_t)q) >> (32 - DEC_LUT_BITS));
             if (e3 == 0) break;
-            em.two(r.count, e3);
-#ifdef __CUDA_ARCH__
-            r.count += __byte_perm(e3, 0, 0x4442);  // byte 2: one PRMT
-#else
-            r.count += (e3 >> 16) & 0xFFu;
-#endif
+            em.two(e3);
             q += (int32_t)(e3 >> 24);
         }
         if (q >= (int32_t)stop) break;
         uint32_t sym;
         q += (int32_t)dec_one(t, row, (uint32_t)q, &sym, &r.bad);
-        em.one(r.count, sym);
-        r.count++;
+        em.one(sym);
     }
     r.end = (uint32_t)q;
+    r.count = em.count();
     return r;
 }
 
@@ -604,17 +603,19 @@ SHAFA_HD DecSub dec_emit_to(const V &t, uint32_t row, uint32_t start, uint32_t s
 template <typename F>
 struct DecFnSink {
     F f;
-    SHAFA_HD void one(uint32_t i, uint32_t sym) { f(i, sym); }
-    SHAFA_HD void two(uint32_t i, uint32_t e3)
+    uint32_t n;
+    SHAFA_HD void one(uint32_t sym) { f(n++, sym); }
+    SHAFA_HD void two(uint32_t e3)
     {
-        f(i, e3 & 0xFFu);
-        if (e3 & 0x20000u) f(i + 1, (e3 >> 8) & 0xFFu);
+        f(n++, e3 & 0xFFu);
+        if (e3 & 0x20000u) f(n++, (e3 >> 8) & 0xFFu);
     }
+    SHAFA_HD uint32_t count() const { return n; }
 };
 template <typename V, typename Emit>
 SHAFA_HD DecSub dec_emit_subsequence(const V &t, uint32_t row, uint32_t start, uint32_t stop, Emit emit)
 {
-    DecFnSink<Emit> sink{emit};
+    DecFnSink<Emit> sink{emit, 0u};
     return dec_emit_to(t, row, start, stop, sink);
 }
 

@@ -537,33 +537,37 @@ struct DecWriteShared {
     alignas(16) uint8_t stage[DEC_STAGE + 32];
 };
 
-// Sink of the write pass: symbol i of the thread goes to shared byte address base + i.  CHECKED drops
-// the symbols at or past `room` (padding bits after a block's last symbol decode to garbage).
+// Sink of the write pass: the thread's symbols go to consecutive shared byte addresses from `base`.  CHECKED
+// drops the symbols at or past `room` (padding bits after a block's last symbol decode to garbage).
 template <bool CHECKED>
 struct StageSink {
     uint32_t base, room;
-    __device__ __forceinline__ void put_if(uint32_t addr, uint32_t sym, uint32_t p) const  // store if p != 0
+    uint32_t addr;  // where the next symbol goes
+    __device__ __forceinline__ void put_if(uint32_t a, uint32_t sym, uint32_t p) const  // store if p != 0
     {
-        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p st.shared.u8 [%0], %1;\n\t}" ::"r"(addr), "r"(sym), "r"(p) : "memory");
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p st.shared.u8 [%0], %1;\n\t}" ::"r"(a), "r"(sym), "r"(p) : "memory");
     }
-    __device__ __forceinline__ void one(uint32_t i, uint32_t sym) const
+    __device__ __forceinline__ void one(uint32_t sym)
     {
         if (CHECKED)
-            put_if(base + i, sym, i < room);
+            put_if(addr, sym, addr - base < room);
         else
-            asm volatile("st.shared.u8 [%0], %1;" ::"r"(base + i), "r"(sym) : "memory");
+            asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(sym) : "memory");
+        addr++;
     }
-    __device__ __forceinline__ void two(uint32_t i, uint32_t e3) const
+    __device__ __forceinline__ void two(uint32_t e3)
     {
         const uint32_t second = e3 & 0x20000u;
         if (CHECKED) {
-            put_if(base + i, e3, i < room);
-            put_if(base + i + 1, e3 >> 8, (i + 1 < room) ? second : 0u);
+            put_if(addr, e3, addr - base < room);
+            put_if(addr + 1, e3 >> 8, (addr + 1 - base < room) ? second : 0u);
         } else {
-            asm volatile("st.shared.u8 [%0], %1;" ::"r"(base + i), "r"(e3) : "memory");
-            put_if(base + i + 1, e3 >> 8, second);
+            asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(e3) : "memory");
+            put_if(addr + 1, e3 >> 8, second);
         }
+        addr += __byte_perm(e3, 0, 0x4442);  // byte 2: one or two symbols
     }
+    __device__ __forceinline__ uint32_t count() const { return addr - base; }
 };
 
 __global__ void __launch_bounds__(DEC_THREADS)
@@ -625,10 +629,10 @@ k_dec_write(const uint8_t *__restrict__ payload, DecPlan plan, DecTablesGlobal g
                 asm volatile("" : "+r"(dst_s));
                 DecSub r;
                 if (seq_room >= total) {  // every symbol of this sequence is real (all but a block's last sequences)
-                    StageSink<false> sink{dst_s, room};
+                    StageSink<false> sink{dst_s, room, dst_s};
                     r = dec_emit_to(t, tid * DEC_ROW, sub_start(rec), stop, sink);
                 } else {
-                    StageSink<true> sink{dst_s, room};
+                    StageSink<true> sink{dst_s, room, dst_s};
                     r = dec_emit_to(t, tid * DEC_ROW, sub_start(rec), stop, sink);
                 }
                 bad |= r.bad && room;

@@ -133,6 +133,13 @@ __device__ __forceinline__ uint32_t lds32(uint32_t saddr)
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr));
     return v;
 }
+// LUT entry of byte j (0..15, compile-time) of a 16-byte vector in this lane's column: byte extract (PRMT),
+// multiply-add, load -- the generic (w >> 8k) & 0xff form costs one instruction more per lookup
+__device__ __forceinline__ uint32_t enc_lookup(uint32_t lut_lane, const uint4 &x, int j)
+{
+    const uint32_t w = (j < 4) ? x.x : (j < 8) ? x.y : (j < 12) ? x.z : x.w;
+    return lds32(lut_lane + __byte_perm(w, 0, 0x4440 | (j & 3)) * (ENC_COPIES * 4));
+}
 __device__ __forceinline__ void red_or_if(uint32_t saddr, uint32_t value, bool cond)
 {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p red.shared.or.b32 [%0], %1;\n\t}" ::"r"(saddr), "r"(value),
@@ -169,12 +176,12 @@ __device__ __forceinline__ void enc_pack_fast(uint32_t lut_lane, uint32_t stage_
         asm volatile("" : "+r"(v[c].x), "+r"(v[c].y), "+r"(v[c].z), "+r"(v[c].w));
 #pragma unroll
         for (int j = 0; j < 16; j += (PAIR ? 2 : 1)) {
-            const uint32_t e0 = lds32(lut_lane + byte_of(v[c], j) * (ENC_COPIES * 4));
-            uint32_t code = e0 >> 5, l = e0 & 31u;
+            const uint32_t e0 = enc_lookup(lut_lane, v[c], j);
+            uint32_t code = enc_code(e0), l = enc_len(e0);
             if (PAIR) {
-                const uint32_t e1 = lds32(lut_lane + byte_of(v[c], j + 1) * (ENC_COPIES * 4));
-                const uint32_t l1 = e1 & 31u;
-                code = (code << l1) | (e1 >> 5);
+                const uint32_t e1 = enc_lookup(lut_lane, v[c], j + 1);
+                const uint32_t l1 = enc_len(e1);
+                code = (code << l1) | enc_code(e1);
                 l += l1;
             }
             acc = (acc << l) | code;
@@ -200,10 +207,10 @@ __device__ __forceinline__ void enc_pack_thread(uint32_t lut_lane, uint32_t stag
         for (int j = 0; j < 16; j++) {
             uint32_t ee = lds32(lut_lane + byte_of(v[c], j) * (ENC_COPIES * 4));
             if (!ALL_VALID) ee = ((vmask >> (c * 16 + j)) & 1ull) ? ee : 0u;
-            const uint32_t l = ee & 31u;
+            const uint32_t l = enc_len(ee);
             const uint32_t q = (uint32_t)o & 31u;
             const uint32_t w = (uint32_t)(o >> 5);                             // arithmetic shift: before the window -> huge
-            const uint64_t v64 = (uint64_t)(ee >> 5) << ((64u - q - l) & 63u);  // q + l <= 57; l = 0 carries no bits
+            const uint64_t v64 = (uint64_t)enc_code(ee) << ((64u - q - l) & 63u);  // q + l <= 57; l = 0 carries no bits
             const uint32_t hi = (uint32_t)(v64 >> 32), lo = (uint32_t)v64;
             red_or_if(stage_s + w * 4u, hi, hi != 0 && w < nw);
             red_or_if(stage_s + w * 4u + 4u, lo, lo != 0 && w + 1u < nw);
@@ -278,7 +285,7 @@ k_sf_encode(const uint8_t *__restrict__ in, const uint64_t *__restrict__ off, co
 #pragma unroll
             for (int c = 0; c < ENC_VECS; c++)
 #pragma unroll
-                for (int j = 0; j < 16; j++) bits += lds32(lut_lane + byte_of(v[c], j) * (ENC_COPIES * 4)) & 31u;
+                for (int j = 0; j < 16; j++) bits += enc_len(enc_lookup(lut_lane, v[c], j));
         } else {
 #pragma unroll
             for (int c = 0; c < ENC_VECS; c++)
@@ -287,7 +294,7 @@ k_sf_encode(const uint8_t *__restrict__ in, const uint64_t *__restrict__ off, co
                     const uint64_t q = pos + 16 * c + j;
                     if (q >= lo && q < hi) {
                         vmask |= 1ull << (c * 16 + j);
-                        bits += lds32(lut_lane + byte_of(v[c], j) * (ENC_COPIES * 4)) & 31u;
+                        bits += enc_len(lds32(lut_lane + byte_of(v[c], j) * (ENC_COPIES * 4)));
                     }
                 }
         }
@@ -343,9 +350,9 @@ k_sf_encode(const uint8_t *__restrict__ in, const uint64_t *__restrict__ off, co
                     // (up to) 32 symbols just before it, right-aligned (what lies further back is shifted out)
                     uint32_t ee = 0;
                     if (base >= lo + 1 + lane) ee = sh.lut[(uint32_t)in[base - 1 - lane] * ENC_COPIES + lane];
-                    const uint32_t l = ee & 31u;
+                    const uint32_t l = enc_len(ee);
                     const uint32_t s_prev = warp_incl_scan(l) - l;  // bits of nearer symbols
-                    uint32_t w = (l && s_prev < 32u) ? ((ee >> 5) << s_prev) : 0u;
+                    uint32_t w = (l && s_prev < 32u) ? (enc_code(ee) << s_prev) : 0u;
                     w = __reduce_or_sync(FULL, w);
                     if (lane == 0) sh.stage[0] = w;
                 }

@@ -415,7 +415,7 @@ static Bytes emu_sf_encode(const Bytes &stream, uint64_t lo, uint64_t hi, const 
         for (int tid = 0; tid < NT; tid++) {
             for (int k = 0; k < IT; k++) {
                 const uint64_t q = base + (uint64_t)tid * IT + k;
-                if (q >= lo && q < hi) bits[tid] += lut[stream[q]] & 31;
+                if (q >= lo && q < hi) bits[tid] += enc_len(lut[stream[q]]);
             }
             tile_bits += bits[tid];
         }
@@ -432,8 +432,8 @@ static Bytes emu_sf_encode(const Bytes &stream, uint64_t lo, uint64_t hi, const 
                     for (int k = 0; k < IT; k++) {
                         const uint64_t q64 = base + (uint64_t)tid * IT + k;
                         const uint32_t ee = (q64 >= lo && q64 < hi) ? lut[stream[q64]] : 0;
-                        const uint32_t l = ee & 31, q = (uint32_t)o & 31u, wi = (uint32_t)(o >> 5);
-                        const uint64_t v64 = (uint64_t)(ee >> 5) << ((64u - q - l) & 63u);
+                        const uint32_t l = enc_len(ee), q = (uint32_t)o & 31u, wi = (uint32_t)(o >> 5);
+                        const uint64_t v64 = (uint64_t)enc_code(ee) << ((64u - q - l) & 63u);
                         const uint32_t hiw = (uint32_t)(v64 >> 32), low = (uint32_t)v64;
                         if (hiw && wi < nw) {
                             CHECK((stage[wi] & hiw) == 0, "overlapping bits in a staging word");
@@ -454,10 +454,10 @@ static Bytes emu_sf_encode(const Bytes &stream, uint64_t lo, uint64_t hi, const 
                 for (int lane = 0; lane < 32; lane++) {
                     uint32_t ee = 0;
                     if (base >= lo + 1 + lane) ee = lut[stream[base - 1 - lane]];
-                    const uint32_t l = ee & 31;
+                    const uint32_t l = enc_len(ee);
                     if (l && s_prev < r) {
                         const uint32_t room = r - s_prev;
-                        wv |= ((ee >> 5) & ((1u << room) - 1u)) << (32 - r + s_prev);
+                        wv |= (enc_code(ee) & ((1u << room) - 1u)) << (32 - r + s_prev);
                     }
                     s_prev += l;
                 }
