@@ -25,6 +25,7 @@ enum ScratchSlot {
     SCR_DEC_LUT,    // decode tables
     SCR_DEC_SUB,    // decode sub-sequence info
     SCR_DEC_SEQ,    // decode sequence info
+    SCR_DEC_FB,     // decode sync: per-CTA tables of the all-starts fallback
     SCR_STAGE_A,    // host API staging (input)
     SCR_STAGE_B,
     SCR_STAGE_C,

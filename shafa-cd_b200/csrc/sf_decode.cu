@@ -108,6 +108,7 @@ struct DecPlan {
 };
 
 constexpr int DEC_MAP_MAX = 16;     // longest code for which the all-starts fallback of k_dec_sync is used
+constexpr int DEC_FB_BYTES = DEC_THREADS * DEC_MAP_MAX * 2 + (DEC_THREADS / 32) * DEC_MAP_MAX * 33;  // per CTA: map + paths
 constexpr int DEC_MAX_ROUNDS = 12;  // sync rounds before that fallback is taken in any case
 constexpr int DEC_STAGE = 12288;  // symbols of one sequence staged in shared memory before the coalesced copy-out
 
@@ -284,9 +285,9 @@ __device__ __forceinline__ void dec_chunk(uint64_t nseq, uint64_t *first, uint64
 }
 
 // ---- phase 1: synchronise inside each sequence ----------------------------------------------
-__global__ void __launch_bounds__(DEC_THREADS)
+__global__ void __launch_bounds__(DEC_THREADS, 6)
 k_dec_sync(const uint8_t *__restrict__ payload, DecPlan plan, DecTablesGlobal g, uint16_t *__restrict__ sub_info,
-           uint32_t *__restrict__ seq_end, uint32_t *__restrict__ seq_count, uint64_t nseq)
+           uint32_t *__restrict__ seq_end, uint32_t *__restrict__ seq_count, uint64_t nseq, uint8_t *__restrict__ fallback)
 {
     __shared__ DecShared sh;
     __shared__ __align__(16) uint8_t s_lut2[DEC_LUT2_SIZE];
@@ -297,9 +298,11 @@ k_dec_sync(const uint8_t *__restrict__ payload, DecPlan plan, DecTablesGlobal g,
     __shared__ uint32_t s_wcnt[DEC_THREADS / 32];
     __shared__ uint32_t s_nlist;
     __shared__ uint32_t s_wsum[DEC_THREADS / 32];
-    __shared__ uint16_t s_map[DEC_THREADS * DEC_MAP_MAX];  // [sub-sequence][start] -> (overshoot << 10) | count
-    __shared__ uint8_t s_path[(DEC_THREADS / 32) * DEC_MAP_MAX * 32];  // [warp][entry offset][i]: start of the warp's i-th sub-sequence
-    __shared__ uint8_t s_path_out[(DEC_THREADS / 32) * DEC_MAP_MAX];   // [warp][entry offset]: offset handed to the next warp
+    // tables of the all-starts fallback: rarely used, so they live in this CTA's slice of a global scratch buffer
+    // (L2-resident) instead of costing every launch 12 KiB of shared memory and a CTA per SM
+    uint16_t *const s_map = reinterpret_cast<uint16_t *>(fallback + (size_t)blockIdx.x * DEC_FB_BYTES);  // [sub-sequence][start] -> (overshoot << 10) | count
+    uint8_t *const s_path = reinterpret_cast<uint8_t *>(s_map + DEC_THREADS * DEC_MAP_MAX);               // [warp][entry offset][i]: start of the warp's i-th sub-sequence
+    uint8_t *const s_path_out = s_path + (DEC_THREADS / 32) * DEC_MAP_MAX * 32;                          // [warp][entry offset]: offset handed to the next warp
     __shared__ uint32_t s_maxlen;
     const unsigned tid = threadIdx.x, lane = lane_id(), warp = warp_id();
     uint64_t seq_first, seq_last;
@@ -725,8 +728,10 @@ int launch_sf_decode(shafa_cuda_ctx *ctx, const uint8_t *d_payload, const uint64
     if (grid_sync > nseq) grid_sync = nseq;
     if (grid_write > nseq) grid_write = nseq;
     SHAFA_LAUNCH(ctx, "dec_tables", k_dec_tables, dim3((unsigned)nb), dim3(256), 0, d_len, d_code, g);
+    uint8_t *fb = (uint8_t *)scratch_get(ctx, SCR_DEC_FB, (size_t)grid_sync * DEC_FB_BYTES);
+    if (!fb) return SHAFA_LACK_OF_MEMORY;
     SHAFA_LAUNCH(ctx, "dec_sync", k_dec_sync, dim3((unsigned)grid_sync), dim3(DEC_THREADS), 0, d_payload, plan, g, sub_info,
-                 seq_end, seq_count, nseq);
+                 seq_end, seq_count, nseq, fb);
     SHAFA_CHECK_LAUNCH(ctx);
     // stitch across chunk boundaries until a pass moves no sequence end (normally the first pass)
     uint32_t *h_flag = (uint32_t *)pinned_get(ctx, 64);
