@@ -99,7 +99,7 @@ _modules_error shafa_compress(char **const path)
         }
         if (err) goto out;
         const uint64_t ptotal = poff[nb - 1] + ((z[nb - 1] + 15) & ~15ull);
-        h_payload = shafa_cuda_host_alloc(ptotal + 16);
+        h_payload = cli_host_alloc(ptotal + 16);
         if (!h_payload) {
             err = _LACK_OF_MEMORY;
             goto out;
@@ -125,7 +125,7 @@ out:
         if (d_code) shafa_cuda_dev_free(g, d_code);
         if (d_payload) shafa_cuda_dev_free(g, d_payload);
     }
-    if (h_payload) shafa_cuda_host_free(h_payload);
+    if (h_payload) cli_host_free(h_payload);
     if (!err) {
         printf("Module: C (Symbol codes' codification) [libshafa_cuda]\nNumber of blocks: %llu\n", (unsigned long long)nb);
         for (uint64_t b = 0; b < nb; b++)

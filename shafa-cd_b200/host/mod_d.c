@@ -59,7 +59,7 @@ static _modules_error expand_on_device(shafa_cuda_ctx *g, const void *d_rle, con
     if (!err) {
         uint64_t tot = 0;
         for (uint64_t b = 0; b < nb; b++) tot += fin[b];
-        *h_out = shafa_cuda_host_alloc(tot + 16);
+        *h_out = cli_host_alloc(tot + 16);
         if (!*h_out)
             err = _LACK_OF_MEMORY;
         else if (!(err = gpu_status(shafa_cuda_memcpy_d2h(g, *h_out, d_out, tot))))
@@ -141,7 +141,7 @@ _modules_error rle_decompress(char **const path)
     err = write_all(p_out, h_out, out_size); /* d.c:218 */
 out:
     if (g && d_rle) shafa_cuda_dev_free(g, d_rle);
-    if (h_out) shafa_cuda_host_free(h_out);
+    if (h_out) cli_host_free(h_out);
     if (!err) {
         summary("RLE", now_ms() - t0, sizes, fin, nb, p_out);
         free(*path); /* d.c:378-379 */
@@ -206,7 +206,7 @@ _modules_error shafa_decompress(char **const path, const bool decompress_rle)
     fin = malloc((nb + 1) * sizeof *fin);
     code = malloc((nb * 256 + 1) * sizeof *code);
     len = malloc(nb * 256 + 1);
-    h_payload = shafa_cuda_host_alloc(shaf.size + 16 * nb + 64);
+    h_payload = cli_host_alloc(shaf.size + 16 * nb + 64);
     if (!z || !poff || !n || !offsets || !fin || !code || !len || !h_payload) {
         err = _LACK_OF_MEMORY;
         goto out;
@@ -253,7 +253,7 @@ _modules_error shafa_decompress(char **const path, const bool decompress_rle)
         if (decompress_rle) { /* d.c:574-586 */
             if ((err = expand_on_device(g, d_sym, offsets, nb, fin, &h_out, &out_size))) goto out;
         } else {
-            h_out = shafa_cuda_host_alloc(stotal + 16);
+            h_out = cli_host_alloc(stotal + 16);
             if (!h_out) {
                 err = _LACK_OF_MEMORY;
                 goto out;
@@ -272,8 +272,8 @@ out:
         if (d_code) shafa_cuda_dev_free(g, d_code);
         if (d_sym) shafa_cuda_dev_free(g, d_sym);
     }
-    if (h_payload) shafa_cuda_host_free(h_payload);
-    if (h_out) shafa_cuda_host_free(h_out);
+    if (h_payload) cli_host_free(h_payload);
+    if (h_out) cli_host_free(h_out);
     if (!err) {
         summary(decompress_rle ? "SHAFA & RLE" : "SHAFA", now_ms() - t0, z, fin, nb, p_out);
         free(*path); /* d.c:814-815 */

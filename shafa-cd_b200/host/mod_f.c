@@ -116,7 +116,7 @@ _modules_error freq_rle_compress(char **const path, const bool force_rle, const 
         if ((err = gpu_status(shafa_cuda_rle_encode_blocks(g, d_in, n, bs, d_rle, cap, rle_sizes, d_hist)))) goto out;
         uint64_t tot = 0;
         for (uint64_t b = 0; b < nb; b++) tot += rle_sizes[b];
-        h_rle = shafa_cuda_host_alloc(tot + 16);
+        h_rle = cli_host_alloc(tot + 16);
         if (!h_rle) {
             err = _LACK_OF_MEMORY;
             goto out;
@@ -146,7 +146,7 @@ out:
     if (d_in) shafa_cuda_dev_free(g, d_in);
     if (d_rle) shafa_cuda_dev_free(g, d_rle);
     if (d_hist) shafa_cuda_dev_free(g, d_hist);
-    if (h_rle) shafa_cuda_host_free(h_rle);
+    if (h_rle) cli_host_free(h_rle);
     blob_free(&in);
     if (!err) {
         const bool wrote_freq = !use_rle || force_freq;

@@ -80,6 +80,29 @@ _modules_error gpu_status(int rc)
 
 /* ---- files ----------------------------------------------------------------------------- */
 
+/* Host buffers of the CLI are used once per process.  Page-locking a GiB costs several times what the
+ * pageable copy costs over a pinned one, so they are plain page-aligned allocations unless SHAFA_CLI_PINNED
+ * is set (a long-lived caller of the library should pin its buffers instead: that is what bench.py's e2e does). */
+static bool cli_pinned(void)
+{
+    const char *e = getenv("SHAFA_CLI_PINNED");
+    return e && *e && *e != '0';
+}
+void *cli_host_alloc(size_t bytes)
+{
+    if (cli_pinned()) return shafa_cuda_host_alloc(bytes);
+    void *p = NULL;
+    return posix_memalign(&p, 4096, bytes ? bytes : 1) == 0 ? p : NULL;
+}
+void cli_host_free(void *p)
+{
+    if (!p) return;
+    if (cli_pinned())
+        shafa_cuda_host_free(p);
+    else
+        free(p);
+}
+
 _modules_error blob_read(const char *path, blob *b)
 {
     b->data = NULL;
@@ -96,9 +119,12 @@ _modules_error blob_read(const char *path, blob *b)
         fclose(f);
         return _FILE_STREAM_FAILED;
     }
-    b->data = shafa_cuda_host_alloc((size_t)sz + 64);
-    b->pinned = b->data != NULL;
-    if (!b->data) b->data = malloc((size_t)sz + 64);
+    b->pinned = cli_pinned();
+    b->data = cli_host_alloc((size_t)sz + 64);
+    if (!b->data && b->pinned) { /* no CUDA device to pin against; the module will fail later */
+        b->pinned = false;
+        b->data = malloc((size_t)sz + 64);
+    }
     if (!b->data) {
         fclose(f);
         return _LACK_OF_MEMORY;

@@ -29,13 +29,16 @@ void gpu_release(void);
 /* libshafa_cuda status -> _modules_error (same numbering) */
 _modules_error gpu_status(int rc);
 
-/* whole file -> pinned host buffer (16 spare bytes after the end). */
+/* whole file -> host buffer (64 zeroed spare bytes after the end); pageable unless SHAFA_CLI_PINNED is set */
 typedef struct {
     uint8_t *data;
     uint64_t size;
-    bool pinned; /* false: plain malloc (no CUDA device to pin against; the module will fail later) */
+    bool pinned; /* data came from shafa_cuda_host_alloc (else from malloc / posix_memalign) */
 } blob;
 _modules_error blob_read(const char *path, blob *b);
+/* large one-shot host buffers of the CLI: pageable by default, pinned with SHAFA_CLI_PINNED=1 */
+void *cli_host_alloc(size_t bytes);
+void cli_host_free(void *p);
 void blob_free(blob *b);
 
 /* cursor over "@...@..." text */
