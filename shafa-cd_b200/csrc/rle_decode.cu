@@ -11,10 +11,12 @@
 // inside the block) carries the state across 16 KiB tiles -- tiles whose map is
 // constant (almost all) publish their exit state without waiting.  A CTA scan of
 // output sizes plus chain #2 (over all tiles of the file) places the tile in the
-// output.  The tile's output is materialised in a 32 KiB staging buffer that is
-// co-aligned with the destination and copied out with 16-byte stores; a tile
-// that expands to more than one buffer (long runs) goes through it window by
-// window, every thread writing only the part of its output inside the window.
+// output.  The tile's size is published right after the scan; its output is
+// materialised in a 24 KiB staging buffer at tile-relative offsets, the prefix is
+// resolved behind that work, and the copy-out realigns (copy_out_unaligned).  A
+// tile that expands past the buffer (long runs) is placed first and expanded
+// straight into global memory, each warp filling the runs of its own 32 threads
+// with 16-byte stores.
 #include "common.cuh"
 #include "core.h"
 #include "internal.h"
@@ -108,6 +110,56 @@ __device__ __forceinline__ void rld_emit(uint8_t *stage_base, uint32_t wlo, uint
         const uint32_t lo = o > wlo ? o : wlo;
         const uint32_t hi = (o + len < whi) ? (o + len) : whi;
         if (lo < hi) rld_fill(stage_base + lo, sym, hi - lo);
+    }
+}
+
+// `len` (<= 255) copies of `sym` at dst in global memory, by the 32 lanes of a warp: bytes up to the first
+// 16-byte boundary, 16-byte stores, tail bytes
+__device__ __forceinline__ void rld_fill_global(uint8_t *dst, uint32_t sym, uint32_t len, unsigned lane)
+{
+    const uint32_t mis = (16u - (uint32_t)((uintptr_t)dst & 15u)) & 15u;
+    const uint32_t head = mis < len ? mis : len;
+    if (lane < head) dst[lane] = (uint8_t)sym;
+    const uint32_t body = (len - head) >> 4;  // <= 15 chunks
+    const uint32_t w = sym * 0x01010101u;
+    if (lane < body) st_stream16(dst + head + 16 * lane, make_uint4(w, w, w, w));
+    const uint32_t done = head + 16 * body;
+    if (lane < len - done) dst[done + lane] = (uint8_t)sym;
+}
+
+// A warp expands the records of its own 32 threads straight into global memory, one record at a time (tiles
+// whose output does not fit the staging buffer).  `out_tile` is where the tile's output starts; lit / run are the
+// thread's literal and count-byte positions relative to its first valid byte j0.  Not inlined: keeps the
+// registers of this rare path out of the common one.
+__device__ __noinline__ void rld_expand_direct(const uint8_t *__restrict__ in, uint8_t *__restrict__ out_tile, uint64_t pos, int j0,
+                                               uint32_t obytes, uint32_t my_out, uint64_t lit, uint64_t run, uint32_t prevb)
+{
+    const unsigned lane = lane_id();
+    for (int src = 0; src < 32; src++) {
+        if (__shfl_sync(FULL, obytes, src) == 0) continue;  // uniform
+        const uint64_t lt = __shfl_sync(FULL, lit, src), rn = __shfl_sync(FULL, run, src);
+        const uint32_t prev_src = __shfl_sync(FULL, prevb, src);
+        const uint8_t *psrc = in + (pos - ((uint64_t)lane - (uint64_t)src) * RLD_PER_THREAD) + __shfl_sync(FULL, j0, src);
+        uint8_t *o = out_tile + __shfl_sync(FULL, my_out, src);
+        uint64_t eb = lt | rn;
+        while (eb) {  // the same trip for every lane: all operands are the source lane's
+            const int q = ctz64(eb);
+            if ((rn >> q) & 1ull) {
+                const uint32_t cnt = psrc[q];  // every lane reads the same byte (broadcast)
+                const uint32_t len = cnt ? cnt : 1u;
+                const uint32_t sym = q ? (uint32_t)psrc[q - 1] : prev_src;
+                rld_fill_global(o, sym, len, lane);
+                o += len;
+                eb &= eb - 1;
+            } else {
+                // literals at consecutive positions are consecutive in the output: copy the segment
+                const uint64_t rest = lt >> q;
+                const uint32_t seg = (~rest) ? (uint32_t)ctz64(~rest) : 64u;
+                for (uint32_t k = lane; k < seg; k += 32) o[k] = psrc[q + k];
+                o += seg;
+                eb &= (seg >= 64u) ? 0ull : ~(((1ull << seg) - 1ull) << q);
+            }
+        }
     }
 }
 
@@ -252,19 +304,38 @@ k_rle_decode(const uint8_t *__restrict__ in, const uint64_t *__restrict__ off, c
         const uint32_t my_out = block_excl_scan<RLD_THREADS>(obytes, sh.scan, &tile_out);
         if (tid == 0) lookback_publish(desc_out, (int64_t)t, 0, tile_out);  // the size now, the place after the staging
 
-        // ---- materialise the tile's output at tile-relative offsets, one staging window at a time ----
         const bool single = tile_out <= (uint32_t)RLD_STAGE;
-        bool placed = false;
-        uint64_t out0 = 0;
-        for (uint32_t w0 = 0; w0 < tile_out || !placed; w0 += RLD_STAGE) {
-            const uint32_t w1 = (tile_out - w0 < (uint32_t)RLD_STAGE) ? tile_out : (w0 + RLD_STAGE);
+        if (!single) {
+            // ---- the tile expands past the staging buffer (long runs): place it first, then every warp expands
+            // the records of its own 32 threads straight into global memory, one record at a time ----
+            if (warp == 0) {
+                const uint64_t pfx = lookback_resolve(desc_out, (int64_t)t, 0, tile_out);
+                if (lane == 0) sh.out_prefix = pfx;
+            }
+            __syncthreads();
+            const uint64_t big0 = sh.out_prefix;
+            if (is_last && tid == 0) {
+                blk_end[b] = big0 + tile_out;
+                if (fsm_apply(sh.tile_map, tile_entry) != 0) atomicOr(err, (uint32_t)ERR_RLE_TRUNCATED);  // block ends inside a triple
+            }
+            if (big0 + tile_out > out_capacity) {
+                if (tid == 0) atomicOr(err, (uint32_t)ERR_CAPACITY);
+                continue;
+            }
+            rld_expand_direct(in, out + big0, pos, j0, obytes, my_out, m.lit, m.run, prevb);
+            continue;
+        }
+
+        // ---- materialise the tile's output at tile-relative offsets in the staging buffer ----
+        {
+            const uint32_t w0 = 0, w1 = tile_out;  // the whole tile is one window of the stage
             // my output occupies tile-space [a, a+obytes)
             const uint32_t a = my_out;
-            if (obytes && a < w1 && a + obytes > w0) {
-                uint8_t *sb = sh.stage - w0;  // sb[x] is tile-space position x
+            if (obytes) {
+                uint8_t *sb = sh.stage;  // sb[x] is tile-space position x
                 uint32_t o = a;
-                if (full && single) {
-                    uint32_t o_s = stage_s + a;  // single window: w0 = 0
+                if (full) {
+                    uint32_t o_s = stage_s + a;
                     // literals: one uniform, fully predicated pass -- the offset of position q is
                     // (literals before q) + (bytes of the runs before q), kept as a running sum
 #pragma unroll 1
@@ -300,7 +371,7 @@ k_rle_decode(const uint8_t *__restrict__ in, const uint64_t *__restrict__ off, c
                     }
                 }
             }
-            if (single) {
+            {
                 // runs.  Short ones (<= 16 bytes: the common case in text) are written by their own lane, all
                 // lanes in parallel; long ones are filled by the whole warp, one run at a time.
                 uint64_t long_runs = 0;
@@ -348,27 +419,22 @@ k_rle_decode(const uint8_t *__restrict__ in, const uint64_t *__restrict__ off, c
                     }
                 }
             }
-            if (!placed) {  // first window: the tile's place in the output, looked up behind the staging work
-                if (warp == 0) {
-                    const uint64_t pfx = lookback_resolve(desc_out, (int64_t)t, 0, tile_out);
-                    if (lane == 0) sh.out_prefix = pfx;
-                }
-                __syncthreads();
-                placed = true;
-                out0 = sh.out_prefix;
-                if (is_last && tid == 0) {
-                    blk_end[b] = out0 + tile_out;
-                    if (fsm_apply(sh.tile_map, tile_entry) != 0) atomicOr(err, (uint32_t)ERR_RLE_TRUNCATED);  // block ends inside a triple
-                }
-                if (out0 + tile_out > out_capacity) {
-                    if (tid == 0) atomicOr(err, (uint32_t)ERR_CAPACITY);
-                    break;
-                }
-            } else {
-                __syncthreads();
+            // the tile's place in the output, looked up behind the staging work
+            if (warp == 0) {
+                const uint64_t pfx = lookback_resolve(desc_out, (int64_t)t, 0, tile_out);
+                if (lane == 0) sh.out_prefix = pfx;
             }
-            if (w1 > w0) copy_out_unaligned<RLD_THREADS>(out + out0 + w0, sh.stage, w1 - w0);
-            if (w1 < tile_out) __syncthreads();  // the next window overwrites the stage
+            __syncthreads();
+            const uint64_t out0 = sh.out_prefix;
+            if (is_last && tid == 0) {
+                blk_end[b] = out0 + tile_out;
+                if (fsm_apply(sh.tile_map, tile_entry) != 0) atomicOr(err, (uint32_t)ERR_RLE_TRUNCATED);  // block ends inside a triple
+            }
+            if (out0 + tile_out > out_capacity) {
+                if (tid == 0) atomicOr(err, (uint32_t)ERR_CAPACITY);
+                continue;
+            }
+            if (tile_out) copy_out_unaligned<RLD_THREADS>(out + out0, sh.stage, tile_out);
         }
     }
 }
