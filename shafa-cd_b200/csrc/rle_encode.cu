@@ -5,23 +5,25 @@
 //
 // Tile = 16 KiB of one block (tiles never straddle a block), 256 threads x 64
 // contiguous bytes held in registers (four 16-byte vectors).  Per tile:
-//   1. loads; "continuation" bits E (byte equals its predecessor) as one 64-bit
-//      mask per thread by SIMD byte compares; the neighbours' edge bits arrive by
-//      warp shuffles, the warp edges read one extra word.  ~E is the run-head
-//      bitmask, kept in shared memory together with a 288-position look-ahead
-//      halo (positions at/after the block end count as heads).
+//   1. loads; "continuation" bits E (byte equals its predecessor) and zero bits Z as
+//      64-bit masks per thread (exact byte tests + dp4a gathers, common.cuh); the
+//      neighbours' edge bits arrive by warp shuffles, the warp edges read one extra
+//      word.  ~E is the run-head bitmask, kept in shared memory together with a
+//      288-position look-ahead halo (positions at/after the block end count as heads).
 //   2. chain #1 (decoupled look-back inside the block): length of the run that
 //      is still open at the tile start (needed for k mod 255).
-//   3. what every position emits: threads whose positions all have k < 255 use
-//      the bit-parallel rule shafa::rle_fast_masks64 (core.h); threads deep
-//      inside a >= 255-byte run use the general per-position walk.
-//   4. CTA scan of emitted bytes, chain #2 (look-back over ALL tiles of the
-//      file) gives the tile's offset in the compacted output.  The chain's
-//      prefix frontier moves one look-back window per L2 round trip, which is
-//      why tiles are 16 KiB and the window 128 descriptors.
-//   5. bytes are staged in shared memory co-aligned with the destination and
-//      copied out with 16-byte stores; the same staging buffer feeds the fused
-//      256-bin histogram (8 striped sub-histograms to spread equal-byte hits).
+//   3. what every position emits: the bit-parallel rule shafa::rle_fast_masks64
+//      (core.h); inside a run longer than 255 bytes the first position of every
+//      further 255-byte chunk is turned into a head first (rle_chunk_heads).
+//   4. CTA scan of emitted bytes; the tile's size is published at once (chain #2,
+//      look-back over ALL tiles of the file).  The chain's prefix frontier moves
+//      one look-back window per L2 round trip, which is why tiles are 16 KiB and
+//      the window 128 descriptors.
+//   5. bytes are staged in shared memory at tile-relative offsets (uniform
+//      predicated literal pass + sparse triple loop); chain #2 is resolved behind
+//      that work and the copy-out realigns (copy_out_unaligned).  The same staging
+//      buffer feeds the fused 256-bin histogram (8 striped sub-histograms to
+//      spread equal-byte hits).
 #include "common.cuh"
 #include "core.h"
 #include "internal.h"

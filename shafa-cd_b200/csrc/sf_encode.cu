@@ -5,15 +5,20 @@
 // Single pass over the symbol stream (algorithmic bytes S + Z):
 //   * exact payload sizes come from histogram x code length (k_sf_block_bits),
 //     so every block gets a 16-byte aligned payload slot before encoding starts;
-//   * tiles are 4096-byte aligned windows of the stream intersected with the
-//     block (aligned 16-byte loads even for the ragged .rle stream);
-//   * per tile: conflict-free code LUT lookups (one private bank per lane),
-//     CTA scan of bit lengths, decoupled look-back along the block's tiles for
-//     the tile's bit offset, packing into big-endian words in shared memory, and
-//     coalesced word stores.  A 32-bit word that straddles two tiles is written
-//     by the tile holding its last bit, which re-encodes the <= 31 preceding
-//     symbols, so no output word is ever touched twice and no memset/atomics on
-//     global memory are needed.
+//   * tiles are 16 KiB aligned windows of the stream intersected with the
+//     block (aligned 16-byte loads even for the ragged .rle stream), 64 symbols
+//     per thread;
+//   * per tile: conflict-free code LUT lookups (one private bank per lane), a
+//     length pass and a CTA scan of bit lengths; the tile's bit count is published
+//     at once.  Codes are packed at tile-relative bit positions through a 64-bit
+//     register accumulator (whole words as plain shared stores, only a thread's
+//     last partial word is OR-ed in); the decoupled look-back along the block's
+//     tiles is resolved behind the packing, and the copy-out shifts by the
+//     prefix's low five bits, byte-swaps and writes 16-byte groups.  A 32-bit
+//     word that straddles two tiles is written by the tile holding its last bit,
+//     which rebuilds the preceding bits from the <= 32 preceding symbols, so no
+//     output word is ever touched twice and no memset/atomics on global memory
+//     are needed.
 //   * blocks whose longest code exceeds 26 bits (never seen on real data; the
 //     format allows it) take k_sf_encode_long, a simple one-CTA-per-block kernel.
 #include "common.cuh"
