@@ -2,6 +2,7 @@
 """bench.py -- F+C encode & D decode throughput of the Shafa block pipeline on B200.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload C2|C1|C3|C4] [--bytes B] [--no-cpu]
 
 A "step" is one full F -> T -> C -> D round trip over one synthetic file of
 BASELINE.json configs[1]: 1 GiB low-entropy text-like bytes, m = 8 MiB blocks
@@ -12,8 +13,14 @@ collective on the data path (weak scaling); timing is the max over ranks.
 One JSON line on stdout (rank 0).  `value` is device-resident (input already in
 HBM), `e2e` goes through the host-buffer C-ABI calls with host<->device copies
 inside the timed region, `roofline` is the dominant kernel measured with CUDA
-events on the launch stream, `cpu_baseline` is the unmodified reference binary
-(oracle/_ref/shafa) timed on this box's host cores on a bounded sample.
+events on the launch stream (`traffic` = its DRAM bytes per launch from the
+committed ncu capture, profiles/*_traffic.json), `cpu_baseline` is the unmodified
+reference binary (oracle/_ref/shafa) timed on this box's host cores on a bounded
+sample, multi-threaded as the reference runs by default plus one
+--no-multithread pass.  `clocks` are nvidia-smi samples taken inside the timed
+windows.  `--impl reference` times that binary alone (rank 0 only under
+torchrun).  `--workload` times the other BASELINE input shapes with the same
+harness; the metric is quoted on C2.
 """
 from __future__ import annotations
 
