@@ -44,7 +44,7 @@ GIB = 1 << 30
 MIB = 1 << 20
 WORKLOAD = "C2: 1 GiB text-like synthetic (seed 2024), -b m (8 MiB blocks), F->T->C->D round trip"
 METRIC = "F+C encode & D decode round-trip throughput, GB/s of input"
-CPU_SAMPLE_BYTES = 256 * MIB   # bounded sample of the same generator for the reference arm
+CPU_SAMPLE_BYTES = int(os.environ.get("SHAFA_BENCH_CPU_SAMPLE_MB", "256")) * MIB   # bounded sample of the same generator for the reference arm
 
 
 def measured_peak_hbm():
