@@ -480,7 +480,9 @@ static int encode_host_impl(shafa_cuda_ctx *ctx, const uint8_t *h_in, uint64_t n
 {
     CTX_ENTER(ctx);
     if (!out || !h_in) return SHAFA_OUTSIDE_MODULE;
-    if (block_size < 512) block_size = 512;                       // utils/file.c:61-65
+    if (block_size == 0) block_size = 524288;                     // utils/file.c:62 (the reference's default)
+    if (block_size < 512) block_size = 512;                       // utils/file.c:63
+    if (n >= (1ull << 48)) return SHAFA_LACK_OF_MEMORY;           // keeps every nb * 256 * 8 product far from wrapping
     if (block_size > 67108864ull) return SHAFA_FILE_STREAM_FAILED;
     if (mode < 0 && n < 1024) return SHAFA_FILE_TOO_SMALL;        // f.c:220,366 (a file-level rule)
     if (n == 0) return SHAFA_FILE_TOO_SMALL;
@@ -639,12 +641,17 @@ int shafa_cuda_rle_decode_host(shafa_cuda_ctx *ctx, const uint8_t *h_rle, const 
     uint8_t *d_rle = (uint8_t *)scratch_get(ctx, SCR_STAGE_A, round16(total) + 64);
     uint8_t *d_out = (uint8_t *)scratch_get(ctx, SCR_STAGE_B, round16(out_capacity) + 64);
     uint64_t *fin = h_final_sizes ? h_final_sizes : (uint64_t *)malloc(nb * sizeof(uint64_t));
-    if (!d_rle || !d_out || !fin) return SHAFA_LACK_OF_MEMORY;
+    if (!d_rle || !d_out || !fin) {
+        if (!h_final_sizes) free(fin);
+        return SHAFA_LACK_OF_MEMORY;
+    }
+    memset(fin, 0, nb * sizeof(uint64_t));
     int rc = shafa_cuda_memcpy_h2d(ctx, d_rle, h_rle, total);
     if (!rc) rc = shafa_cuda_rle_decode_blocks(ctx, d_rle, h_offsets, nb, d_out, out_capacity, fin);
     uint64_t produced = 0;
-    for (uint64_t b = 0; b < nb; b++) produced += fin[b];
-    if (h_out_size) *h_out_size = produced;  // valid even on SHAFA_LACK_OF_MEMORY so the caller can retry
+    if (!rc || rc == SHAFA_LACK_OF_MEMORY)  // the sizes are exact in both cases (the caller may retry with a larger buffer)
+        for (uint64_t b = 0; b < nb; b++) produced += fin[b];
+    if (h_out_size) *h_out_size = produced;
     if (!rc) rc = shafa_cuda_memcpy_d2h(ctx, h_out, d_out, produced);
     if (!rc) rc = shafa_cuda_synchronize(ctx);
     if (!h_final_sizes) free(fin);

@@ -103,7 +103,9 @@ int encode_host_pipelined(shafa_cuda_ctx *ctx, const uint8_t *h_in, uint64_t n, 
 {
     if (!ctx || !out || !h_in) return SHAFA_OUTSIDE_MODULE;
     if (cudaSetDevice(ctx->device) != cudaSuccess) return SHAFA_THREAD_CREATION_FAILED;
-    if (block_size < 512) block_size = 512;  // utils/file.c:61-65
+    if (block_size == 0) block_size = 524288;                     // utils/file.c:62 (the reference's default)
+    if (block_size < 512) block_size = 512;                       // utils/file.c:63
+    if (n >= (1ull << 48)) return SHAFA_LACK_OF_MEMORY;           // keeps every nb * 256 * 8 product far from wrapping
     if (block_size > 67108864ull) return SHAFA_FILE_STREAM_FAILED;
     if (mode < 0 && n < 1024) return SHAFA_FILE_TOO_SMALL;  // f.c:220,366
     if (n == 0) return SHAFA_FILE_TOO_SMALL;
@@ -160,16 +162,22 @@ int encode_host_pipelined(shafa_cuda_ctx *ctx, const uint8_t *h_in, uint64_t n, 
     std::atomic<int> err{0};
     const bool rle_mode = out->rle_mode, want_orig = out->hist_orig != nullptr;
 
-    auto fail = [&](int code) {
+    std::mutex err_m;
+    std::string err_text;
+    auto fail_from = [&](shafa_cuda_ctx *w, int code) {
         int expected = 0;
-        err.compare_exchange_strong(expected, code);
+        if (err.compare_exchange_strong(expected, code)) {
+            std::lock_guard<std::mutex> lk(err_m);
+            err_text = w ? shafa_cuda_last_error(w) : "worker context could not be created";  // the FIRST failing worker's text
+        }
         rle_chain.abort();
         pay_chain.abort();
     };
 
     auto work = [&](int widx) {
         shafa_cuda_ctx *w = worker_ctx(ctx, widx);
-        if (!w) return fail(SHAFA_LACK_OF_MEMORY);
+        if (!w) return fail_from(nullptr, SHAFA_LACK_OF_MEMORY);
+        auto fail = [&](int code) { fail_from(w, code); };
         for (;;) {
             const uint64_t c = next.fetch_add(1);
             if (c >= ch.count || err.load()) return;
@@ -240,7 +248,10 @@ int encode_host_pipelined(shafa_cuda_ctx *ctx, const uint8_t *h_in, uint64_t n, 
     }
     rc = err.load();
     if (rc) {
-        if (ctx->workers[0]) set_error(ctx, rc, "pipelined encode: %s", shafa_cuda_last_error(ctx->workers[0]));
+        // copies into the caller's buffers may still be in flight on the streams of workers that bailed out
+        for (int i = 0; i < PIPE_MAX_WORKERS; i++)
+            if (ctx->workers[i]) cudaStreamSynchronize(ctx->workers[i]->stream);
+        set_error(ctx, rc, "pipelined encode: %s", err_text.c_str());
         out->rle = nullptr;  // caller-owned buffers stay with the caller
         out->payload = nullptr;
         shafa_cuda_encoded_free(out);
@@ -275,14 +286,20 @@ int decode_host_pipelined(shafa_cuda_ctx *ctx, const uint8_t *h_payload, const u
         fin_local.assign(nb, 0);
         fin = fin_local.data();
     }
-    auto fail = [&](int code) {
+    std::mutex err_m;
+    std::string err_text;
+    auto fail_from = [&](shafa_cuda_ctx *w, int code) {
         int expected = 0;
-        err.compare_exchange_strong(expected, code);
+        if (err.compare_exchange_strong(expected, code)) {
+            std::lock_guard<std::mutex> lk(err_m);
+            err_text = w ? shafa_cuda_last_error(w) : "worker context could not be created";
+        }
         out_chain.abort();
     };
     auto work = [&](int widx) {
         shafa_cuda_ctx *w = worker_ctx(ctx, widx);
-        if (!w) return fail(SHAFA_LACK_OF_MEMORY);
+        if (!w) return fail_from(nullptr, SHAFA_LACK_OF_MEMORY);
+        auto fail = [&](int code) { fail_from(w, code); };
         for (;;) {
             const uint64_t c = next.fetch_add(1);
             if (c >= ch.count || err.load()) return;
@@ -358,7 +375,9 @@ int decode_host_pipelined(shafa_cuda_ctx *ctx, const uint8_t *h_payload, const u
     }
     const int rc = err.load();
     if (rc) {
-        if (ctx->workers[0]) set_error(ctx, rc, "pipelined decode: %s", shafa_cuda_last_error(ctx->workers[0]));
+        for (int i = 0; i < PIPE_MAX_WORKERS; i++)
+            if (ctx->workers[i]) cudaStreamSynchronize(ctx->workers[i]->stream);
+        set_error(ctx, rc, "pipelined decode: %s", err_text.c_str());
         return rc;
     }
     const uint64_t total = out_chain.base[ch.count];

@@ -678,7 +678,9 @@ int launch_sf_decode(shafa_cuda_ctx *ctx, const uint8_t *d_payload, const uint64
         hp[4 * nb + b] = nseq;
         out_off += h_n[b];
         nseq += (h_z[b] + DEC_SEQ_BYTES - 1) / DEC_SEQ_BYTES;
-        if (h_n[b] != 0 && h_z[b] == 0) return set_error(ctx, SHAFA_FILE_UNRECOGNIZABLE, "sf_decode: block %llu has symbols but an empty payload", (unsigned long long)b);
+        // A one-symbol block is written as "@0@" by module C and its .cod block holds 256 empty strings: which
+        // symbol it was is not in the files (the reference decoder dereferences NULL there, d.c:533-536).
+        if (h_n[b] != 0 && h_z[b] == 0) return set_error(ctx, SHAFA_FILE_UNRECOGNIZABLE, "sf_decode: block %llu has %llu symbols but an empty payload (one-symbol block: not decodable from .cod/.shaf)", (unsigned long long)b, (unsigned long long)h_n[b]);
     }
     hp[5 * nb] = nseq;
     if (nseq == 0) return SHAFA_SUCCESS;

@@ -39,7 +39,7 @@ k_sf_block_bits(const uint64_t *__restrict__ hist, const uint8_t *__restrict__ l
     const uint32_t b = blockIdx.x * 8 + warp_id();
     if (b >= nb) return;
     uint64_t bits = 0;
-    uint32_t fl = 0;
+    uint32_t fl = 0, present = 0, uncoded = 0, coded = 0;
 #pragma unroll
     for (int k = 0; k < 8; k++) {
         const int s = k * 32 + lane_id();
@@ -47,9 +47,18 @@ k_sf_block_bits(const uint64_t *__restrict__ hist, const uint8_t *__restrict__ l
         const uint32_t l = lens[(uint64_t)b * 256 + s];
         bits += h * l;
         if (l > (uint32_t)ENC_SHORT_MAX) fl |= 1u;
-        if (h != 0 && l == 0) fl |= 2u;
+        present += h != 0;
+        uncoded += (h != 0 && l == 0);
+        coded += l != 0;
     }
     bits = warp_sum64(bits);
+    present = __reduce_add_sync(FULL, present);
+    uncoded = __reduce_add_sync(FULL, uncoded);
+    coded = __reduce_add_sync(FULL, coded);
+    // A block with ONE distinct symbol gets the empty code (t.c:185: start == end appends no bit) and the
+    // reference packer then writes "@0@" with no payload (c.c:65-80): bits = 0 here, not an error.  Any other
+    // symbol that occurs without a code is a malformed .cod.
+    if (uncoded && !(present == 1 && coded == 0)) fl |= 2u;
     fl = __reduce_or_sync(FULL, fl);
     if (lane_id() == 0) {
         bits_out[b] = bits;

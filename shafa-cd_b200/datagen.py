@@ -97,5 +97,28 @@ def mixed4m(n: int, seed: int = 5) -> np.ndarray:
     return mixed(n, seed=seed, segment=4 * MIB)
 
 
+def mixed_tiled(n: int, seed: int = 5, segment: int = 64 * MIB) -> np.ndarray:
+    """C5 at its full 16 GiB: the same cycle of 64 MiB run-heavy / zipf / text / uniform segments as
+    `mixed`, but built from eight base segments (two per kind, seeds seed .. seed+7) so that the input
+    can be produced in seconds on the GPU box: segment i is base (i % 8) rotated by (i * 1000003) mod
+    `segment` bytes -- the same statistics per kind, different bytes in every block.  Segment 0 is the
+    unrotated run-heavy base, so block 0 selects R mode."""
+    gens = (runheavy, zipf, textlike, uniform)
+    bases = [gens[k % 4](segment, seed=seed + k) for k in range(8)]
+    out = np.empty(n, dtype=np.uint8)
+    i = 0
+    for lo in range(0, n, segment):
+        hi = min(n, lo + segment)
+        base = bases[i % 8]
+        r = (i * 1000003) % segment
+        m = hi - lo
+        first = min(m, segment - r)
+        out[lo:lo + first] = base[r:r + first]
+        if first < m:
+            out[lo + first:hi] = base[:m - first]
+        i += 1
+    return out
+
+
 GENERATORS = {"zipf": zipf, "textlike": textlike, "runheavy": runheavy, "uniform": uniform,
-              "mixed": mixed, "mixed4m": mixed4m}
+              "mixed": mixed, "mixed4m": mixed4m, "mixed_tiled": mixed_tiled}

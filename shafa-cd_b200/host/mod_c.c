@@ -38,6 +38,10 @@ _modules_error shafa_compress(char **const path)
         err = _FILE_UNRECOGNIZABLE;
         goto out;
     }
+    if (!block_count_plausible(nb, cod.size)) {
+        err = _FILE_UNRECOGNIZABLE;
+        goto out;
+    }
     if ((err = blob_read(*path, &sym))) goto out;
     g = gpu();
     if (!g) {
@@ -64,7 +68,7 @@ _modules_error shafa_compress(char **const path)
         }
         if ((err = cod_parse_fields(f, fl, len + b * 256, code + b * 256))) goto out;
         offsets[b + 1] = offsets[b] + sizes[b];
-        if (offsets[b + 1] > sym.size) { /* c.c:392 short read */
+        if (sizes[b] > sym.size || offsets[b + 1] > sym.size) { /* c.c:392 short read (and no wrap-around) */
             err = _FILE_STREAM_FAILED;
             goto out;
         }

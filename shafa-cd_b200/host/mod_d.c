@@ -98,7 +98,7 @@ _modules_error rle_decompress(char **const path)
         err = _FILE_STREAM_FAILED;
         goto out;
     }
-    if (mode != 'R') { /* d.c:270 */
+    if (mode != 'R' || !block_count_plausible(nb, freq.size)) { /* d.c:270 */
         err = _FILE_UNRECOGNIZABLE;
         goto out;
     }
@@ -119,7 +119,7 @@ _modules_error rle_decompress(char **const path)
         }
         cur_field(&c, &f, &fl);
         offsets[b + 1] = offsets[b] + sizes[b];
-        if (offsets[b + 1] > rle.size) { /* d.c:84 short read */
+        if (sizes[b] > rle.size || offsets[b + 1] > rle.size) { /* d.c:84 short read (and no wrap-around) */
             err = _FILE_STREAM_FAILED;
             goto out;
         }
@@ -195,7 +195,7 @@ _modules_error shafa_decompress(char **const path, const bool decompress_rle)
         err = _FILE_STREAM_FAILED;
         goto out;
     }
-    if (!((mode == 'N' && !decompress_rle) || mode == 'R')) { /* d.c:678 */
+    if (!((mode == 'N' && !decompress_rle) || mode == 'R') || !block_count_plausible(nb, cod.size)) { /* d.c:678 */
         err = _FILE_UNRECOGNIZABLE;
         goto out;
     }
@@ -229,6 +229,12 @@ _modules_error shafa_decompress(char **const path, const bool decompress_rle)
             goto out;
         }
         if ((err = cod_parse_fields(f, fl, len + b * 256, code + b * 256))) goto out;
+        /* a block decodes to at most 64 MiB + 1 KiB of symbols in any file module C can write (2n + 3 of a 64 MiB block
+         * is the hard bound); anything larger is a forged header -- and would wrap the sums below */
+        if (n[b] > 2ull * MIB_64 + 3) {
+            err = _FILE_UNRECOGNIZABLE;
+            goto out;
+        }
         offsets[b + 1] = offsets[b] + n[b];
     }
     g = gpu();

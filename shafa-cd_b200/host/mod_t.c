@@ -66,6 +66,10 @@ _modules_error get_shafa_codes(const char *path)
         err = _FILE_UNRECOGNIZABLE;
         goto out;
     }
+    if (!block_count_plausible(nb, in.size)) {
+        err = _FILE_UNRECOGNIZABLE;
+        goto out;
+    }
     if (!g) {
         err = _THREAD_CREATION_FAILED;
         goto out;

@@ -4,55 +4,6 @@
 #include <string.h>
 #include <time.h>
 
-/* ---- extensions ---------------------------------------------------------------- */
-
-bool check_ext(const char *path, const char *ext)
-{
-    if (!path) return false;
-    const size_t lp = strlen(path), le = strlen(ext);
-    return lp >= le && strcmp(path + (lp - le), ext) == 0;
-}
-
-char *add_ext(const char *path, const char *ext)
-{
-    const size_t lp = strlen(path), le = strlen(ext);
-    char *out = malloc(lp + le + 1);
-    if (out) {
-        memcpy(out, path, lp);
-        memcpy(out + lp, ext, le + 1);
-    }
-    return out;
-}
-
-char *rm_ext(const char *path)
-{
-    const char *dot = strrchr(path, '.');
-    const size_t keep = dot ? (size_t)(dot - path) : strlen(path);
-    char *out = malloc(keep + 1);
-    if (out) {
-        memcpy(out, path, keep);
-        out[keep] = '\0';
-    }
-    return out;
-}
-
-/* ---- errors ------------------------------------------------------------------------ */
-
-const char *error_msg(int num)
-{
-    switch (num) {
-    case _SUCCESS: return "No error\n";
-    case _LACK_OF_MEMORY: return "Not enough memory for allocation\n";
-    case _FILE_INACCESSIBLE: return "File can't be accessed. Either lack of permissions or file doesn't exist\n";
-    case _FILE_UNRECOGNIZABLE: return "File not recognized\n";
-    case _FILE_STREAM_FAILED: return "Can't communicate properly with file's stream\n";
-    case _FILE_TOO_SMALL: return "File too small for decompression\n";
-    case _THREAD_CREATION_FAILED: return "Thread couldn't be created\n";
-    case _THREAD_TERMINATION_FAILED: return "Thread didn't terminate properly\n";
-    default: return "Unknown error";
-    }
-}
-
 /* ---- GPU context ------------------------------------------------------------------- */
 
 static shafa_cuda_ctx *g_ctx;
@@ -199,6 +150,8 @@ _modules_error cod_parse_fields(const uint8_t *p, size_t n, uint8_t *len, uint64
     }
     return p == end ? _SUCCESS : _FILE_UNRECOGNIZABLE; /* c.c:174-177 */
 }
+
+bool block_count_plausible(uint64_t nb, uint64_t container_bytes) { return nb <= container_bytes / 258u; }
 
 double now_ms(void)
 {

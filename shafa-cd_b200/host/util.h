@@ -54,6 +54,11 @@ bool cur_field(cursor *c, const uint8_t **start, size_t *len);
  * Codes longer than 64 bits are legal in the format but not supported: _FILE_UNRECOGNIZABLE. */
 _modules_error cod_parse_fields(const uint8_t *p, size_t n, uint8_t *len, uint64_t *code);
 
+/* Block counts come from untrusted "@N@<count>" headers and size every table that follows.  A .freq / .cod
+ * block is at least "@d@" plus 255 ';' = 258 bytes, so a count above file_size / 258 is a lie
+ * (_FILE_UNRECOGNIZABLE) -- checked BEFORE anything is allocated from it. */
+bool block_count_plausible(uint64_t nb, uint64_t container_bytes);
+
 double now_ms(void);
 
 #endif

@@ -55,3 +55,9 @@ def shafa(pkg):
 
 def small_cases():
     return sorted(p.name for p in GOLDEN.iterdir() if p.is_dir() and (p / "input.bin").exists())
+
+
+def encode_only_cases():
+    """Reference fixtures whose input has a one-symbol block: F, T, C only (the reference decoder crashes on them)."""
+    d = GOLDEN / "encode_only"
+    return sorted(p.name for p in d.iterdir() if (p / "input.bin").exists()) if d.is_dir() else []

@@ -89,6 +89,43 @@ BIG = [
 ]
 
 
+def one_symbol_tail() -> np.ndarray:
+    """size % block == 1 in N mode: the last block is one byte."""
+    return datagen.zipf(2 * 65536 + 1, seed=6)
+
+
+def one_symbol_homogeneous_last_block() -> np.ndarray:
+    """N mode, last block = 1000 copies of one byte (block 0 decides N for the whole file)."""
+    a = datagen.uniform(2 * 65536 + 1000, seed=8)
+    a[2 * 65536:] = 77
+    return a
+
+
+def one_symbol_rle_last_block() -> np.ndarray:
+    """R mode (-c r), last block = 3 identical non-zero bytes: three literals of one symbol in the .rle block."""
+    a = datagen.textlike(65536 + 3, seed=9)
+    a[65536:] = 66
+    return a
+
+
+# Inputs with a block that holds ONE distinct symbol: T gives it the empty code (t.c:185), C writes "@0@" and
+# the reference decoder then crashes (d.c:533-536), so these pin F, T and C only (SURVEY.md 2.2-1).
+ENCODE_ONLY = [
+    ("tail_1byte", one_symbol_tail, []),
+    ("homog_last_block", one_symbol_homogeneous_last_block, []),
+    ("rle_last_3same", one_symbol_rle_last_block, ["-c", "r"]),
+]
+
+
+def encode_only(workdir: Path, fflags):
+    run(["input.bin", "-m", "f"] + fflags, workdir)
+    rle = (workdir / "input.bin.rle").exists()
+    base = "input.bin.rle" if rle else "input.bin"
+    run([base + ".freq", "-m", "t"], workdir)
+    run([base, "-m", "c"], workdir)
+    return {p.name[len("input.bin"):]: p.read_bytes() for p in sorted(workdir.iterdir()) if p.name != "input.bin"}
+
+
 def pipeline(workdir: Path, fflags, bflag):
     """F -> T -> C -> D with the reference; returns {suffix: bytes}."""
     b = ["-b", bflag] if bflag else []
@@ -184,7 +221,7 @@ def t_cases() -> bytes:
 def main():
     if not REF.exists():
         subprocess.check_call(["make", "-C", str(ROOT / "oracle"), "_ref"])
-    for name, gen, fflags in SMALL:
+    for name, gen, fflags in ([] if "--encode-only" in sys.argv else SMALL):
         d = OUT / name
         if d.exists():
             shutil.rmtree(d)
@@ -199,6 +236,24 @@ def main():
             (d / ("input.bin" + suffix)).write_bytes(blob)
         (d / "flags.json").write_text(json.dumps({"fflags": fflags, "block": "default"}))
         print(name, data.size, sorted(arte))
+
+    for name, gen, fflags in ENCODE_ONLY:
+        d = OUT / "encode_only" / name
+        if d.exists():
+            shutil.rmtree(d)
+        d.mkdir(parents=True)
+        data = np.ascontiguousarray(gen(), dtype=np.uint8)
+        with tempfile.TemporaryDirectory() as td:
+            td = Path(td)
+            (td / "input.bin").write_bytes(data.tobytes())
+            arte = encode_only(td, fflags)
+        (d / "input.bin").write_bytes(data.tobytes())
+        for suffix, blob in arte.items():
+            (d / ("input.bin" + suffix)).write_bytes(blob)
+        (d / "flags.json").write_text(json.dumps({"fflags": fflags, "block": "default"}))
+        print("encode_only", name, data.size, sorted(arte))
+    if "--encode-only" in sys.argv:
+        return
 
     big = {}
     for name, gname, n, seed, bflag, fflags in BIG:

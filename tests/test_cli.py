@@ -10,7 +10,7 @@ from pathlib import Path
 import numpy as np
 import pytest
 
-from conftest import GOLDEN, ROOT, small_cases
+from conftest import GOLDEN, ROOT, encode_only_cases, small_cases
 
 BIN = ROOT / "shafa-cd_b200" / "shafa"
 
@@ -129,3 +129,63 @@ def test_cross_decode_with_reference_binary(pkg, orc, tmp_path):
     assert run(["x.rle.shaf", "-m", "d"], theirs).returncode == 0                 # we decode the reference's files
     assert (ours / "x").read_bytes() == data.tobytes() and (theirs / "x").read_bytes() == data.tobytes()
     _ = shutil
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", encode_only_cases())
+def test_cli_one_symbol_block(case, tmp_path):
+    """`shafa x` on a file whose last block holds one distinct symbol exits 0 and writes the reference's bytes."""
+    d = GOLDEN / "encode_only" / case
+    flags = json.loads((d / "flags.json").read_text())
+    (tmp_path / "input.bin").write_bytes((d / "input.bin").read_bytes())
+    assert run(["input.bin"] + flags["fflags"], tmp_path).returncode == 0      # F, T, C in one invocation
+    expected = sorted(p.name for p in d.iterdir() if p.name != "flags.json")
+    assert sorted(p.name for p in tmp_path.iterdir()) == expected
+    for name in expected:
+        assert (tmp_path / name).read_bytes() == (d / name).read_bytes(), name
+    shaf = [n for n in expected if n.endswith(".shaf")][0]
+    assert run([shaf, "-m", "d"], tmp_path).returncode == 1                     # refused, not a crash
+
+
+REFDRIVER = ROOT / "oracle" / "_ref" / "shafa_refdriver"
+
+
+def test_reference_driver_links_against_our_modules():
+    """the reference's unmodified shafa.c + extensions.c + errors.c link against
+    host/mod_*.c + util.c + ref_shim.c + libshafa_cuda (CPU-only check: it links and parses options)."""
+    if not Path("/root/reference/src/shafa.c").exists():
+        pytest.skip("reference sources not on this box (the binary is prebuilt in the build container)")
+    subprocess.check_call(["make", "-C", str(ROOT / "oracle"), "refdriver"], stdout=subprocess.DEVNULL)
+    assert REFDRIVER.exists()
+    r = subprocess.run([str(REFDRIVER)], capture_output=True, timeout=60)
+    assert r.returncode == 1 and b"No file input" in r.stderr                    # shafa.c:269-272
+    r = subprocess.run([str(REFDRIVER), "x", "-m", "q"], capture_output=True, timeout=60)
+    assert r.returncode == 1 and b"Wrong Options" in r.stderr                    # shafa.c:277-280
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", small_cases())
+def test_reference_driver_binding_matches_reference_files(case, tmp_path):
+    """The golden cases through the REFERENCE's driver bound to our modules."""
+    if not REFDRIVER.exists():
+        pytest.skip("oracle/_ref/shafa_refdriver not present on this box")
+    d = GOLDEN / case
+    flags = json.loads((d / "flags.json").read_text())
+    original = (d / "input.bin").read_bytes()
+    (tmp_path / "input.bin").write_bytes(original)
+
+    def ref(args):
+        return subprocess.run([str(REFDRIVER)] + args, cwd=tmp_path, capture_output=True, timeout=600)
+
+    assert ref(["input.bin", "-m", "f", "-m", "t", "-m", "c"] + flags["fflags"]).returncode == 0
+    rle = (tmp_path / "input.bin.rle").exists()
+    if rle and (tmp_path / "input.bin.freq").exists():
+        assert ref(["input.bin.freq", "-m", "t"]).returncode == 0
+    expected = sorted(p.name for p in d.iterdir() if p.name != "flags.json")
+    assert sorted(p.name for p in tmp_path.iterdir()) == expected
+    for name in expected:
+        assert (tmp_path / name).read_bytes() == (d / name).read_bytes(), name
+    (tmp_path / "input.bin").unlink()
+    shaf = "input.bin.rle.shaf" if rle else "input.bin.shaf"
+    assert ref([shaf, "--no-multithread"]).returncode == 0                       # default -m d; the flag is accepted
+    assert (tmp_path / "input.bin").read_bytes() == original

@@ -7,7 +7,7 @@ import json
 import numpy as np
 import pytest
 
-from conftest import GOLDEN, small_cases
+from conftest import GOLDEN, encode_only_cases, small_cases
 
 pytestmark = pytest.mark.gpu
 
@@ -361,3 +361,24 @@ def test_pipeline_big_golden(shafa, orc, pkg):
         if f["rle_mode"] and "f" in fflags[1::2]:
             arte[".freq"] = f["freq"]
         _check_pipeline(shafa, orc, data, BLOCKS[spec["block"]], fflags, lambda s, arte=arte: arte.get(s))
+
+
+@pytest.mark.parametrize("case", encode_only_cases())
+def test_one_symbol_block_encode(shafa, pkg, case):
+    """One distinct symbol in a block: z = 0 and an empty payload, byte-identical to the reference's files;
+    decoding such a block is refused (the symbol is not in the files; the reference decoder crashes, d.c:533-536)."""
+    d = GOLDEN / "encode_only" / case
+    flags = json.loads((d / "flags.json").read_text())
+    data = np.frombuffer((d / "input.bin").read_bytes(), dtype=np.uint8)
+    enc = shafa.encode(data, 65536, force_rle="r" in flags["fflags"][1::2])
+    base = "input.bin.rle" if enc.rle_mode else "input.bin"
+    assert enc.rle_mode == (d / "input.bin.rle").exists()
+    if enc.rle_mode:
+        assert_same(enc.rle_bytes(), (d / "input.bin.rle").read_bytes(), ".rle")
+    assert enc.freq_text() == (d / (base + ".freq")).read_bytes()
+    assert enc.cod_text() == (d / (base + ".cod")).read_bytes()
+    assert_same(enc.shaf_bytes(), (d / (base + ".shaf")).read_bytes(), ".shaf")
+    assert int(enc.z[-1]) == 0 and int(enc.code_len[-1].max()) == 0
+    with pytest.raises(pkg.ShafaError) as e:
+        shafa.decode(enc)
+    assert e.value.code == 4

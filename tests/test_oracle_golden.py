@@ -8,7 +8,7 @@ import json
 import numpy as np
 import pytest
 
-from conftest import GOLDEN, small_cases
+from conftest import GOLDEN, encode_only_cases, small_cases
 
 BLOCKS = {"default": 65536, "K": 655360, "m": 8388608, "M": 67108864}
 
@@ -107,3 +107,23 @@ def test_block_primitives_roundtrip(orc, pkg):
         for s, c in enumerate(codes):
             assert ln[s] == len(c) and (not c or int(c, 2) == int(cd[s]))
         assert mx == max(len(c) for c in codes)
+
+
+@pytest.mark.parametrize("case", encode_only_cases())
+def test_one_symbol_block_encode(orc, case):
+    """A block with one distinct symbol: empty code (t.c:185), "@0@" in the .shaf (c.c:65-80)."""
+    d = GOLDEN / "encode_only" / case
+    flags = json.loads((d / "flags.json").read_text())
+    data = np.frombuffer((d / "input.bin").read_bytes(), dtype=np.uint8)
+    f = orc.module_f(data, 65536, force_rle="r" in flags["fflags"][1::2], force_freq=False)
+    base = "input.bin.rle" if f["rle_mode"] else "input.bin"
+    assert f["rle_mode"] == (d / "input.bin.rle").exists()
+    if f["rle_mode"]:
+        assert f["rle"] == (d / "input.bin.rle").read_bytes()
+    freq = f["rle_freq"] if f["rle_mode"] else f["freq"]
+    assert freq == (d / (base + ".freq")).read_bytes()
+    cod = orc.module_t(freq)
+    assert cod == (d / (base + ".cod")).read_bytes()
+    shaf = orc.module_c(f["rle"] if f["rle_mode"] else data.tobytes(), cod)
+    assert shaf == (d / (base + ".shaf")).read_bytes()
+    assert b"@0@" in shaf[-8:]
