@@ -222,7 +222,7 @@ class ClockSampler:
 
 ALGO_BYTES_DOC = {
     "rle_encode": "N + R", "rle_encode_sizes": "n0 (block-0 probe)", "histogram": "S", "sf_encode": "S + Z",
-    "dec_sync": "Z", "dec_write": "Z + S", "rle_decode": "R + N",
+    "dec_fused": "Z + S", "dec_sync": "Z", "dec_write": "Z + S", "rle_decode": "R + N",
 }
 
 
@@ -390,8 +390,8 @@ def run_ours(args):
     if rank == 0:
         peak, peak_src = measured_peak_hbm()
         R = info["R"]
-        algo = {"rle_encode": n + R, "rle_encode_sizes": min(n, bs), "histogram": S, "sf_encode": S + Z, "dec_sync": Z,
-                "dec_write": Z + S, "rle_decode": R + n}
+        algo = {"rle_encode": n + R, "rle_encode_sizes": min(n, bs), "histogram": S, "sf_encode": S + Z, "dec_fused": Z + S,
+                "dec_sync": Z, "dec_write": Z + S, "rle_decode": R + n}
         kernels = {}
         for name, st in kstats.items():
             per_step_ms = st["ms"] / args.steps

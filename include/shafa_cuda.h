@@ -184,7 +184,7 @@ typedef struct {
     uint64_t payload_total;
     uint64_t *payload_offsets;  /* [B]                                            */
     uint64_t *z;                /* [B] payload bytes per block (.shaf "@z@")      */
-    int owns_rle, owns_payload; /* set by the library                             */
+    int owns_rle, owns_payload; /* set by the library (1: pinned, 2: malloc'd)    */
 } shafa_cuda_encoded;
 
 /* F -> T -> C for one host buffer (H2D, kernels, D2H inside). */
@@ -211,6 +211,35 @@ int shafa_cuda_decode_host(shafa_cuda_ctx *ctx, const uint8_t *h_payload,
 int shafa_cuda_rle_decode_host(shafa_cuda_ctx *ctx, const uint8_t *h_rle, const uint64_t *h_offsets,
                                uint64_t n_blocks, uint8_t *h_out, uint64_t out_capacity,
                                uint64_t *h_out_size, uint64_t *h_final_sizes);
+
+/* ---- one file sharded over N GPUs by one host process ----------------------------
+ *
+ * Replaces the reference's "one pthread per block, writes serialised by a join chain"
+ * (utils/multithread.c:70-87,126-194) across GPUs: the blocks of ONE file are cut into chunks of
+ * whole blocks, every chunk goes to whichever worker stream of whichever device is free, and the
+ * results land compacted, in block order, in the caller's host buffers.  No collective: blocks are
+ * independent, the only file-wide scalar is block 0's R/N decision (f.c:246-258), taken on
+ * devices[0].  Outputs are byte-identical to the single-device calls for any device list. */
+typedef struct shafa_cuda_multi shafa_cuda_multi;
+int shafa_cuda_multi_create(const int *devices, int n_devices, shafa_cuda_multi **out);
+int shafa_cuda_multi_destroy(shafa_cuda_multi *m);
+int shafa_cuda_multi_device_count(const shafa_cuda_multi *m);
+/* context i of the set (borrowed: e.g. for shafa_cuda_sf_build_codes on small tables) */
+shafa_cuda_ctx *shafa_cuda_multi_ctx(shafa_cuda_multi *m, int i);
+const char *shafa_cuda_multi_last_error(const shafa_cuda_multi *m);
+uint64_t shafa_cuda_multi_launch_count(const shafa_cuda_multi *m);
+/* as shafa_cuda_encode_host.  out->rle / out->payload may be preset (pinned memory from
+ * shafa_cuda_host_alloc is pinned for every device); otherwise pageable buffers are allocated here
+ * (owns_* = 2: released with free() by shafa_cuda_encoded_free). */
+int shafa_cuda_encode_host_multi(shafa_cuda_multi *m, const uint8_t *h_in, uint64_t n, uint64_t block_size, int force_rle,
+                                 int force_freq, shafa_cuda_encoded *out);
+/* as shafa_cuda_decode_host / shafa_cuda_rle_decode_host */
+int shafa_cuda_decode_host_multi(shafa_cuda_multi *m, const uint8_t *h_payload, const uint64_t *h_payload_offsets,
+                                 const uint64_t *h_z, const uint64_t *h_n, uint64_t n_blocks, const uint8_t *h_len,
+                                 const uint64_t *h_code, int rle_expand, uint8_t *h_out, uint64_t out_capacity,
+                                 uint64_t *h_out_size, uint64_t *h_final_sizes);
+int shafa_cuda_rle_decode_host_multi(shafa_cuda_multi *m, const uint8_t *h_rle, const uint64_t *h_offsets, uint64_t n_blocks,
+                                     uint8_t *h_out, uint64_t out_capacity, uint64_t *h_out_size, uint64_t *h_final_sizes);
 
 #ifdef __cplusplus
 }

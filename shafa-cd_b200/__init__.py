@@ -14,6 +14,7 @@ from .binding import (  # noqa: F401
     Encoded,
     Shafa,
     ShafaError,
+    ShafaMulti,
     cod_text,
     declared_symbols,
     freq_text,

@@ -102,6 +102,18 @@ def load_library() -> C.CDLL:
     L.shafa_cuda_encoded_free.argtypes = [C.POINTER(EncodedC)]
     L.shafa_cuda_decode_host.argtypes = [vp, vp, vp, vp, vp, u64, vp, vp, C.c_int, vp, u64, u64p, vp]
     L.shafa_cuda_rle_decode_host.argtypes = [vp, vp, vp, u64, vp, u64, u64p, vp]
+    L.shafa_cuda_multi_create.argtypes = [C.POINTER(C.c_int), C.c_int, C.POINTER(vp)]
+    L.shafa_cuda_multi_destroy.argtypes = [vp]
+    L.shafa_cuda_multi_device_count.argtypes = [vp]
+    L.shafa_cuda_multi_ctx.argtypes = [vp, C.c_int]
+    L.shafa_cuda_multi_ctx.restype = vp
+    L.shafa_cuda_multi_last_error.argtypes = [vp]
+    L.shafa_cuda_multi_last_error.restype = C.c_char_p
+    L.shafa_cuda_multi_launch_count.argtypes = [vp]
+    L.shafa_cuda_multi_launch_count.restype = u64
+    L.shafa_cuda_encode_host_multi.argtypes = [vp, vp, u64, u64, C.c_int, C.c_int, C.POINTER(EncodedC)]
+    L.shafa_cuda_decode_host_multi.argtypes = [vp, vp, vp, vp, vp, u64, vp, vp, C.c_int, vp, u64, u64p, vp]
+    L.shafa_cuda_rle_decode_host_multi.argtypes = [vp, vp, vp, u64, vp, u64, u64p, vp]
     _ = u64p
     _lib = L
     return L
@@ -480,4 +492,92 @@ class Shafa:
         size = C.c_uint64(0)
         self._check(self.lib.shafa_cuda_rle_decode_host(self.ctx, rle.ctypes.data, offsets.ctypes.data, len(offsets) - 1,
                                                        out.ctypes.data, out.nbytes, C.byref(size), fin.ctypes.data))
+        return out[: size.value], fin
+
+
+class ShafaMulti:
+    """ONE file sharded over several GPUs by this one process (shafa_cuda_*_multi): chunks of whole
+    blocks go to whichever device is free, results land in block order in host buffers.  No collective.  The same
+    device may be listed more than once (useful on a one-GPU box: the sharding logic is the same)."""
+
+    def __init__(self, devices):
+        self.lib = load_library()
+        devs = (C.c_int * len(devices))(*[int(d) for d in devices])
+        h = C.c_void_p()
+        rc = self.lib.shafa_cuda_multi_create(devs, len(devices), C.byref(h))
+        if rc:
+            raise ShafaError(rc, f"shafa_cuda_multi_create({list(devices)})")
+        self.h = h
+        self.devices = list(devices)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.shafa_cuda_multi_destroy(self.h)
+            self.h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def last_error(self) -> str:
+        return self.lib.shafa_cuda_multi_last_error(self.h).decode(errors="replace")
+
+    def launch_count(self) -> int:
+        return int(self.lib.shafa_cuda_multi_launch_count(self.h))
+
+    def _check(self, rc: int):
+        if rc:
+            raise ShafaError(rc, self.last_error())
+
+    def encode_raw(self, data, block_size: int, force_rle=False, force_freq=False, rle_buf=None, payload_buf=None) -> EncodedC:
+        a = _u8(data)
+        c = EncodedC()
+        if rle_buf is not None:
+            c.rle = C.cast(rle_buf.ctypes.data, C.POINTER(C.c_uint8))
+            c.rle_capacity = rle_buf.nbytes
+        if payload_buf is not None:
+            c.payload = C.cast(payload_buf.ctypes.data, C.POINTER(C.c_uint8))
+            c.payload_capacity = payload_buf.nbytes
+        self._check(self.lib.shafa_cuda_encode_host_multi(self.h, a.ctypes.data, a.size, block_size, int(force_rle), int(force_freq), C.byref(c)))
+        return c
+
+    def encoded_free(self, c: EncodedC):
+        self.lib.shafa_cuda_encoded_free(C.byref(c))
+
+    def encode(self, data, block_size: int, force_rle=False, force_freq=False) -> Encoded:
+        c = self.encode_raw(data, block_size, force_rle, force_freq)
+        try:
+            return Encoded(c)
+        finally:
+            self.encoded_free(c)
+
+    def decode_tables(self, payload, payload_offsets, z, n, code_len, code_bits, rle_expand: bool, out_capacity: int,
+                      out: np.ndarray | None = None):
+        payload, code_len = _u8(payload), _u8(code_len)
+        payload_offsets, z, n, code_bits = _u64(payload_offsets), _u64(z), _u64(n), _u64(code_bits)
+        if out is None:
+            out = np.empty(out_capacity, dtype=np.uint8)
+        fin = np.zeros(len(n), dtype=np.uint64)
+        size = C.c_uint64(0)
+        self._check(self.lib.shafa_cuda_decode_host_multi(self.h, payload.ctypes.data, payload_offsets.ctypes.data, z.ctypes.data, n.ctypes.data,
+                                                         len(n), code_len.ctypes.data, code_bits.ctypes.data, int(rle_expand),
+                                                         out.ctypes.data, out.nbytes, C.byref(size), fin.ctypes.data))
+        return out[: size.value], fin
+
+    def decode(self, enc: Encoded, rle_expand: bool | None = None) -> np.ndarray:
+        expand = enc.rle_mode if rle_expand is None else (rle_expand and enc.rle_mode)
+        cap = enc.n if expand else int(enc.sym_sizes.sum())
+        out, _ = self.decode_tables(enc.payload, enc.payload_offsets, enc.z, enc.sym_sizes, enc.code_len, enc.code_bits, expand, cap + 64)
+        return out
+
+    def rle_decode_host(self, rle, offsets, out_capacity: int, out: np.ndarray | None = None):
+        rle, offsets = _u8(rle), _u64(offsets)
+        if out is None:
+            out = np.empty(out_capacity, dtype=np.uint8)
+        fin = np.zeros(len(offsets) - 1, dtype=np.uint64)
+        size = C.c_uint64(0)
+        self._check(self.lib.shafa_cuda_rle_decode_host_multi(self.h, rle.ctypes.data, offsets.ctypes.data, len(offsets) - 1,
+                                                             out.ctypes.data, out.nbytes, C.byref(size), fin.ctypes.data))
         return out[: size.value], fin

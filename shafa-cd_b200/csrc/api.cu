@@ -170,7 +170,9 @@ static int finish_with_err(shafa_cuda_ctx *ctx, uint32_t *d_err, const char *wha
         return SHAFA_THREAD_TERMINATION_FAILED;
     }
     const uint32_t bits = *h;
+    ctx->last_err_bits = bits;
     if (!bits) return SHAFA_SUCCESS;
+    if (bits & ERR_TIMEOUT) return set_error(ctx, SHAFA_THREAD_TERMINATION_FAILED, "%s: a device-side wait timed out (error bits 0x%x)", what, bits);
     if (bits & ERR_CAPACITY) return set_error(ctx, SHAFA_LACK_OF_MEMORY, "%s: output buffer too small", what);
     return set_error(ctx, SHAFA_FILE_UNRECOGNIZABLE, "%s: malformed input (error bits 0x%x)", what, bits);
 }
@@ -265,7 +267,7 @@ const char *shafa_cuda_last_error(const shafa_cuda_ctx *ctx) { return ctx ? ctx-
 void *shafa_cuda_host_alloc(size_t bytes)
 {
     void *p = nullptr;
-    if (cudaMallocHost(&p, bytes ? bytes : 16) != cudaSuccess) {
+    if (cudaHostAlloc(&p, bytes ? bytes : 16, cudaHostAllocPortable) != cudaSuccess) {  // portable: pinned for every device
         cudaGetLastError();
         return nullptr;
     }
@@ -435,9 +437,19 @@ int shafa_cuda_sf_decode_blocks(shafa_cuda_ctx *ctx, const uint8_t *d_payload, c
     uint32_t *d_err;
     int rc = err_reset(ctx, &d_err);
     if (rc) return rc;
-    rc = launch_sf_decode(ctx, d_payload, h_payload_offsets, h_z, h_n, nb, d_len, d_code, d_sym, d_err);
+    rc = launch_sf_decode(ctx, d_payload, h_payload_offsets, h_z, h_n, nb, d_len, d_code, d_sym, d_err, false);
     if (rc) return rc;
-    return finish_with_err(ctx, d_err, "sf_decode_blocks");
+    rc = finish_with_err(ctx, d_err, "sf_decode_blocks");
+    if (rc == SHAFA_FILE_UNRECOGNIZABLE && (ctx->last_err_bits & ERR_SPECULATION)) {
+        // The single-pass decoder guessed that a sequence's end does not depend on where its first code starts,
+        // checked the guess, and found it wrong somewhere (codes that do not self-synchronise): its output is not
+        // trusted.  Decode again with the exact path.
+        if ((rc = err_reset(ctx, &d_err))) return rc;
+        rc = launch_sf_decode(ctx, d_payload, h_payload_offsets, h_z, h_n, nb, d_len, d_code, d_sym, d_err, true);
+        if (rc) return rc;
+        rc = finish_with_err(ctx, d_err, "sf_decode_blocks (exact path)");
+    }
+    return rc;
 }
 
 int shafa_cuda_rle_decode_blocks(shafa_cuda_ctx *ctx, const uint8_t *d_rle, const uint64_t *h_offsets, uint64_t nb,
@@ -467,8 +479,14 @@ void shafa_cuda_encoded_free(shafa_cuda_encoded *e)
     free(e->code_bits);
     free(e->payload_offsets);
     free(e->z);
-    if (e->owns_rle && e->rle) cudaFreeHost(e->rle);
-    if (e->owns_payload && e->payload) cudaFreeHost(e->payload);
+    if (e->owns_rle == 2)
+        free(e->rle);
+    else if (e->owns_rle && e->rle)
+        cudaFreeHost(e->rle);
+    if (e->owns_payload == 2)
+        free(e->payload);
+    else if (e->owns_payload && e->payload)
+        cudaFreeHost(e->payload);
     memset(e, 0, sizeof *e);
 }
 
@@ -618,7 +636,7 @@ int shafa_cuda_encode_host(shafa_cuda_ctx *ctx, const uint8_t *h_in, uint64_t n,
 {
     if (out && out->payload && out->payload_capacity && out->rle && out->rle_capacity && n >= (64ull << 20) && ctx &&
         ctx->stream == ctx->own_stream)
-        return encode_host_pipelined(ctx, h_in, n, block_size, force_rle, force_freq, -1, out);
+        return encode_host_pipelined(&ctx, 1, h_in, n, block_size, force_rle, force_freq, -1, out);
     return encode_host_impl(ctx, h_in, n, block_size, force_rle, force_freq, -1, out);
 }
 
@@ -627,7 +645,7 @@ int shafa_cuda_encode_shard_host(shafa_cuda_ctx *ctx, const uint8_t *h_in, uint6
 {
     if (out && out->payload && out->payload_capacity && out->rle && out->rle_capacity && n >= (64ull << 20) && ctx &&
         ctx->stream == ctx->own_stream)
-        return encode_host_pipelined(ctx, h_in, n, block_size, 0, force_freq, rle_mode ? 1 : 0, out);
+        return encode_host_pipelined(&ctx, 1, h_in, n, block_size, 0, force_freq, rle_mode ? 1 : 0, out);
     return encode_host_impl(ctx, h_in, n, block_size, 0, force_freq, rle_mode ? 1 : 0, out);
 }
 
@@ -670,7 +688,7 @@ int shafa_cuda_decode_host(shafa_cuda_ctx *ctx, const uint8_t *h_payload, const 
         uint64_t sym_total = 0;
         for (uint64_t b = 0; b < nb; b++) sym_total += h_n[b];
         if (nb >= 8 && sym_total >= (64ull << 20) && ctx->stream == ctx->own_stream)
-            return decode_host_pipelined(ctx, h_payload, h_payload_offsets, h_z, h_n, nb, h_len, h_code, rle_expand, h_out,
+            return decode_host_pipelined(&ctx, 1, h_payload, h_payload_offsets, h_z, h_n, nb, h_len, h_code, nullptr, rle_expand, h_out,
                                          out_capacity, h_out_size, h_final_sizes);
     }
     uint64_t ptotal = 0, stotal = 0;

@@ -80,6 +80,17 @@ __device__ __forceinline__ uint64_t desc_load(const uint64_t *p)
     return v;
 }
 
+__device__ __forceinline__ void st_relaxed_u32(uint32_t *p, uint32_t v)
+{
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t *p)
+{
+    uint32_t v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
 // ---- warp primitives ------------------------------------------------------------
 __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v)
 {

@@ -651,4 +651,183 @@ SHAFA_HD uint32_t dec_lut3_entry(const uint16_t *lut1, uint32_t e)
     return (l0 << 24) | (1u << 16) | (e0 >> 8);
 }
 
+
+// =============================================================================
+// Fused single-pass decoder (sf_decode_fused.cu): decode ONCE, speculatively, and keep the symbols.
+//
+// A thread decodes its 128-bit sub-sequence from bit 0 before it knows where the first code really
+// starts, and keeps what it decoded as a list of RECORDS (one per table lookup: one or two symbols and
+// the bit position they start at).  When the true start s arrives (the predecessor's end) the thread
+// walks single codes from s only until it lands on a position where a record starts: from there on
+// the speculative path IS the true path (decoding from a given bit is deterministic), so the final
+// symbols are a short HEAD (the codes walked from s) followed by the tail of the record list.  A
+// prefix code re-synchronises within a few codes, so every payload bit is decoded about 1.2 times
+// instead of once per synchronisation round plus once more for the output.
+//
+//   pair-LUT entry (12-bit window -> its first one or two whole codes):
+//     [7:0] sym0  [15:8] sym1  [22:16] bits of the codes taken  [27:24] bits of the first code  [29:28] how many (1|2)
+//     0 = the first code is longer than 12 bits (or the window is no code): sorted search
+//   record = entry with byte 2 replaced by the start position (< 128) inside the sub-sequence
+// =============================================================================
+constexpr int DECF_CAP = 24;    // records per sub-sequence (more than ~48 symbols in 128 bits overflow into the direct path)
+constexpr int DECF_HEAD = 16;   // head symbols kept per sub-sequence before the list is rebuilt from the new start
+
+SHAFA_HD uint32_t decf_total(uint32_t e) { return (e >> 16) & 0x7Fu; }
+SHAFA_HD uint32_t decf_len0(uint32_t e) { return (e >> 24) & 0xFu; }
+SHAFA_HD uint32_t decf_n(uint32_t e) { return e >> 28; }
+SHAFA_HD uint32_t decf_pos(uint32_t rec) { return (rec >> 16) & 0xFFu; }
+
+// pair-LUT entry for the 12-bit window value e, from lut1 ((sym << 8) | len, 0xFF = long, 0 = none)
+SHAFA_HD uint32_t decf_entry(const uint16_t *lut1, uint32_t e)
+{
+    const uint32_t e0 = lut1[e];
+    const uint32_t l0 = e0 & 0xFFu;
+    if (l0 - 1u >= (uint32_t)DEC_LUT_BITS) return 0;
+    const uint32_t e1 = lut1[(e << l0) & (DEC_LUT_SIZE - 1)];
+    const uint32_t l1 = e1 & 0xFFu;
+    if (l1 - 1u < (uint32_t)DEC_LUT_BITS && l0 + l1 <= (uint32_t)DEC_LUT_BITS)
+        return (e0 >> 8) | ((e1 >> 8) << 8) | ((l0 + l1) << 16) | (l0 << 24) | (2u << 28);
+    return (e0 >> 8) | (l0 << 16) | (l0 << 24) | (1u << 28);
+}
+
+// code at the 64-bit window by sorted search (codes longer than the LUT window): length, or 0 if no code
+template <typename V>
+SHAFA_HD uint32_t decf_long(const V &t, uint64_t window, uint32_t *sym)
+{
+    int lo = 0, hi = 256;  // count of entries <= window
+    while (lo < hi) {
+        const int m = (lo + hi) >> 1;
+        if (t.sleft[m] <= window)
+            lo = m + 1;
+        else
+            hi = m;
+    }
+    if (lo == 0) return 0;
+    const int r = lo - 1;
+    const uint32_t len = t.slen[r];
+    if (len == 0 || (window >> (64 - len)) != (t.sleft[r] >> (64 - len))) return 0;
+    *sym = t.ssym[r];
+    return len;
+}
+
+// entry (1 or 2 symbols) for the code(s) at bit q; a long or invalid code comes back as a one-symbol entry
+template <typename V>
+SHAFA_HD uint32_t decf_lookup(const V &t, uint32_t row, uint32_t q, uint32_t *bad)
+{
+    uint32_t e = t.lp(dec_window32(t, row, q) >> (32 - DEC_LUT_BITS));
+    if (e == 0) {
+        uint32_t sym = 0;
+        uint32_t l = decf_long(t, dec_window64(t, row, q), &sym);
+        if (l == 0) {
+            *bad = 1;
+            l = 1;
+        }
+        e = sym | (l << 16) | (1u << 28);
+    }
+    return e;
+}
+
+struct DecfMain {      // the record list of a sub-sequence
+    uint32_t m;        // records stored
+    uint32_t k;        // symbols in them (all symbols of the walk if norec)
+    uint32_t end;      // bit position (relative to the sub-sequence) where the walk left [.., stop)
+    uint32_t norec;    // the list overflowed DECF_CAP: k and end are right, the records are not usable
+    uint32_t bad;
+};
+
+// Walk the sub-sequence from `start`, two codes per lookup where a 12-bit window holds them, and store one
+// record per lookup at slot + 4 j.  Symbols are those that START in [start, stop).
+template <typename V>
+SHAFA_HD DecfMain decf_pass(const V &t, uint32_t row, uint32_t slot, uint32_t start, uint32_t stop)
+{
+    DecfMain r;
+    r.norec = 0;
+    r.bad = 0;
+    uint32_t q = start, k = 0, j = 0;
+    while (q < stop && j < (uint32_t)DECF_CAP) {
+        const uint32_t e = decf_lookup(t, row, q, &r.bad);
+        t.st32(slot + 4u * j, (e & 0xFF00FFFFu) | (q << 16));
+        j++;
+        q += decf_total(e);
+        k += decf_n(e);
+    }
+    if (q >= stop) {
+        if (j) {  // the last lookup may have taken a second code that starts at or after `stop`: it belongs to the next range
+            const uint32_t rec = t.ld32(slot + 4u * (j - 1));
+            const uint32_t q0 = decf_pos(rec);
+            if (decf_n(rec) == 2u && q0 + decf_len0(rec) >= stop) {
+                t.st32(slot + 4u * (j - 1), (rec & 0x0FFFFFFFu) | (1u << 28));
+                k--;
+                q = q0 + decf_len0(rec);
+            }
+        }
+    } else {  // out of record space (codes of 1-2 bits): count on, one code at a time
+        r.norec = 1;
+        while (q < stop) {
+            const uint32_t e = decf_lookup(t, row, q, &r.bad);
+            q += decf_n(e) == 2u ? decf_len0(e) : decf_total(e);
+            k++;
+        }
+    }
+    r.m = j;
+    r.k = k;
+    r.end = q;
+    return r;
+}
+
+struct DecfSplice {
+    uint32_t kind;   // 0 = met the record list at record jsp, 1 = left the range without meeting it, 2 = head full (rebuild the list)
+    uint32_t hn;     // head symbols written
+    uint32_t jsp;    // first record that belongs to the true path
+    uint32_t kskip;  // symbols in the records before it
+    uint32_t end;    // kind 1: where the walk left the range
+    uint32_t bad;
+};
+
+// The true start `s` is known: walk single codes from it until a record of the list starts at the same bit.
+template <typename V>
+SHAFA_HD DecfSplice decf_splice(const V &t, uint32_t row, uint32_t slot, uint32_t head, const DecfMain &mn, uint32_t s, uint32_t stop)
+{
+    DecfSplice r;
+    r.hn = r.jsp = r.kskip = r.end = r.bad = 0;
+    const uint32_t m = mn.norec ? 0u : mn.m;
+    uint32_t q = s, j = 0, kskip = 0, hn = 0;
+    for (;;) {
+        if (q >= stop) {
+            r.kind = 1;
+            r.end = q;
+            break;
+        }
+        uint32_t p = 0xFFFFFFFFu;
+        while (j < m) {
+            const uint32_t rec = t.ld32(slot + 4u * j);
+            p = decf_pos(rec);
+            if (p >= q) break;
+            kskip += decf_n(rec);
+            j++;
+        }
+        if (j < m && p == q) {
+            r.kind = 0;
+            break;
+        }
+        if (hn == (uint32_t)DECF_HEAD) {
+            r.kind = 2;
+            break;
+        }
+        const uint32_t e = decf_lookup(t, row, q, &r.bad);
+        t.st8(head + hn, e & 0xFFu);
+        hn++;
+        q += decf_n(e) == 2u ? decf_len0(e) : decf_total(e);
+    }
+    r.hn = hn;
+    r.jsp = j;
+    r.kskip = kskip;
+    return r;
+}
+
+// What a sub-sequence finally holds: `hn` head symbols, then the symbols of records [jsp, m)
+struct DecfFinal {
+    uint32_t start, end, count, hn, jsp;
+};
+
 }  // namespace shafa

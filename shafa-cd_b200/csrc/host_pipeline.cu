@@ -39,6 +39,25 @@ uint64_t pipe_chunk_bytes()
     return (uint64_t)(mb < 1 ? 1 : mb) << 20;
 }
 
+// worker contexts of all participating devices, device-major.  One device: pipe_workers() of them; several
+// devices (one file sharded over N GPUs): at most 16 host threads in total, at least two per
+// device so that each GPU's copies overlap its kernels.
+bool gather_workers(shafa_cuda_ctx *const *ctxs, int n_ctx, std::vector<shafa_cuda_ctx *> &out)
+{
+    int per = pipe_workers();
+    if (n_ctx > 1) {
+        const int cap = 16 / n_ctx < 2 ? 2 : 16 / n_ctx;
+        if (per > cap) per = cap;
+    }
+    for (int c = 0; c < n_ctx; c++)
+        for (int i = 0; i < per; i++) {
+            shafa_cuda_ctx *w = worker_ctx(ctxs[c], i);
+            if (!w) return false;
+            out.push_back(w);
+        }
+    return true;
+}
+
 struct Chain {
     std::mutex m;
     std::condition_variable cv;
@@ -80,11 +99,11 @@ struct Chunks {
     uint64_t count;  // number of chunks
 };
 
-Chunks plan_chunks(uint64_t nb, uint64_t bytes)
+Chunks plan_chunks(uint64_t nb, uint64_t bytes, size_t n_workers)
 {
     const uint64_t chunk = pipe_chunk_bytes();
     uint64_t want = (bytes + chunk - 1) / chunk;
-    if (want < 2 * (uint64_t)pipe_workers()) want = 2 * (uint64_t)pipe_workers();  // enough chunks to keep both copy directions busy
+    if (want < 2 * (uint64_t)n_workers) want = 2 * (uint64_t)n_workers;  // enough chunks to keep both copy directions busy
     if (want > nb) want = nb;
     if (want < 1) want = 1;
     Chunks c;
@@ -98,10 +117,11 @@ Chunks plan_chunks(uint64_t nb, uint64_t bytes)
 // ---------------------------------------------------------------------------------------------------
 // encode
 // ---------------------------------------------------------------------------------------------------
-int encode_host_pipelined(shafa_cuda_ctx *ctx, const uint8_t *h_in, uint64_t n, uint64_t block_size, int force_rle,
+int encode_host_pipelined(shafa_cuda_ctx *const *ctxs, int n_ctx, const uint8_t *h_in, uint64_t n, uint64_t block_size, int force_rle,
                           int force_freq, int mode, shafa_cuda_encoded *out)
 {
-    if (!ctx || !out || !h_in) return SHAFA_OUTSIDE_MODULE;
+    if (!ctxs || n_ctx < 1 || !ctxs[0] || !out || !h_in) return SHAFA_OUTSIDE_MODULE;
+    shafa_cuda_ctx *const ctx = ctxs[0];  // block 0's owner: the R/N decision of the whole file is taken here (f.c:246-258)
     if (cudaSetDevice(ctx->device) != cudaSuccess) return SHAFA_THREAD_CREATION_FAILED;
     if (block_size == 0) block_size = 524288;                     // utils/file.c:62 (the reference's default)
     if (block_size < 512) block_size = 512;                       // utils/file.c:63
@@ -156,7 +176,14 @@ int encode_host_pipelined(shafa_cuda_ctx *ctx, const uint8_t *h_in, uint64_t n, 
     out->payload = user_payload;
     out->payload_capacity = pay_cap;
 
-    const Chunks ch = plan_chunks(nb, n);
+    std::vector<shafa_cuda_ctx *> workers;
+    if (!gather_workers(ctxs, n_ctx, workers)) {
+        out->rle = nullptr;
+        out->payload = nullptr;
+        shafa_cuda_encoded_free(out);
+        return set_error(ctx, SHAFA_LACK_OF_MEMORY, "pipelined encode: worker contexts could not be created");
+    }
+    const Chunks ch = plan_chunks(nb, n, workers.size());
     Chain rle_chain(ch.count), pay_chain(ch.count);
     std::atomic<uint64_t> next{0};
     std::atomic<int> err{0};
@@ -175,8 +202,8 @@ int encode_host_pipelined(shafa_cuda_ctx *ctx, const uint8_t *h_in, uint64_t n, 
     };
 
     auto work = [&](int widx) {
-        shafa_cuda_ctx *w = worker_ctx(ctx, widx);
-        if (!w) return fail_from(nullptr, SHAFA_LACK_OF_MEMORY);
+        shafa_cuda_ctx *w = workers[widx];
+        if (cudaSetDevice(w->device) != cudaSuccess) return fail_from(nullptr, SHAFA_THREAD_CREATION_FAILED);
         auto fail = [&](int code) { fail_from(w, code); };
         for (;;) {
             const uint64_t c = next.fetch_add(1);
@@ -241,16 +268,22 @@ int encode_host_pipelined(shafa_cuda_ctx *ctx, const uint8_t *h_in, uint64_t n, 
     };
 
     {
+        // chunks go to whichever worker is free, devices interleaved (worker i of every device before worker i + 1)
         std::vector<std::thread> threads;
-        const int nw = (int)((ch.count < (uint64_t)pipe_workers()) ? ch.count : pipe_workers());
-        for (int i = 0; i < nw; i++) threads.emplace_back(work, i);
+        const size_t nw = ch.count < workers.size() ? (size_t)ch.count : workers.size();
+        const size_t per = workers.size() / (size_t)n_ctx;
+        for (size_t i = 0; i < nw; i++) threads.emplace_back(work, (int)((i % (size_t)n_ctx) * per + i / (size_t)n_ctx));
         for (auto &t : threads) t.join();
     }
+    cudaSetDevice(ctx->device);
     rc = err.load();
     if (rc) {
         // copies into the caller's buffers may still be in flight on the streams of workers that bailed out
-        for (int i = 0; i < PIPE_MAX_WORKERS; i++)
-            if (ctx->workers[i]) cudaStreamSynchronize(ctx->workers[i]->stream);
+        for (shafa_cuda_ctx *w : workers) {
+            cudaSetDevice(w->device);
+            cudaStreamSynchronize(w->stream);
+        }
+        cudaSetDevice(ctx->device);
         set_error(ctx, rc, "pipelined encode: %s", err_text.c_str());
         out->rle = nullptr;  // caller-owned buffers stay with the caller
         out->payload = nullptr;
@@ -266,17 +299,26 @@ int encode_host_pipelined(shafa_cuda_ctx *ctx, const uint8_t *h_in, uint64_t n, 
 // ---------------------------------------------------------------------------------------------------
 // decode
 // ---------------------------------------------------------------------------------------------------
-int decode_host_pipelined(shafa_cuda_ctx *ctx, const uint8_t *h_payload, const uint64_t *h_payload_offsets,
+// h_payload == nullptr: "-d r" -- the symbol stream itself is given (h_sym, blocks at the running sums of h_n) and only
+// expanded (rle_block_decompressor, d.c:116-197)
+int decode_host_pipelined(shafa_cuda_ctx *const *ctxs, int n_ctx, const uint8_t *h_payload, const uint64_t *h_payload_offsets,
                           const uint64_t *h_z, const uint64_t *h_n, uint64_t nb, const uint8_t *h_len,
-                          const uint64_t *h_code, int rle_expand, uint8_t *h_out, uint64_t out_capacity,
+                          const uint64_t *h_code, const uint8_t *h_sym, int rle_expand, uint8_t *h_out, uint64_t out_capacity,
                           uint64_t *h_out_size, uint64_t *h_final_sizes)
 {
-    if (!ctx) return SHAFA_OUTSIDE_MODULE;
+    if (!ctxs || n_ctx < 1 || !ctxs[0]) return SHAFA_OUTSIDE_MODULE;
+    shafa_cuda_ctx *const ctx = ctxs[0];
     if (cudaSetDevice(ctx->device) != cudaSuccess) return SHAFA_THREAD_CREATION_FAILED;
     if (h_out_size) *h_out_size = 0;
     uint64_t sym_total = 0;
-    for (uint64_t b = 0; b < nb; b++) sym_total += h_n[b];
-    const Chunks ch = plan_chunks(nb, sym_total);
+    std::vector<uint64_t> sym_off(nb + 1, 0);
+    for (uint64_t b = 0; b < nb; b++) {
+        sym_total += h_n[b];
+        sym_off[b + 1] = sym_total;
+    }
+    std::vector<shafa_cuda_ctx *> workers;
+    if (!gather_workers(ctxs, n_ctx, workers)) return set_error(ctx, SHAFA_LACK_OF_MEMORY, "pipelined decode: worker contexts could not be created");
+    const Chunks ch = plan_chunks(nb, sym_total, workers.size());
     Chain out_chain(ch.count);
     std::atomic<uint64_t> next{0};
     std::atomic<int> err{0};
@@ -297,14 +339,48 @@ int decode_host_pipelined(shafa_cuda_ctx *ctx, const uint8_t *h_payload, const u
         out_chain.abort();
     };
     auto work = [&](int widx) {
-        shafa_cuda_ctx *w = worker_ctx(ctx, widx);
-        if (!w) return fail_from(nullptr, SHAFA_LACK_OF_MEMORY);
+        shafa_cuda_ctx *w = workers[widx];
+        if (cudaSetDevice(w->device) != cudaSuccess) return fail_from(nullptr, SHAFA_THREAD_CREATION_FAILED);
         auto fail = [&](int code) { fail_from(w, code); };
         for (;;) {
             const uint64_t c = next.fetch_add(1);
             if (c >= ch.count || err.load()) return;
             const uint64_t b0 = c * ch.per, b1 = (b0 + ch.per < nb) ? b0 + ch.per : nb, cb = b1 - b0;
             int r;
+            if (!h_payload) {  // RLE expansion only: the chunk's slice of the symbol stream goes up as it is
+                const uint64_t slo = sym_off[b0], stot = sym_off[b1] - sym_off[b0];
+                std::vector<uint64_t> offsets(cb + 1, 0);
+                for (uint64_t b = 0; b < cb; b++) offsets[b + 1] = offsets[b] + h_n[b0 + b];
+                uint8_t *d_sym = (uint8_t *)scratch_get(w, SCR_STAGE_B, round16(stot) + 64);
+                if (!d_sym) return fail(SHAFA_LACK_OF_MEMORY);
+                if ((r = shafa_cuda_memcpy_h2d(w, d_sym, h_sym + slo, stot))) return fail(r);
+                uint64_t cap = 0;
+                for (uint64_t b = 0; b < cb; b++) {
+                    const uint64_t s = h_n[b0 + b];
+                    cap += (s <= 65536 ? 65536 : s <= 655360 ? 655360 : s <= 8388608 ? 8388608 : 67108864) + 1024;  // d.c:129-136
+                }
+                uint8_t *d_out = (uint8_t *)scratch_get(w, SCR_STAGE_F, round16(cap) + 64);
+                if (!d_out) return fail(SHAFA_LACK_OF_MEMORY);
+                r = shafa_cuda_rle_decode_blocks(w, d_sym, offsets.data(), cb, d_out, cap, fin + b0);
+                if (r == SHAFA_LACK_OF_MEMORY) {
+                    cap = 0;
+                    for (uint64_t b = 0; b < cb; b++) cap += fin[b0 + b];
+                    d_out = (uint8_t *)scratch_get(w, SCR_STAGE_F, round16(cap) + 64);
+                    if (!d_out) return fail(SHAFA_LACK_OF_MEMORY);
+                    r = shafa_cuda_rle_decode_blocks(w, d_sym, offsets.data(), cb, d_out, cap, fin + b0);
+                }
+                if (r) return fail(r);
+                uint64_t produced = 0;
+                for (uint64_t b = 0; b < cb; b++) produced += fin[b0 + b];
+                uint64_t base;
+                if (!out_chain.wait(c, &base)) return;
+                out_chain.publish(c + 1, base + produced);
+                if (base + produced <= out_capacity) {
+                    if ((r = shafa_cuda_memcpy_d2h(w, h_out + base, d_out, produced))) return fail(r);
+                    if ((r = shafa_cuda_synchronize(w))) return fail(r);
+                }
+                continue;
+            }
             // payload slice of this chunk: slots are laid out in block order by the encoder / the .shaf reader;
             // be general and take min/max over the chunk's blocks
             uint64_t plo = ~0ull, phi = 0, stot = 0;
@@ -369,14 +445,19 @@ int decode_host_pipelined(shafa_cuda_ctx *ctx, const uint8_t *h_payload, const u
     };
     {
         std::vector<std::thread> threads;
-        const int nw = (int)((ch.count < (uint64_t)pipe_workers()) ? ch.count : pipe_workers());
-        for (int i = 0; i < nw; i++) threads.emplace_back(work, i);
+        const size_t nw = ch.count < workers.size() ? (size_t)ch.count : workers.size();
+        const size_t per = workers.size() / (size_t)n_ctx;
+        for (size_t i = 0; i < nw; i++) threads.emplace_back(work, (int)((i % (size_t)n_ctx) * per + i / (size_t)n_ctx));
         for (auto &t : threads) t.join();
     }
+    cudaSetDevice(ctx->device);
     const int rc = err.load();
     if (rc) {
-        for (int i = 0; i < PIPE_MAX_WORKERS; i++)
-            if (ctx->workers[i]) cudaStreamSynchronize(ctx->workers[i]->stream);
+        for (shafa_cuda_ctx *w : workers) {
+            cudaSetDevice(w->device);
+            cudaStreamSynchronize(w->stream);
+        }
+        cudaSetDevice(ctx->device);
         set_error(ctx, rc, "pipelined decode: %s", err_text.c_str());
         return rc;
     }

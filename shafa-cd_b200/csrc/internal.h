@@ -26,6 +26,7 @@ enum ScratchSlot {
     SCR_DEC_SUB,    // decode sub-sequence info
     SCR_DEC_SEQ,    // decode sequence info
     SCR_DEC_FB,     // decode sync: per-CTA tables of the all-starts fallback
+    SCR_DEC_REC,    // fused decoder: per-sequence records
     SCR_STAGE_A,    // host API staging (input)
     SCR_STAGE_B,
     SCR_STAGE_C,
@@ -48,6 +49,7 @@ struct shafa_cuda_ctx {
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
     char err[512] = {0};
+    uint32_t last_err_bits = 0;  // device error word of the last finished call (shafa::ErrBits)
     void *scratch[shafa::SCR_COUNT] = {nullptr};
     size_t scratch_cap[shafa::SCR_COUNT] = {0};
     uint8_t *pinned = nullptr;  // pinned ring for per-call metadata
@@ -103,19 +105,22 @@ enum ErrBits : uint32_t {
     ERR_PAYLOAD_SHORT = 8,   // payload holds fewer symbols than announced
     ERR_BAD_WINDOW = 16,     // bit pattern that is no code
     ERR_CAPACITY = 32,       // output buffer too small
-    ERR_RLE_TRUNCATED = 64   // RLE block ends inside a triple
+    ERR_RLE_TRUNCATED = 64,  // RLE block ends inside a triple
+    ERR_SPECULATION = 128,   // fused SF decoder: a sequence's end depended on its start (decode again, exact path)
+    ERR_TIMEOUT = 256        // fused SF decoder: a bounded device-side wait gave up (never seen; keeps a bug from hanging the GPU)
 };
-enum OccId { OCC_SF_ENCODE = 0, OCC_RLE_ENC = 1 /* +variant 0..3 */, OCC_RLE_DEC = 5, OCC_DEC_SYNC = 6, OCC_DEC_WRITE = 7, OCC_HIST = 8 };
+enum OccId { OCC_SF_ENCODE = 0, OCC_RLE_ENC = 1 /* +variant 0..3 */, OCC_RLE_DEC = 5, OCC_DEC_SYNC = 6, OCC_DEC_WRITE = 7, OCC_HIST = 8, OCC_DEC_FUSED = 9 };
 enum MiscSlot { MISC_COUNTER = 0, MISC_FLAG = 16, MISC_ERR = 32, MISC_WORDS = 64 };  // uint32 indices into SCR_MISC
 uint32_t *misc_ptr(shafa_cuda_ctx *ctx, int which);
 shafa_cuda_ctx *worker_ctx(shafa_cuda_ctx *ctx, int i);  // lazily created child context i (0..3) on the same device
 
-// host_pipeline.cu: chunked, overlapped versions of the whole-shard host calls (nullptr-safe fallbacks live in api.cu)
-int encode_host_pipelined(shafa_cuda_ctx *ctx, const uint8_t *h_in, uint64_t n, uint64_t block_size, int force_rle,
+// host_pipeline.cu: chunked, overlapped versions of the whole-shard host calls over the worker contexts of one or
+// several devices (ctxs[0] owns the file's block 0)
+int encode_host_pipelined(shafa_cuda_ctx *const *ctxs, int n_ctx, const uint8_t *h_in, uint64_t n, uint64_t block_size, int force_rle,
                           int force_freq, int mode, shafa_cuda_encoded *out);
-int decode_host_pipelined(shafa_cuda_ctx *ctx, const uint8_t *h_payload, const uint64_t *h_payload_offsets,
+int decode_host_pipelined(shafa_cuda_ctx *const *ctxs, int n_ctx, const uint8_t *h_payload, const uint64_t *h_payload_offsets,
                           const uint64_t *h_z, const uint64_t *h_n, uint64_t nb, const uint8_t *h_len,
-                          const uint64_t *h_code, int rle_expand, uint8_t *h_out, uint64_t out_capacity,
+                          const uint64_t *h_code, const uint8_t *h_sym, int rle_expand, uint8_t *h_out, uint64_t out_capacity,
                           uint64_t *h_out_size, uint64_t *h_final_sizes);
 
 // hist.cu
@@ -135,7 +140,7 @@ int launch_sf_encode(shafa_cuda_ctx *ctx, const uint8_t *d_sym, const uint64_t *
 // sf_decode.cu
 int launch_sf_decode(shafa_cuda_ctx *ctx, const uint8_t *d_payload, const uint64_t *h_payload_off,
                      const uint64_t *h_z, const uint64_t *h_n, uint64_t nb, const uint8_t *d_len,
-                     const uint64_t *d_code, uint8_t *d_sym, uint32_t *d_err);
+                     const uint64_t *d_code, uint8_t *d_sym, uint32_t *d_err, bool force_exact);
 
 // rle_encode.cu (synchronises: returns per-block sizes)
 int launch_rle_encode(shafa_cuda_ctx *ctx, const uint8_t *d_in, uint64_t n, uint64_t block_size, uint8_t *d_rle,

@@ -19,24 +19,13 @@
 //                  symbols staged and written at their scanned offsets, clipped at
 //                  the block's symbol count
 // Algorithmic bytes: Z (payload in) + S (symbols out).
-#include "common.cuh"
-#include "core.h"
-#include "internal.h"
+#include "sf_decode.cuh"
 
 namespace shafa {
 
 // ---- tables -----------------------------------------------------------------------------
-struct DecTablesGlobal {
-    uint16_t *lut;    // [nb][4096]  first-level: (sym << 8) | len
-    uint8_t *lut2;    // [nb][8192]  (nsym << 4) | bits of all whole codes in a 13-bit window
-    uint32_t *lut3;   // [nb][4096]  first one or two codes of the window with their symbols
-    uint64_t *sleft;  // [nb][256]
-    uint8_t *slen;    // [nb][256]
-    uint8_t *ssym;    // [nb][256]
-};
-
 __global__ void __launch_bounds__(256)
-k_dec_tables(const uint8_t *__restrict__ lens, const uint64_t *__restrict__ codes, DecTablesGlobal g)
+k_dec_tables(const uint8_t *__restrict__ lens, const uint64_t *__restrict__ codes, DecTablesGlobal g, int force_exact)
 {
     __shared__ uint64_t left[256];
     __shared__ uint8_t len_s[256];
@@ -44,6 +33,8 @@ k_dec_tables(const uint8_t *__restrict__ lens, const uint64_t *__restrict__ code
     __shared__ uint8_t sn[256];
     __shared__ uint8_t ss[256];
     __shared__ uint16_t lut1[DEC_LUT_SIZE];
+    __shared__ uint32_t len_count[65];
+    __shared__ uint32_t s_flags;
     const unsigned s = threadIdx.x;
     const uint64_t b = blockIdx.x;
     const uint32_t l = lens[b * 256 + s];
@@ -51,7 +42,9 @@ k_dec_tables(const uint8_t *__restrict__ lens, const uint64_t *__restrict__ code
     const uint64_t lf = l ? (c << (64 - l)) : ~0ull;
     left[s] = lf;
     len_s[s] = (uint8_t)l;
+    if (s < 65) len_count[s] = 0;
     __syncthreads();
+    if (l && l <= 64) atomicAdd(&len_count[l], 1u);
     // order by (left-aligned code, absent last, symbol)
     uint32_t rank = 0;
     for (int t = 0; t < 256; t++) {
@@ -67,6 +60,37 @@ k_dec_tables(const uint8_t *__restrict__ lens, const uint64_t *__restrict__ code
     g.sleft[b * 256 + s] = sl[s];
     g.slen[b * 256 + s] = sn[s];
     g.ssym[b * 256 + s] = ss[s];
+    // ---- what kind of code is this (thread r looks at rank r) ----
+    {
+        const uint32_t lr = sn[s];
+        // prefix-free <=> no code is a prefix of its successor in sorted order (equal codes included)
+        const bool clash = lr != 0 && s + 1 < 256 && sn[s + 1] != 0 && ((sl[s + 1] >> (64 - lr)) == (sl[s] >> (64 - lr)));
+        const int any_clash = __syncthreads_or(clash);
+        if (s == 0) {
+            // Kraft sum in units of 2^-64 as a 128-bit number: complete <=> it is exactly 2^64
+            uint64_t lo = 0, hi = 0;
+            uint32_t minlen = 0, maxlen = 0;
+            for (uint32_t k = 1; k <= 64; k++) {
+                const uint64_t cnt = len_count[k];
+                if (!cnt) continue;
+                if (!minlen) minlen = k;
+                maxlen = k;
+                const uint64_t add_lo = cnt << (64 - k);
+                const uint64_t add_hi = (k == 64) ? 0ull : (cnt >> k);
+                const uint64_t nlo = lo + add_lo;
+                hi += add_hi + (nlo < lo ? 1ull : 0ull);
+                lo = nlo;
+            }
+            uint32_t f = 0;
+            if (!any_clash && hi == 1ull && lo == 0ull) f |= DECB_COMPLETE;
+            if (2u * minlen > maxlen) f |= DECB_NOSYNC;
+            if (maxlen > 32u) f |= DECB_WIDE;
+            s_flags = f;
+            g.flags[b] = (uint8_t)f;
+        }
+        __syncthreads();
+    }
+    const bool fused = !force_exact && dec_block_fused_ok((uint8_t)s_flags);
     for (int e = s; e < DEC_LUT_SIZE; e += 256) {
         const uint64_t window = (uint64_t)e << (64 - DEC_LUT_BITS);
         int lo = 0, hi = 256;
@@ -87,26 +111,37 @@ k_dec_tables(const uint8_t *__restrict__ lens, const uint64_t *__restrict__ code
                 entry = (uint16_t)DEC_LONG;
         }
         lut1[e] = entry;
-        g.lut[b * DEC_LUT_SIZE + e] = entry;
+        if (!fused) g.lut[b * DEC_LUT_SIZE + e] = entry;
     }
     __syncthreads();
-    for (int e = s; e < DEC_LUT_SIZE; e += 256) {
-        g.lut2[b * DEC_LUT2_SIZE + 2 * e] = dec_lut2_entry(lut1, 2u * (uint32_t)e);
-        g.lut2[b * DEC_LUT2_SIZE + 2 * e + 1] = dec_lut2_entry(lut1, 2u * (uint32_t)e + 1u);
-        g.lut3[b * DEC_LUT_SIZE + e] = dec_lut3_entry(lut1, (uint32_t)e);
+    // only the tables of the path the block takes are written (6,554 blocks x 50 KB otherwise)
+    if (fused) {
+        for (int e = s; e < DEC_LUT_SIZE; e += 256) g.lutp[b * DEC_LUT_SIZE + e] = decf_entry(lut1, (uint32_t)e);
+    } else {
+        for (int e = s; e < DEC_LUT_SIZE; e += 256) {
+            g.lut2[b * DEC_LUT2_SIZE + 2 * e] = dec_lut2_entry(lut1, 2u * (uint32_t)e);
+            g.lut2[b * DEC_LUT2_SIZE + 2 * e + 1] = dec_lut2_entry(lut1, 2u * (uint32_t)e + 1u);
+            g.lut3[b * DEC_LUT_SIZE + e] = dec_lut3_entry(lut1, (uint32_t)e);
+        }
+    }
+}
+
+// per sequence of the fused plan: where its payload lies and how much of it to copy (one CTA per block)
+__global__ void __launch_bounds__(256)
+k_dec_seqrec(DecPlan plan, DecSeqRec *__restrict__ rec)
+{
+    const uint32_t b = blockIdx.x;
+    const uint64_t s0 = plan.seq0[b], s1 = plan.seq0[b + 1];
+    const uint64_t slot = (plan.z[b] + 15) & ~15ull, off0 = plan.pay_off[b];
+    for (uint64_t i = threadIdx.x; s0 + i < s1; i += 256) {
+        const uint64_t off = off0 + i * DEC_SEQ_BYTES;
+        const uint64_t left_bytes = slot - i * DEC_SEQ_BYTES;
+        const uint32_t bytes = left_bytes < (uint64_t)DEC_SEQ_BYTES + 16 ? (uint32_t)left_bytes : (uint32_t)DEC_SEQ_BYTES + 16u;
+        rec[s0 + i] = make_uint4((uint32_t)off, (uint32_t)(off >> 32), b, bytes);
     }
 }
 
 // ---- shared helpers -----------------------------------------------------------------------
-struct DecPlan {
-    const uint64_t *pay_off;  // [nb]
-    const uint64_t *z;        // [nb]
-    const uint64_t *n;        // [nb] symbols per block
-    const uint64_t *out_off;  // [nb] output offset of each block
-    const uint64_t *seq0;     // [nb+1] first sequence of each block
-    uint32_t nb;
-};
-
 constexpr int DEC_MAP_MAX = 16;     // longest code for which the all-starts fallback of k_dec_sync is used
 constexpr int DEC_FB_BYTES = DEC_THREADS * DEC_MAP_MAX * 2 + (DEC_THREADS / 32) * DEC_MAP_MAX * 33;  // per CTA: map + paths
 constexpr int DEC_MAX_ROUNDS = 12;  // sync rounds before that fallback is taken in any case
@@ -138,13 +173,7 @@ __device__ __forceinline__ void dec_load_tables(DecShared &sh, const DecTablesGl
     sh.ssym[tid] = g.ssym[(uint64_t)b * 256 + tid];
 }
 
-// Thread s builds the row of sub-sequence s straight from global memory: payload bytes [16 s, 16 s + 24)
-// of the sequence as six big-endian words; bytes at or past z read as zero.  The loads are issued one
-// sequence ahead (dec_fetch_row) and only turned into a row when that sequence's turn comes.
-struct RowRegs {
-    uint4 v;
-    uint2 u;
-};
+// The loads are issued one sequence ahead (dec_fetch_row) and only turned into a row when that sequence's turn comes.
 __device__ __forceinline__ RowRegs dec_fetch_row(const uint8_t *payload, uint64_t pay_off, uint64_t z, uint64_t seq_in_block)
 {
     const uint64_t o = seq_in_block * DEC_SEQ_BYTES + (uint64_t)threadIdx.x * 16;  // offset in the block's payload
@@ -158,29 +187,6 @@ __device__ __forceinline__ RowRegs dec_fetch_row(const uint8_t *payload, uint64_
     if (o + 16 < slot) r.u = __ldg(reinterpret_cast<const uint2 *>(base + o + 16));
     return r;
 }
-__device__ __forceinline__ void dec_store_row(DecShared &sh, const RowRegs &r, uint64_t z, uint64_t seq_in_block)
-{
-    const unsigned tid = threadIdx.x;
-    const uint64_t o = seq_in_block * DEC_SEQ_BYTES + (uint64_t)tid * 16;
-    uint32_t w[DEC_ROW_WORDS] = {r.v.x, r.v.y, r.v.z, r.v.w, r.u.x, r.u.y};
-    if (o + 4 * DEC_ROW_WORDS > z) {  // only at the end of a block
-#pragma unroll
-        for (int k = 0; k < DEC_ROW_WORDS; k++) {
-            const uint64_t bo = o + 4 * k;
-            if (bo >= z)
-                w[k] = 0;
-            else if (bo + 4 > z)
-                w[k] &= (0xffffffffu >> (8 * (uint32_t)(bo + 4 - z)));
-        }
-    }
-#pragma unroll
-    for (int k = 0; k < DEC_ROW_WORDS; k++) w[k] = bswap32(w[k]);
-    uint64_t row[DEC_ROW];
-    dec_row_from_words(w, row);
-#pragma unroll
-    for (int k = 0; k < DEC_ROW; k++) sh.pairs[tid * DEC_ROW + k] = row[k];
-}
-
 // Which block a sequence belongs to, tracked incrementally while a CTA walks its chunk (every thread
 // keeps the same copy: no broadcast through shared memory, no barrier).
 struct SeqCursor {
@@ -304,6 +310,7 @@ k_dec_sync(const uint8_t *__restrict__ payload, DecPlan plan, DecTablesGlobal g,
     uint8_t *const s_path = reinterpret_cast<uint8_t *>(s_map + DEC_THREADS * DEC_MAP_MAX);               // [warp][entry offset][i]: start of the warp's i-th sub-sequence
     uint8_t *const s_path_out = s_path + (DEC_THREADS / 32) * DEC_MAP_MAX * 32;                          // [warp][entry offset]: offset handed to the next warp
     __shared__ uint32_t s_maxlen;
+    __shared__ uint32_t s_nosync;  // the block's code has nearly one length (k_dec_tables): go to all starts at once
     const unsigned tid = threadIdx.x, lane = lane_id(), warp = warp_id();
     uint64_t seq_first, seq_last;
     dec_chunk(nseq, &seq_first, &seq_last);
@@ -322,7 +329,10 @@ k_dec_sync(const uint8_t *__restrict__ payload, DecPlan plan, DecTablesGlobal g,
         if (b != cur_block) {
             cur_block = b;
             dec_load_tables(sh, g, b, s_lut2);
-            if (tid == 0) s_maxlen = 0;
+            if (tid == 0) {
+                s_maxlen = 0;
+                s_nosync = (g.flags[b] & DECB_NOSYNC) != 0;
+            }
             __syncthreads();
             const uint32_t wmax = __reduce_max_sync(FULL, (uint32_t)sh.slen[tid]);
             if (lane == 0) atomicMax(&s_maxlen, wmax);
@@ -330,7 +340,7 @@ k_dec_sync(const uint8_t *__restrict__ payload, DecPlan plan, DecTablesGlobal g,
         // The first sub-sequence starts where the previous sequence ended.  Inside a chunk that is known;
         // the first sequence of a chunk assumes 0 and k_dec_stitch repairs it (a block's first sequence IS 0).
         if (sib == 0 || seq == seq_first) carry = 0;
-        dec_store_row(sh, cur.row, z, sib);
+        dec_store_row(sh.pairs, cur.row, z, sib);
         cur = nxt;
         __syncthreads();
         const DecViewS t = dec_view_of(sh, s_lut2, nullptr);
@@ -347,8 +357,13 @@ k_dec_sync(const uint8_t *__restrict__ payload, DecPlan plan, DecTablesGlobal g,
             s_count[sid] = (uint16_t)r.count;
             s_ends[sid] = r.end > (uint32_t)DEC_SUB_BITS ? r.end - DEC_SUB_BITS : 0;  // overshoot into the next sub-sequence
         };
-        run(tid, tid ? 0u : carry);
         const uint32_t maxlen = s_maxlen;  // (written before the barrier above)
+        // codes of nearly one length: the speculative rounds would be wasted, take every start right away
+        const bool all_starts_now = s_nosync && maxlen <= (uint32_t)DEC_MAP_MAX;
+        if (all_starts_now)
+            s_start[tid] = 0xffffu;  // "not decoded yet": every sub-sequence counts as changed below
+        else
+            run(tid, tid ? 0u : carry);
         uint32_t round = 1;
         // Rounds until every sub-sequence starts where its predecessor ended.  Round 2 moves almost every
         // start; later rounds touch only the few sub-sequences whose predecessor had not synchronised yet,
@@ -361,7 +376,7 @@ k_dec_sync(const uint8_t *__restrict__ payload, DecPlan plan, DecTablesGlobal g,
             const uint32_t total = (uint32_t)__syncthreads_count(changed);
             if (total == 0) break;
             round++;
-            if (((round > 3 && total > DEC_THREADS / 2) || round > DEC_MAX_ROUNDS) && maxlen <= (uint32_t)DEC_MAP_MAX) {
+            if ((all_starts_now || (round > 3 && total > DEC_THREADS / 2) || round > DEC_MAX_ROUNDS) && maxlen <= (uint32_t)DEC_MAP_MAX) {
                 // Codes of (nearly) one length never re-synchronise, and the rounds above would then settle
                 // one sub-sequence at a time.  Instead every thread decodes its sub-sequence from EVERY start
                 // that can occur (an overshoot is shorter than the longest code) and one thread follows the
@@ -612,7 +627,7 @@ k_dec_write(const uint8_t *__restrict__ payload, DecPlan plan, DecTablesGlobal g
             uint4 *dst3 = reinterpret_cast<uint4 *>(ws.lut3);
             for (int i = tid; i < DEC_LUT_SIZE * 4 / 16; i += DEC_THREADS) dst3[i] = src3[i];
         }
-        dec_store_row(sh, cur.row, z, sib);  // read back by this thread only
+        dec_store_row(sh.pairs, cur.row, z, sib);  // read back by this thread only
         uint32_t total;
         // the scan's barriers also fence the table loads above and the previous sequence's copy-out
         const uint32_t excl = block_excl_scan<DEC_THREADS>(sub_count(rec), sh.scan, &total);
@@ -658,34 +673,27 @@ k_dec_write(const uint8_t *__restrict__ payload, DecPlan plan, DecTablesGlobal g
 }
 
 // ---- launcher -------------------------------------------------------------------------------------
-int launch_sf_decode(shafa_cuda_ctx *ctx, const uint8_t *d_payload, const uint64_t *h_payload_off,
-                     const uint64_t *h_z, const uint64_t *h_n, uint64_t nb, const uint8_t *d_len,
-                     const uint64_t *d_code, uint8_t *d_sym, uint32_t *d_err)
+// plan arrays of one path: pay_off[nb] z[nb] n[nb] out_off[nb] seq0[nb+1]; blocks of the OTHER path get z = n = 0
+// (no sequences), so one output buffer is filled by both.
+static uint64_t fill_plan(uint64_t *hp, const uint64_t *h_payload_off, const uint64_t *h_z, const uint64_t *h_n, uint64_t nb,
+                          const uint8_t *flags, bool want_fused)
 {
-    if (nb == 0) return SHAFA_SUCCESS;
-    // plan arrays: pay_off[nb] z[nb] n[nb] out_off[nb] seq0[nb+1]
-    const size_t plan_words = 5 * nb + 1;
-    uint64_t *hp = (uint64_t *)pinned_get(ctx, plan_words * sizeof(uint64_t));
-    uint64_t *dp = (uint64_t *)scratch_get(ctx, SCR_PLAN, plan_words * sizeof(uint64_t));
-    if (!hp || !dp) return SHAFA_LACK_OF_MEMORY;
     uint64_t nseq = 0, out_off = 0;
     for (uint64_t b = 0; b < nb; b++) {
-        if (h_payload_off[b] & 15) return set_error(ctx, SHAFA_FILE_STREAM_FAILED, "sf_decode: payload offset not 16-byte aligned");
+        const bool mine = flags ? (dec_block_fused_ok(flags[b]) == want_fused) : !want_fused;
         hp[b] = h_payload_off[b];
-        hp[nb + b] = h_z[b];
-        hp[2 * nb + b] = h_n[b];
+        hp[nb + b] = mine ? h_z[b] : 0;
+        hp[2 * nb + b] = mine ? h_n[b] : 0;
         hp[3 * nb + b] = out_off;
         hp[4 * nb + b] = nseq;
         out_off += h_n[b];
-        nseq += (h_z[b] + DEC_SEQ_BYTES - 1) / DEC_SEQ_BYTES;
-        // A one-symbol block is written as "@0@" by module C and its .cod block holds 256 empty strings: which
-        // symbol it was is not in the files (the reference decoder dereferences NULL there, d.c:533-536).
-        if (h_n[b] != 0 && h_z[b] == 0) return set_error(ctx, SHAFA_FILE_UNRECOGNIZABLE, "sf_decode: block %llu has %llu symbols but an empty payload (one-symbol block: not decodable from .cod/.shaf)", (unsigned long long)b, (unsigned long long)h_n[b]);
+        if (mine) nseq += (h_z[b] + DEC_SEQ_BYTES - 1) / DEC_SEQ_BYTES;
     }
     hp[5 * nb] = nseq;
-    if (nseq == 0) return SHAFA_SUCCESS;
-    if (nseq > 0x7fffffffull) return set_error(ctx, SHAFA_LACK_OF_MEMORY, "sf_decode: too many sequences");
-    SHAFA_CUDA_TRY(ctx, cudaMemcpyAsync(dp, hp, plan_words * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+    return nseq;
+}
+static DecPlan plan_at(const uint64_t *dp, uint64_t nb)
+{
     DecPlan plan;
     plan.pay_off = dp;
     plan.z = dp + nb;
@@ -693,20 +701,14 @@ int launch_sf_decode(shafa_cuda_ctx *ctx, const uint8_t *d_payload, const uint64
     plan.out_off = dp + 3 * nb;
     plan.seq0 = dp + 4 * nb;
     plan.nb = (uint32_t)nb;
+    return plan;
+}
 
-    // tables
-    const size_t lut_bytes = nb * DEC_LUT_SIZE * sizeof(uint16_t);
-    const size_t tab_bytes = 4 * lut_bytes + nb * 256 * (sizeof(uint64_t) + 2);
-    uint8_t *tab = (uint8_t *)scratch_get(ctx, SCR_DEC_LUT, tab_bytes);
-    if (!tab) return SHAFA_LACK_OF_MEMORY;
-    DecTablesGlobal g;
-    g.sleft = (uint64_t *)tab;
-    g.lut = (uint16_t *)(tab + nb * 256 * sizeof(uint64_t));
-    g.lut2 = (uint8_t *)(tab + nb * 256 * sizeof(uint64_t) + lut_bytes);  // DEC_LUT2_SIZE bytes per block = lut_bytes per block
-    g.lut3 = (uint32_t *)(tab + nb * 256 * sizeof(uint64_t) + 2 * lut_bytes);
-    g.slen = tab + nb * 256 * sizeof(uint64_t) + 4 * lut_bytes;
-    g.ssym = g.slen + nb * 256;
-
+// the exact path: sync / stitch / scan / write over the blocks of `plan`
+static int launch_sf_decode_exact(shafa_cuda_ctx *ctx, const uint8_t *d_payload, const DecPlan &plan, const DecTablesGlobal &g,
+                                  uint64_t nb, uint64_t nseq, uint8_t *d_sym, uint32_t *d_err)
+{
+    if (nseq == 0) return SHAFA_SUCCESS;
     uint16_t *sub_info = (uint16_t *)scratch_get(ctx, SCR_DEC_SUB, nseq * DEC_THREADS * sizeof(uint16_t));
     // seq arrays: seq_end u32[nseq], seq_count u32[nseq], seq_excl u64[nseq]
     uint8_t *seqbuf = (uint8_t *)scratch_get(ctx, SCR_DEC_SEQ, nseq * 16 + 64);
@@ -729,7 +731,6 @@ int launch_sf_decode(shafa_cuda_ctx *ctx, const uint8_t *d_payload, const uint64
     uint64_t grid_sync = (uint64_t)ctx->sm_count * occ_sync * 4, grid_write = (uint64_t)ctx->sm_count * occ_write * 4;
     if (grid_sync > nseq) grid_sync = nseq;
     if (grid_write > nseq) grid_write = nseq;
-    SHAFA_LAUNCH(ctx, "dec_tables", k_dec_tables, dim3((unsigned)nb), dim3(256), 0, d_len, d_code, g);
     uint8_t *fb = (uint8_t *)scratch_get(ctx, SCR_DEC_FB, (size_t)grid_sync * DEC_FB_BYTES);
     if (!fb) return SHAFA_LACK_OF_MEMORY;
     SHAFA_LAUNCH(ctx, "dec_sync", k_dec_sync, dim3((unsigned)grid_sync), dim3(DEC_THREADS), 0, d_payload, plan, g, sub_info,
@@ -753,6 +754,80 @@ int launch_sf_decode(shafa_cuda_ctx *ctx, const uint8_t *d_payload, const uint64
                  sub_info, seq_excl, d_sym, nseq, d_err);
     SHAFA_CHECK_LAUNCH(ctx);
     return SHAFA_SUCCESS;
+}
+
+// force_exact: every block through the exact path (set after the fused kernel reported ERR_SPECULATION, or by
+// SHAFA_DECODE_EXACT=1 for A/B measurements)
+int launch_sf_decode(shafa_cuda_ctx *ctx, const uint8_t *d_payload, const uint64_t *h_payload_off,
+                     const uint64_t *h_z, const uint64_t *h_n, uint64_t nb, const uint8_t *d_len,
+                     const uint64_t *d_code, uint8_t *d_sym, uint32_t *d_err, bool force_exact)
+{
+    if (nb == 0) return SHAFA_SUCCESS;
+    {
+        // The fused single-pass kernel (sf_decode_fused.cu) is correct and tested, but on B200 it is latency-bound at
+        // three resident CTAs per SM (72 KB of records per CTA) and 2.4x slower than this file's multi-kernel path
+        // (profiles/r02_fused_decoder.md): it runs only when asked for.
+        const char *e = getenv("SHAFA_DECODE_FUSED");
+        if (!(e && *e && *e != '0')) force_exact = true;
+    }
+    uint64_t any = 0;
+    for (uint64_t b = 0; b < nb; b++) {
+        if (h_payload_off[b] & 15) return set_error(ctx, SHAFA_FILE_STREAM_FAILED, "sf_decode: payload offset not 16-byte aligned");
+        // A one-symbol block is written as "@0@" by module C and its .cod block holds 256 empty strings: which
+        // symbol it was is not in the files (the reference decoder dereferences NULL there, d.c:533-536).
+        if (h_n[b] != 0 && h_z[b] == 0) return set_error(ctx, SHAFA_FILE_UNRECOGNIZABLE, "sf_decode: block %llu has %llu symbols but an empty payload (one-symbol block: not decodable from .cod/.shaf)", (unsigned long long)b, (unsigned long long)h_n[b]);
+        any += (h_z[b] + DEC_SEQ_BYTES - 1) / DEC_SEQ_BYTES;
+    }
+    if (any == 0) return SHAFA_SUCCESS;
+    if (any > 0x7fffffffull) return set_error(ctx, SHAFA_LACK_OF_MEMORY, "sf_decode: too many sequences");
+
+    // tables
+    const size_t lut_bytes = nb * DEC_LUT_SIZE * sizeof(uint16_t);
+    const size_t tab_bytes = 6 * lut_bytes + nb * 256 * (sizeof(uint64_t) + 2) + nb + 64;
+    uint8_t *tab = (uint8_t *)scratch_get(ctx, SCR_DEC_LUT, tab_bytes);
+    if (!tab) return SHAFA_LACK_OF_MEMORY;
+    DecTablesGlobal g;
+    g.sleft = (uint64_t *)tab;
+    uint8_t *p = tab + nb * 256 * sizeof(uint64_t);
+    g.lut = (uint16_t *)p;   p += lut_bytes;
+    g.lut2 = p;              p += lut_bytes;  // DEC_LUT2_SIZE bytes per block = lut_bytes per block
+    g.lut3 = (uint32_t *)p;  p += 2 * lut_bytes;
+    g.lutp = (uint32_t *)p;  p += 2 * lut_bytes;
+    g.slen = p;              p += nb * 256;
+    g.ssym = p;              p += nb * 256;
+    g.flags = p;
+    SHAFA_LAUNCH(ctx, "dec_tables", k_dec_tables, dim3((unsigned)nb), dim3(256), 0, d_len, d_code, g, force_exact ? 1 : 0);
+    SHAFA_CHECK_LAUNCH(ctx);
+
+    // which path each block takes is a property of its code table, decided on the device; the plans are built here
+    const uint8_t *h_flags = nullptr;
+    if (!force_exact) {
+        uint8_t *hf = (uint8_t *)pinned_get(ctx, nb);
+        if (!hf) return SHAFA_LACK_OF_MEMORY;
+        SHAFA_CUDA_TRY(ctx, cudaMemcpyAsync(hf, g.flags, nb, cudaMemcpyDeviceToHost, ctx->stream));
+        SHAFA_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        h_flags = hf;
+    }
+    const size_t plan_words = 5 * nb + 1;
+    uint64_t *hp = (uint64_t *)pinned_get(ctx, 2 * plan_words * sizeof(uint64_t));
+    uint64_t *dp = (uint64_t *)scratch_get(ctx, SCR_PLAN, 2 * plan_words * sizeof(uint64_t));
+    if (!hp || !dp) return SHAFA_LACK_OF_MEMORY;
+    const uint64_t nseq_fused = h_flags ? fill_plan(hp, h_payload_off, h_z, h_n, nb, h_flags, true) : 0;
+    const uint64_t nseq_exact = fill_plan(hp + plan_words, h_payload_off, h_z, h_n, nb, h_flags, false);
+    SHAFA_CUDA_TRY(ctx, cudaMemcpyAsync(dp, hp, 2 * plan_words * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+    int rc = SHAFA_SUCCESS;
+    if (nseq_fused) {
+        const DecPlan plan = plan_at(dp, nb);
+        DecSeqRec *rec = (DecSeqRec *)scratch_get(ctx, SCR_DEC_REC, nseq_fused * sizeof(DecSeqRec));
+        if (!rec) return SHAFA_LACK_OF_MEMORY;
+        SHAFA_LAUNCH(ctx, "dec_seqrec", k_dec_seqrec, dim3((unsigned)nb), dim3(256), 0, plan, rec);
+        SHAFA_CHECK_LAUNCH(ctx);
+        if ((rc = launch_sf_decode_fused(ctx, d_payload, plan, g, rec, nseq_fused, d_sym, d_err))) return rc;
+    }
+    if (nseq_exact) {
+        rc = launch_sf_decode_exact(ctx, d_payload, plan_at(dp + plan_words, nb), g, nb, nseq_exact, d_sym, d_err);
+    }
+    return rc;
 }
 
 }  // namespace shafa

@@ -11,6 +11,15 @@
 
 #include "util.h"
 
+void c_summary(uint64_t nb, const uint64_t *sizes, const uint64_t *z, double ms, const char *p_shaf)
+{
+    printf("Module: C (Symbol codes' codification) [libshafa_cuda]\nNumber of blocks: %llu\n", (unsigned long long)nb);
+    for (uint64_t b = 0; b < nb; b++)
+        printf("Size before/after & compression rate (Block %llu): %llu/%llu -> %d%%\n", (unsigned long long)b,
+               (unsigned long long)sizes[b], (unsigned long long)z[b], (int)(((float)z[b] / sizes[b]) * 100));
+    printf("Module runtime (milliseconds): %f\nGenerated file %s\n", ms, p_shaf);
+}
+
 _modules_error shafa_compress(char **const path)
 {
     const double t0 = now_ms();
@@ -111,17 +120,7 @@ _modules_error shafa_compress(char **const path)
         if ((err = gpu_status(shafa_cuda_memcpy_d2h(g, h_payload, d_payload, ptotal)))) goto out;
         if ((err = gpu_status(shafa_cuda_synchronize(g)))) goto out;
     }
-    {
-        FILE *f = fopen(p_shaf, "wb");
-        if (!f) {
-            err = _FILE_INACCESSIBLE;
-            goto out;
-        }
-        bool ok = fprintf(f, "@%llu", (unsigned long long)nb) >= 2; /* c.c:351 */
-        for (uint64_t b = 0; b < nb && ok; b++)                      /* c.c:256-258, in block order */
-            ok = fprintf(f, "@%llu@", (unsigned long long)z[b]) >= 2 && fwrite(h_payload + poff[b], 1, z[b], f) == z[b];
-        if (fclose(f) != 0 || !ok) err = _FILE_STREAM_FAILED;
-    }
+    err = write_shaf_file(p_shaf, nb, z, h_payload, poff);
 out:
     if (g) {
         if (d_sym) shafa_cuda_dev_free(g, d_sym);
@@ -131,11 +130,7 @@ out:
     }
     if (h_payload) cli_host_free(h_payload);
     if (!err) {
-        printf("Module: C (Symbol codes' codification) [libshafa_cuda]\nNumber of blocks: %llu\n", (unsigned long long)nb);
-        for (uint64_t b = 0; b < nb; b++)
-            printf("Size before/after & compression rate (Block %llu): %llu/%llu -> %d%%\n", (unsigned long long)b,
-                   (unsigned long long)sizes[b], (unsigned long long)z[b], (int)(((float)z[b] / sizes[b]) * 100));
-        printf("Module runtime (milliseconds): %f\nGenerated file %s\n", now_ms() - t0, p_shaf);
+        c_summary(nb, sizes, z, now_ms() - t0, p_shaf);
         free(*path); /* c.c:460-461 */
         *path = p_shaf;
         p_shaf = NULL;

@@ -20,14 +20,6 @@ static uint64_t rle_guess(uint64_t rle_block)
     return MIB_64 + KIB_1;
 }
 
-static _modules_error write_all(const char *path, const uint8_t *data, uint64_t n)
-{
-    FILE *f = fopen(path, "wb");
-    if (!f) return _FILE_INACCESSIBLE;
-    const bool ok = fwrite(data, 1, n, f) == n;
-    return (fclose(f) != 0 || !ok) ? _FILE_STREAM_FAILED : _SUCCESS;
-}
-
 static void summary(const char *what, double ms, const uint64_t *before, const uint64_t *after, uint64_t nb, const char *out_path)
 {
     printf("Module: D (%s decoding) [libshafa_cuda]\n", what);

@@ -10,34 +10,8 @@
 
 #include "util.h"
 
-/* f.c:89-119 body: a count is printed when it differs from the previous symbol's */
-static size_t freq_fields(const uint64_t *h, char *out)
-{
-    char *p = out;
-    for (int s = 0; s < 256; s++) {
-        if (s == 0 || h[s] != h[s - 1]) p += sprintf(p, "%llu", (unsigned long long)h[s]);
-        if (s != 255) *p++ = ';';
-    }
-    return (size_t)(p - out);
-}
-
-static _modules_error write_freq_file(const char *path, char mode, uint64_t nb, const uint64_t *sizes, const uint64_t *hist)
-{
-    FILE *f = fopen(path, "wb");
-    if (!f) return _FILE_INACCESSIBLE;
-    char fields[256 * 22];
-    bool ok = fprintf(f, "@%c@%llu", mode, (unsigned long long)nb) >= 4;
-    for (uint64_t b = 0; b < nb && ok; b++) {
-        const size_t k = freq_fields(hist + b * 256, fields);
-        ok = fprintf(f, "@%llu@", (unsigned long long)sizes[b]) >= 2 && fwrite(fields, 1, k, f) == k;
-    }
-    ok = ok && fputs("@0", f) >= 0;
-    if (fclose(f) != 0) ok = false;
-    return ok ? _SUCCESS : _FILE_STREAM_FAILED;
-}
-
-static void summary(uint64_t nb, const uint64_t *sizes, uint64_t n, const uint64_t *rle_sizes, double ms, const char *p_rle,
-                    const char *p_freq, const char *p_rle_freq)
+void f_summary(uint64_t nb, const uint64_t *sizes, uint64_t n, const uint64_t *rle_sizes, double ms, const char *p_rle,
+               const char *p_freq, const char *p_rle_freq)
 {
     printf("Module: f (calculation of symbol frequencies) [libshafa_cuda]\nNumber of blocks: %llu\n", (unsigned long long)nb);
     printf("Size of blocks analyzed in the original file: ");
@@ -150,7 +124,7 @@ out:
     blob_free(&in);
     if (!err) {
         const bool wrote_freq = !use_rle || force_freq;
-        summary(nb, sizes, n, rle_sizes, now_ms() - t0, use_rle ? p_rle : NULL, wrote_freq ? p_freq : NULL, use_rle ? p_rle_freq : NULL);
+        f_summary(nb, sizes, n, rle_sizes, now_ms() - t0, use_rle ? p_rle : NULL, wrote_freq ? p_freq : NULL, use_rle ? p_rle_freq : NULL);
         if (use_rle) { /* f.c:396-399 */
             free(*path);
             *path = p_rle;

@@ -31,6 +31,14 @@ static _modules_error parse_fields(const uint8_t *p, size_t len, uint64_t *h)
     return p == end ? _SUCCESS : _FILE_UNRECOGNIZABLE; /* t.c:61 */
 }
 
+void t_summary(uint64_t nb, const uint64_t *sizes, double ms, const char *p_cod)
+{
+    printf("Module:T (Calculation of symbol codes) [libshafa_cuda]\nNumber of blocks: %llu\nSize of blocks analyzed in the symbol file: ",
+           (unsigned long long)nb);
+    for (uint64_t b = 0; b < nb; b++) printf("%llu%s", (unsigned long long)sizes[b], b + 1 == nb ? " bytes\n" : "/");
+    printf("Module runtime (milliseconds): %f\nGenerated file %s\n", ms, p_cod);
+}
+
 _modules_error get_shafa_codes(const char *path)
 {
     const double t0 = now_ms();
@@ -109,38 +117,12 @@ _modules_error get_shafa_codes(const char *path)
         if ((err = gpu_status(shafa_cuda_memcpy_d2h(g, len, d_len, nb * 256)))) goto out;
         if ((err = gpu_status(shafa_cuda_synchronize(g)))) goto out;
     }
-    {
-        FILE *f = fopen(p_cod, "wb");
-        if (!f) {
-            err = _FILE_INACCESSIBLE;
-            goto out;
-        }
-        char *text = malloc(256 * 65 + 256);
-        bool ok = text && fprintf(f, "@%c@%llu", mode, (unsigned long long)nb) >= 3; /* t.c:302 */
-        for (uint64_t b = 0; b < nb && ok; b++) {
-            char *p = text;
-            for (int s = 0; s < 256; s++) { /* t.c:353-361: codes in symbol order joined by ';' */
-                const unsigned l = len[b * 256 + s];
-                const uint64_t v = code[b * 256 + s];
-                for (unsigned i = 0; i < l; i++) *p++ = ((v >> (l - 1 - i)) & 1) ? '1' : '0';
-                if (s != 255) *p++ = ';';
-            }
-            ok = fprintf(f, "@%llu@", (unsigned long long)sizes[b]) >= 2 && fwrite(text, 1, (size_t)(p - text), f) == (size_t)(p - text);
-        }
-        ok = ok && fputs("@0", f) >= 0; /* t.c:395-396 */
-        free(text);
-        if (fclose(f) != 0 || !ok) err = _FILE_STREAM_FAILED;
-    }
+    err = write_cod_file(p_cod, mode, nb, sizes, len, code);
 out:
     if (d_hist) shafa_cuda_dev_free(g, d_hist);
     if (d_code) shafa_cuda_dev_free(g, d_code);
     if (d_len) shafa_cuda_dev_free(g, d_len);
-    if (!err) {
-        printf("Module:T (Calculation of symbol codes) [libshafa_cuda]\nNumber of blocks: %llu\nSize of blocks analyzed in the symbol file: ",
-               (unsigned long long)nb);
-        for (uint64_t b = 0; b < nb; b++) printf("%llu%s", (unsigned long long)sizes[b], b + 1 == nb ? " bytes\n" : "/");
-        printf("Module runtime (milliseconds): %f\nGenerated file %s\n", now_ms() - t0, p_cod);
-    }
+    if (!err) t_summary(nb, sizes, now_ms() - t0, p_cod);
     blob_free(&in);
     free(sizes);
     free(hist);

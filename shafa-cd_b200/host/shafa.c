@@ -71,13 +71,22 @@ static bool parse_args(int argc, char *const argv[], options *o, const char **fi
 static _modules_error run_modules(const options *o, char **file)
 {
     _modules_error e;
-    if (o->f) {
+    bool f = o->f, t = o->t, c = o->c;
+    if (f && t && c && !getenv("SHAFA_NO_FUSE")) {
+        /* F, T and C in one invocation: one pass over the data, the .rle/.freq/.cod/.shaf files as side outputs */
+        if ((e = shafa_encode_fused(file, o->force_rle, o->force_freq, o->block_size))) {
+            fputs("Module f/t/c: Something went wrong while compressing...\n", stderr);
+            return e;
+        }
+        f = t = c = false;
+    }
+    if (f) {
         if ((e = freq_rle_compress(file, o->force_rle, o->force_freq, o->block_size))) {
             fputs("Module f: Something went wrong while compressing with RLE or creating frequencies' table...\n", stderr);
             return e;
         }
     }
-    if (o->t) {
+    if (t) {
         if (!o->f) { /* stand-alone T is given "<x>.freq" (shafa.c:167-181) */
             if (!check_ext(*file, FREQ_EXT)) {
                 fprintf(stderr, "Module t: Wrong extension... Should end in %s\n", FREQ_EXT);
@@ -93,7 +102,7 @@ static _modules_error run_modules(const options *o, char **file)
             return e;
         }
     }
-    if (o->c) {
+    if (c) {
         if (o->f && !o->t) {
             fputs("Module c: Can't execute module 'c' after 'f' without 't'...\n", stderr);
             return _OUTSIDE_MODULE;

@@ -1,31 +1,94 @@
 #include "util.h"
 
+#include <pthread.h>
 #include <stdlib.h>
 #include <string.h>
 #include <time.h>
 
 /* ---- GPU context ------------------------------------------------------------------- */
 
-static shafa_cuda_ctx *g_ctx;
+static shafa_cuda_multi *g_multi;
+static bool g_multi_tried;
+static pthread_mutex_t g_multi_lock = PTHREAD_MUTEX_INITIALIZER;
+static pthread_t g_prefetch_thread;
+static bool g_prefetch_running;
+
+/* "0-7", "0,2,5", "3" -> device list */
+static int parse_devices(const char *spec, int *devs, int cap)
+{
+    int n = 0;
+    const char *p = spec;
+    while (*p && n < cap) {
+        char *end;
+        const long a = strtol(p, &end, 10);
+        if (end == p || a < 0) return 0;
+        long b = a;
+        p = end;
+        if (*p == '-') {
+            b = strtol(p + 1, &end, 10);
+            if (end == p + 1 || b < a) return 0;
+            p = end;
+        }
+        for (long d = a; d <= b && n < cap; d++) devs[n++] = (int)d;
+        if (*p == ',') p++;
+        else if (*p) return 0;
+    }
+    return n;
+}
+
+shafa_cuda_multi *gpu_multi(void)
+{
+    pthread_mutex_lock(&g_multi_lock);
+    if (!g_multi_tried) {
+        g_multi_tried = true;
+        int devs[64], n = 0;
+        const char *spec = getenv("SHAFA_DEVICES");
+        if (spec && *spec) n = parse_devices(spec, devs, 64);
+        if (n == 0) {
+            const char *dev = getenv("SHAFA_DEVICE");
+            devs[0] = dev ? atoi(dev) : 0;
+            n = 1;
+        }
+        if (shafa_cuda_multi_create(devs, n, &g_multi) != SHAFA_SUCCESS) g_multi = NULL;
+    }
+    shafa_cuda_multi *m = g_multi;
+    pthread_mutex_unlock(&g_multi_lock);
+    return m;
+}
 
 shafa_cuda_ctx *gpu(void)
 {
-    if (!g_ctx) {
-        const char *dev = getenv("SHAFA_DEVICE");
-        if (shafa_cuda_create(dev ? atoi(dev) : 0, &g_ctx) != SHAFA_SUCCESS) g_ctx = NULL;
-    }
-    return g_ctx;
+    shafa_cuda_multi *m = gpu_multi();
+    return m ? shafa_cuda_multi_ctx(m, 0) : NULL;
+}
+
+static void *prefetch_main(void *arg)
+{
+    (void)arg;
+    gpu_multi();
+    return NULL;
+}
+
+void gpu_prefetch(void)
+{
+    if (g_prefetch_running || g_multi_tried) return;
+    g_prefetch_running = pthread_create(&g_prefetch_thread, NULL, prefetch_main, NULL) == 0;
 }
 
 void gpu_release(void)
 {
-    if (g_ctx) shafa_cuda_destroy(g_ctx);
-    g_ctx = NULL;
+    if (g_prefetch_running) {
+        pthread_join(g_prefetch_thread, NULL);
+        g_prefetch_running = false;
+    }
+    if (g_multi) shafa_cuda_multi_destroy(g_multi);
+    g_multi = NULL;
 }
 
 _modules_error gpu_status(int rc)
 {
-    if (rc != SHAFA_SUCCESS && g_ctx && getenv("SHAFA_VERBOSE")) fprintf(stderr, "libshafa_cuda: %s\n", shafa_cuda_last_error(g_ctx));
+    if (rc != SHAFA_SUCCESS && g_multi && getenv("SHAFA_VERBOSE"))
+        fprintf(stderr, "libshafa_cuda: %s | %s\n", shafa_cuda_last_error(shafa_cuda_multi_ctx(g_multi, 0)), shafa_cuda_multi_last_error(g_multi));
     return (_modules_error)rc;
 }
 

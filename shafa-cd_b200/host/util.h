@@ -23,8 +23,13 @@ bool check_ext(const char *path, const char *ext);
 char *add_ext(const char *path, const char *ext);
 char *rm_ext(const char *path);
 
-/* the process-wide GPU context (device from $SHAFA_DEVICE, default 0); NULL if no GPU */
+/* The process-wide GPU set: devices from $SHAFA_DEVICES ("0-7", "0,2,5"; one file is then sharded over them by
+ * block chunks, no collective), else $SHAFA_DEVICE, else device 0.  NULL if there is no usable GPU (no CPU fallback). */
+shafa_cuda_multi *gpu_multi(void);
+/* its first context (the per-module device calls run there) */
 shafa_cuda_ctx *gpu(void);
+/* start creating the contexts on a background thread: CUDA start-up then overlaps the reading of the input file */
+void gpu_prefetch(void);
 void gpu_release(void);
 /* libshafa_cuda status -> _modules_error (same numbering) */
 _modules_error gpu_status(int rc);
@@ -58,6 +63,20 @@ _modules_error cod_parse_fields(const uint8_t *p, size_t n, uint8_t *len, uint64
  * block is at least "@d@" plus 255 ';' = 258 bytes, so a count above file_size / 258 is a lie
  * (_FILE_UNRECOGNIZABLE) -- checked BEFORE anything is allocated from it. */
 bool block_count_plausible(uint64_t nb, uint64_t container_bytes);
+
+/* module summaries (stdout), shared with the fused path */
+void f_summary(uint64_t nb, const uint64_t *sizes, uint64_t n, const uint64_t *rle_sizes, double ms, const char *p_rle,
+               const char *p_freq, const char *p_rle_freq);
+void t_summary(uint64_t nb, const uint64_t *sizes, double ms, const char *p_cod);
+void c_summary(uint64_t nb, const uint64_t *sizes, const uint64_t *z, double ms, const char *p_shaf);
+/* fused.c: F, T and C of one invocation (shafa.c:293-298) in one pass over the data */
+_modules_error shafa_encode_fused(char **path, bool force_rle, bool force_freq, unsigned long block_size);
+
+/* container writers (containers.c) */
+_modules_error write_freq_file(const char *path, char mode, uint64_t nb, const uint64_t *sizes, const uint64_t *hist);
+_modules_error write_cod_file(const char *path, char mode, uint64_t nb, const uint64_t *sizes, const uint8_t *len, const uint64_t *code);
+_modules_error write_shaf_file(const char *path, uint64_t nb, const uint64_t *z, const uint8_t *payload, const uint64_t *poff);
+_modules_error write_all(const char *path, const uint8_t *data, uint64_t n);
 
 double now_ms(void);
 

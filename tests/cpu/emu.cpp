@@ -670,6 +670,153 @@ static Bytes emu_sf_decode(const Bytes &payload, uint64_t n, const uint8_t *len,
     return out;
 }
 
+
+// ------------------------------------------------------------------ fused single-pass decoder emulation (sf_decode_fused.cu)
+// Same control flow as k_dec_fused, sequence after sequence: speculative pass from bit 0 into record lists, rounds with
+// the assumed carry 0, "publish" the end, rounds with the true carry, verify the published end, compaction.
+struct EmuFusedView {
+    const uint64_t *pairs;
+    const uint32_t *lutp;
+    const uint64_t *sleft;
+    const uint8_t *slen, *ssym;
+    uint32_t *slots;   // [sub-sequence][DECF_CAP], addressed in bytes
+    uint8_t *heads;    // [sub-sequence][DECF_HEAD]
+    uint64_t pair(uint32_t slot) const { return pairs[slot]; }
+    uint32_t lp(uint32_t i) const { return lutp[i]; }
+    uint32_t ld32(uint32_t a) const { return slots[a / 4]; }
+    void st32(uint32_t a, uint32_t v) const { slots[a / 4] = v; }
+    void st8(uint32_t a, uint32_t v) const { heads[a] = (uint8_t)v; }
+};
+struct EmuFusedSub {
+    DecfMain mn;
+    uint32_t start, end, count, hn, jsp;
+};
+static int g_fused_specfail = 0, g_fused_kind[3] = {0, 0, 0};
+static Bytes emu_sf_decode_fused(const Bytes &payload, uint64_t n, const uint8_t *len, const uint64_t *code, bool &bad)
+{
+    EmuTables T;
+    emu_dec_tables(len, code, T);
+    std::vector<uint32_t> lutp(DEC_LUT_SIZE);
+    for (int e = 0; e < DEC_LUT_SIZE; e++) lutp[e] = decf_entry(T.lut.data(), (uint32_t)e);
+    const uint64_t z = payload.size();
+    const uint64_t nseq = (z + DEC_SEQ_BYTES - 1) / DEC_SEQ_BYTES;
+    Bytes out(n);
+    uint64_t first = 0;
+    uint32_t prev_end = 0;
+    bad = false;
+    std::vector<uint32_t> slots(DEC_THREADS * DECF_CAP);
+    std::vector<uint8_t> heads(DEC_THREADS * DECF_HEAD);
+    for (uint64_t seq = 0; seq < nseq; seq++) {
+        std::vector<uint64_t> pairs(DEC_PAIR_SLOTS, 0);
+        for (int sid = 0; sid < DEC_THREADS; sid++) {
+            uint32_t words[DEC_ROW_WORDS];
+            for (int i = 0; i < DEC_ROW_WORDS; i++) {
+                uint32_t w = 0;
+                for (int k = 0; k < 4; k++) {
+                    const uint64_t bo = seq * DEC_SEQ_BYTES + (uint64_t)sid * 16 + (uint64_t)i * 4 + k;
+                    w = (w << 8) | (bo < z ? payload[bo] : 0);
+                }
+                words[i] = w;
+            }
+            dec_row_from_words(words, pairs.data() + (size_t)sid * DEC_ROW);
+        }
+        EmuFusedView t{pairs.data(), lutp.data(), T.sleft, T.slen, T.ssym, slots.data(), heads.data()};
+        const uint64_t bits_left = (z - seq * DEC_SEQ_BYTES) * 8;
+        const uint32_t limit = (uint32_t)std::min<uint64_t>(bits_left, DEC_SEQ_BYTES * 8);
+        auto stop_of = [&](int tid) -> uint32_t {
+            const uint32_t sub_lo = tid * DEC_SUB_BITS;
+            return limit > sub_lo ? std::min<uint32_t>(limit - sub_lo, DEC_SUB_BITS) : 0u;
+        };
+        auto over = [](uint32_t end) { return end > (uint32_t)DEC_SUB_BITS ? end - DEC_SUB_BITS : 0u; };
+        EmuFusedSub u[DEC_THREADS];
+        uint32_t ends[DEC_THREADS];
+        for (int tid = 0; tid < DEC_THREADS; tid++) {
+            u[tid].mn = decf_pass(t, tid * DEC_ROW, tid * DECF_CAP * 4, 0u, stop_of(tid));
+            u[tid].start = 0;
+            u[tid].hn = u[tid].jsp = 0;
+            u[tid].count = u[tid].mn.k;
+            u[tid].end = u[tid].mn.end;
+            ends[tid] = over(u[tid].end);
+            if (u[tid].mn.bad) bad = true;
+        }
+        auto restart = [&](int tid, uint32_t s) {
+            EmuFusedSub &x = u[tid];
+            const uint32_t row = tid * DEC_ROW, slot = tid * DECF_CAP * 4, head = tid * DECF_HEAD, stop = stop_of(tid);
+            x.start = s;
+            const DecfSplice sp = decf_splice(t, row, slot, head, x.mn, s, stop);
+            g_fused_kind[sp.kind]++;
+            const uint32_t mrec = x.mn.norec ? 0u : x.mn.m;
+            if (sp.kind == 0) {
+                x.hn = sp.hn; x.jsp = sp.jsp; x.count = sp.hn + (x.mn.k - sp.kskip); x.end = x.mn.end;
+            } else if (sp.kind == 1) {
+                x.hn = sp.hn; x.jsp = mrec; x.count = sp.hn; x.end = sp.end;
+            } else {
+                x.mn = decf_pass(t, row, slot, s, stop);
+                x.hn = 0; x.jsp = 0; x.count = x.mn.k; x.end = x.mn.end;
+            }
+        };
+        auto rounds = [&](uint32_t carry) {
+            for (int iter = 0;; iter++) {
+                uint32_t want[DEC_THREADS];
+                for (int tid = 0; tid < DEC_THREADS; tid++) want[tid] = tid ? ends[tid - 1] : carry;   // snapshot (barrier)
+                bool any = false;
+                for (int tid = 0; tid < DEC_THREADS; tid++)
+                    if (want[tid] != u[tid].start) {
+                        any = true;
+                        restart(tid, want[tid]);
+                        ends[tid] = over(u[tid].end);
+                    }
+                if (!any) break;
+                CHECK(iter < 600, "fused rounds do not converge");
+            }
+        };
+        rounds(0);
+        const uint32_t end0 = ends[DEC_THREADS - 1];
+        if (seq != 0) {
+            rounds(prev_end);
+            if (ends[DEC_THREADS - 1] != end0) g_fused_specfail++;
+        }
+        prev_end = ends[DEC_THREADS - 1];
+        // counts, compaction (stage), copy-out clipped at n
+        uint32_t total = 0;
+        bool direct = false;
+        for (int tid = 0; tid < DEC_THREADS; tid++) {
+            total += u[tid].count;
+            direct |= u[tid].mn.norec != 0;
+        }
+        direct |= total > (uint32_t)(DEC_PAIR_SLOTS * 8);
+        Bytes stage(total + 2);
+        uint32_t d = 0;
+        for (int tid = 0; tid < DEC_THREADS; tid++) {
+            const uint32_t d0 = d;
+            if (!direct) {
+                for (uint32_t i = 0; i < u[tid].hn; i++) stage[d++] = heads[tid * DECF_HEAD + i];
+                const uint32_t mrec = u[tid].mn.norec ? 0u : u[tid].mn.m;
+                for (uint32_t j = u[tid].jsp; j < mrec; j++) {
+                    const uint32_t r = slots[tid * DECF_CAP + j];
+                    stage[d] = (uint8_t)r;
+                    if (r >> 29) stage[d + 1] = (uint8_t)(r >> 8);
+                    d += r >> 28;
+                }
+            } else {
+                uint32_t q = u[tid].start, b2 = 0;
+                const uint32_t stop = stop_of(tid);
+                while (q < stop) {
+                    const uint32_t e = decf_lookup(t, tid * DEC_ROW, q, &b2);
+                    stage[d++] = (uint8_t)e;
+                    q += decf_n(e) == 2u ? decf_len0(e) : decf_total(e);
+                }
+            }
+            CHECK(d - d0 == u[tid].count, "fused: compaction wrote %u symbols, count says %u (seq %llu sub %d)", d - d0, u[tid].count,
+                  (unsigned long long)seq, tid);
+        }
+        for (uint32_t i = 0; i < total && first + i < n; i++) out[first + i] = stage[i];
+        first += total;
+    }
+    if (first < n) bad = true;
+    return out;
+}
+
 static void test_sf_codec(std::mt19937 &rng)
 {
     int max_passes = 0;
@@ -717,6 +864,8 @@ static void test_sf_codec(std::mt19937 &rng)
         Bytes dec = emu_sf_decode(want, n, len, code, bad, &passes);
         max_passes = std::max(max_passes, passes);
         CHECK(!bad && dec == raw, "sf_decode rep %d n %zu", rep, n);
+        Bytes decf = emu_sf_decode_fused(want, n, len, code, bad);
+        CHECK(!bad && decf == raw, "sf_decode_fused rep %d n %zu kind %d maxlen %d", rep, n, kind, maxlen);
     }
     printf("sf codec: max stitch passes %d\n", max_passes);
     // long codes (> 12 bits) through the fallback search, decode only
@@ -742,7 +891,42 @@ static void test_sf_codec(std::mt19937 &rng)
         bool bad;
         Bytes dec = emu_sf_decode(enc, raw.size(), len, code, bad, nullptr);
         CHECK(!bad && dec == raw, "sf_decode long codes (max %d)", maxlen);
+        Bytes decf = emu_sf_decode_fused(enc, raw.size(), len, code, bad);
+        CHECK(!bad && decf == raw, "sf_decode_fused long codes (max %d)", maxlen);
     }
+    // larger inputs for the fused decoder: many sequences, skewed and near-uniform alphabets, two symbols (1-bit codes:
+    // the record lists overflow and the direct path runs)
+    for (int rep = 0; rep < 10; rep++) {
+        size_t n = 200000 + rng() % 300000;
+        Bytes raw(n);
+        if (rep < 4) {
+            raw = gen(rng, n, rep);
+        } else if (rep < 6) {
+            for (auto &v : raw) v = (uint8_t)(rng() & 1);
+        } else if (rep < 8) {
+            for (auto &v : raw) v = (uint8_t)((rng() % 100) < 90 ? 7 : (rng() % 5));
+        } else {
+            for (auto &v : raw) v = (uint8_t)(rng() % 200);
+        }
+        uint64_t hist[256];
+        orc_histogram(raw.data(), n, hist);
+        int distinct = 0;
+        for (int s2 = 0; s2 < 256; s2++) distinct += hist[s2] != 0;
+        if (distinct < 2) continue;
+        uint8_t len[256];
+        uint64_t code[256];
+        const int maxlen = orc_sf_codes_packed(hist, len, code);
+        static char codes[256][ORC_MAX_CODE];
+        codes_to_strings(len, code, codes);
+        Bytes enc((n * maxlen + 7) / 8 + 8);
+        enc.resize(orc_sf_encode_block(raw.data(), n, codes, enc.data()));
+        bool bad;
+        Bytes decf = emu_sf_decode_fused(enc, n, len, code, bad);
+        CHECK(!bad && decf == raw, "sf_decode_fused big rep %d n %zu maxlen %d", rep, n, maxlen);
+        if (getenv("EMU_VERBOSE")) printf("  big rep %d maxlen %d: cumulative met/left/rebuilt %d/%d/%d\n", rep, maxlen, g_fused_kind[0], g_fused_kind[1], g_fused_kind[2]);
+    }
+    printf("fused decoder: splices met/left/rebuilt %d/%d/%d, speculation failures %d\n", g_fused_kind[0], g_fused_kind[1], g_fused_kind[2],
+           g_fused_specfail);
 }
 
 int main()

@@ -189,3 +189,27 @@ def test_reference_driver_binding_matches_reference_files(case, tmp_path):
     shaf = "input.bin.rle.shaf" if rle else "input.bin.shaf"
     assert ref([shaf, "--no-multithread"]).returncode == 0                       # default -m d; the flag is accepted
     assert (tmp_path / "input.bin").read_bytes() == original
+
+
+@pytest.mark.gpu
+def test_cli_fused_equals_separate_modules_and_multi_device(pkg, tmp_path):
+    """`shafa f` (F, T, C fused in one pass) writes the same files as the three modules run one by one
+    (SHAFA_NO_FUSE=1) and as the same invocation sharded over several contexts (SHAFA_DEVICES)."""
+    import os
+    data = pkg.datagen.mixed4m(21 * 1024 * 1024 + 999, seed=31)
+    outs = {}
+    for tag, env in (("fused", {}), ("separate", {"SHAFA_NO_FUSE": "1"}), ("multi", {"SHAFA_DEVICES": "0,0,0"})):
+        d = tmp_path / tag
+        d.mkdir()
+        (d / "f").write_bytes(data.tobytes())
+        r = subprocess.run([str(BIN), "f", "-b", "K", "-c", "f"], cwd=d, capture_output=True, timeout=600, env={**os.environ, **env})
+        assert r.returncode == 0, r.stderr
+        outs[tag] = {p.name: p.read_bytes() for p in d.iterdir() if p.name != "f"}
+        assert sorted(outs[tag]) == ["f.freq", "f.rle", "f.rle.cod", "f.rle.freq", "f.rle.shaf"]
+        (d / "f").unlink()
+        r = subprocess.run([str(BIN), "f.rle.shaf", "-m", "d"], cwd=d, capture_output=True, timeout=600, env={**os.environ, **env})
+        assert r.returncode == 0 and (d / "f").read_bytes() == data.tobytes()
+        (d / "f").unlink()
+        r = subprocess.run([str(BIN), "f.rle", "-m", "d", "-d", "r"], cwd=d, capture_output=True, timeout=600, env={**os.environ, **env})
+        assert r.returncode == 0 and (d / "f").read_bytes() == data.tobytes()
+    assert outs["fused"] == outs["separate"] == outs["multi"]

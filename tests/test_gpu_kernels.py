@@ -382,3 +382,56 @@ def test_one_symbol_block_encode(shafa, pkg, case):
     with pytest.raises(pkg.ShafaError) as e:
         shafa.decode(enc)
     assert e.value.code == 4
+
+
+# ------------------------------------------------------------------ the fused single-pass decoder (opt-in: SHAFA_DECODE_FUSED=1)
+@pytest.fixture
+def fused_decoder(monkeypatch):
+    monkeypatch.setenv("SHAFA_DECODE_FUSED", "1")      # read by launch_sf_decode at every call
+    yield
+
+
+@pytest.mark.parametrize("gen,n,bs", [("textlike", 30_000_000, 8388608), ("zipf", 9_000_000, 655360), ("runheavy", 40_000_000, 8388608),
+                                      ("mixed4m", 26_000_000, 655360), ("uniform", 3_000_000, 655360), ("textlike", 70_001, 65536)])
+def test_fused_decoder_round_trips(shafa, orc, pkg, fused_decoder, gen, n, bs):
+    """k_dec_fused (speculative records + splice, chain warp, bulk async copies) against the oracle's symbol stream;
+    blocks with codes of nearly one length (uniform) are routed to the exact kernels inside the same call."""
+    data = pkg.datagen.GENERATORS[gen](n, seed=23)
+    enc = shafa.encode(data, bs)
+    before = shafa.profile_read() if False else None
+    shafa.profile(True); shafa.profile_reset()
+    sym = shafa.decode(enc, rle_expand=False)
+    stats = shafa.profile_read()
+    shafa.profile(False)
+    f = orc.module_f(data, bs)
+    assert_same(sym, f["rle"] if f["rle_mode"] else data.tobytes(), f"{gen}: fused -d s")
+    assert_same(shafa.decode(enc), data, f"{gen}: fused -m d")
+    if gen != "uniform":
+        assert "dec_fused" in stats, stats.keys()
+    _ = before
+
+
+def test_fused_decoder_golden_payloads(shafa, pkg, fused_decoder):
+    for case in small_cases():
+        d = GOLDEN / case
+        base = "input.bin.rle" if (d / "input.bin.rle").exists() else "input.bin"
+        mode, sizes, ln, cd = pkg.parse_cod((d / (base + ".cod")).read_bytes())
+        z, payload, offs = pkg.parse_shaf((d / (base + ".shaf")).read_bytes())
+        sym, _ = shafa.decode_tables(payload, offs, z, sizes, ln, cd, False, int(sizes.sum()) + 64)
+        assert_same(sym, (d / base).read_bytes(), f"{case}: fused -d s")
+
+
+def test_fused_decoder_speculation_failure_falls_back(shafa, orc, pkg, fused_decoder):
+    """A three-symbol alphabet with codes 0 / 10 / 11 and data that is all '10 10 10 ...' re-synchronises only by luck:
+    whatever the fused kernel guesses is verified, and a wrong guess is decoded again by the exact kernels."""
+    rng = np.random.default_rng(4)
+    data = np.full(3_000_000, 66, dtype=np.uint8)
+    data[rng.integers(0, data.size, size=40)] = 65           # a few 'A' (code 0) and 'C'
+    data[rng.integers(0, data.size, size=40)] = 67
+    data[:3] = [65, 66, 67]
+    hist = orc.histogram(data)
+    ln, cd, _ = orc.sf_codes_packed(hist)
+    payload = orc.sf_encode_block(data, orc.sf_codes(hist))
+    sym, _ = shafa.decode_tables(np.concatenate([payload, np.zeros(32, np.uint8)]), [0], [payload.size], [data.size], ln[None], cd[None], False,
+                                 data.size + 64)
+    assert_same(sym, data, "low-synchronisation code")

@@ -1,7 +1,8 @@
 #!/usr/bin/env python3
 """Per-source-line instruction and stall-sample shares of one kernel in an .ncu-rep.
 
-usage: tools/ncu_lines.py REPORT.ncu-rep KERNEL_REGEX [TOP] [inst|stall]
+usage: tools/ncu_lines.py REPORT.ncu-rep KERNEL_REGEX [TOP] [inst|stall] [SKIP]
+SKIP: matching launches to skip first (template variants share one function name).
 Needs a capture made with --import-source on and code built with -lineinfo.
 """
 import csv
@@ -14,8 +15,10 @@ def main():
     rep, rx = sys.argv[1], sys.argv[2]
     top = int(sys.argv[3]) if len(sys.argv) > 3 else 40
     key = sys.argv[4] if len(sys.argv) > 4 else "stall"
+    skip = sys.argv[5] if len(sys.argv) > 5 else "0"
     txt = subprocess.run(
-        ["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass,cuda", "-k", "regex:" + rx],
+        ["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass,cuda", "-k", "regex:" + rx, "--launch-skip", skip,
+         "--launch-count", "1"],
         capture_output=True, text=True).stdout
     cur_file, hdr, lines = None, None, []
     for r in csv.reader(io.StringIO(txt)):
