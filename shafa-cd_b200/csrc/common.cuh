@@ -303,4 +303,20 @@ __device__ __forceinline__ uint32_t find_block(const uint64_t *__restrict__ tile
     return lo;
 }
 
+// The same for a warp that walks tickets in increasing order and remembers the block of its last ticket: the 32
+// lanes probe the next 32 blocks at once (one load latency instead of a dependent binary search); only a jump
+// past them falls back to the search.  All lanes return the block.
+__device__ __forceinline__ uint32_t find_block_forward(const uint64_t *__restrict__ tile0, uint32_t nb, uint64_t t, uint32_t from)
+{
+    const uint32_t cand = from + lane_id();
+    const bool ok = cand < nb && __ldg(tile0 + cand) <= t;
+    const unsigned m = __ballot_sync(FULL, ok);  // lane 0 is set: tile0[from] <= t by construction
+    if (m == FULL && from + 32u < nb) {          // maybe further ahead than this window
+        uint32_t b = 0;
+        if (lane_id() == 0) b = from + 31u + find_block(tile0 + from + 31u, nb - (from + 31u), t);
+        return __shfl_sync(FULL, b, 0);
+    }
+    return from + (31u - (uint32_t)__clz((int)m));
+}
+
 }  // namespace shafa

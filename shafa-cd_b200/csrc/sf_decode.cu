@@ -552,7 +552,7 @@ k_dec_scan(DecPlan plan, const uint32_t *__restrict__ seq_count, uint64_t *__res
 struct DecWriteShared {
     DecShared d;
     alignas(16) uint32_t lut3[DEC_LUT_SIZE];
-    alignas(16) uint8_t stage[DEC_STAGE + 32];
+    alignas(16) uint8_t stage[DEC_STAGE + 48];  // + the destination's misalignment (< 16)
 };
 
 // Sink of the write pass: the thread's symbols go to consecutive shared byte addresses from `base`.  CHECKED
@@ -628,6 +628,7 @@ k_dec_write(const uint8_t *__restrict__ payload, DecPlan plan, DecTablesGlobal g
             for (int i = tid; i < DEC_LUT_SIZE * 4 / 16; i += DEC_THREADS) dst3[i] = src3[i];
         }
         dec_store_row(sh.pairs, cur.row, z, sib);  // read back by this thread only
+        if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the previous sequence's bulk store has read the stage
         uint32_t total;
         // the scan's barriers also fence the table loads above and the previous sequence's copy-out
         const uint32_t excl = block_excl_scan<DEC_THREADS>(sub_count(rec), sh.scan, &total);
@@ -643,7 +644,12 @@ k_dec_write(const uint8_t *__restrict__ payload, DecPlan plan, DecTablesGlobal g
             uint8_t *gdst = out + plan.out_off[b] + sfirst;
             const uint32_t room = excl < seq_syms ? seq_syms - excl : 0u;
             if (seq_syms <= (uint32_t)DEC_STAGE) {
-                uint32_t dst_s = smem_u32(ws.stage) + excl;  // explicit st.shared: no generic address in the loop
+                // the sequence's place in the output is known before it is decoded (k_dec_scan), so the symbols are staged
+                // CO-ALIGNED with their destination: stage byte (gdst & 15) + i is output byte i, and everything between
+                // the first and the last 16-byte boundary leaves through ONE bulk async store (cp.async.bulk shared ->
+                // global, "TMA" 1-D) issued by one thread
+                const uint32_t mis = (uint32_t)((uintptr_t)gdst & 15u);
+                uint32_t dst_s = smem_u32(ws.stage) + mis + excl;  // explicit st.shared: no generic address in the loop
                 asm volatile("" : "+r"(dst_s));
                 DecSub r;
                 if (seq_room >= total) {  // every symbol of this sequence is real (all but a block's last sequences)
@@ -654,8 +660,20 @@ k_dec_write(const uint8_t *__restrict__ payload, DecPlan plan, DecTablesGlobal g
                     r = dec_emit_to(t, tid * DEC_ROW, sub_start(rec), stop, sink);
                 }
                 bad |= r.bad && room;
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // my stores to the stage, before the bulk copy reads them
                 __syncthreads();
-                copy_out_unaligned<DEC_THREADS>(gdst, ws.stage, seq_syms);
+                {
+                    const uint32_t head = mis ? (16u - mis) : 0u;                       // bytes before the first 16-byte boundary
+                    const uint32_t h = head < seq_syms ? head : seq_syms;
+                    const uint32_t body = (seq_syms - h) & ~15u;                         // whole 16-byte groups
+                    if (tid == 0 && body)
+                        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n\tcp.async.bulk.commit_group;" ::"l"(gdst + h),
+                                     "r"(smem_u32(ws.stage) + mis + h), "r"(body)
+                                     : "memory");
+                    if (tid >= 32 && tid < 32 + h) gdst[tid - 32] = ws.stage[mis + tid - 32];
+                    const uint32_t done = h + body;
+                    if (tid >= 64 && tid < 64 + (seq_syms - done)) gdst[done + tid - 64] = ws.stage[mis + done + tid - 64];
+                }
             } else {
                 uint8_t *dst = gdst + excl;
                 const DecSub r = dec_emit_subsequence(t, tid * DEC_ROW, sub_start(rec), stop, [&](uint32_t i, uint32_t sym) {
@@ -668,6 +686,7 @@ k_dec_write(const uint8_t *__restrict__ payload, DecPlan plan, DecTablesGlobal g
         rec = rec_nxt;
         sfirst = sfirst_nxt;
     }
+    if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // the last bulk store has completed
     // a bad window only matters if it produced one of the n real symbols
     if (bad) atomicOr(err, (uint32_t)ERR_BAD_WINDOW);
 }

@@ -29,6 +29,7 @@ _modules_error shafa_compress(char **const path)
         free(p_shaf);
         return _LACK_OF_MEMORY;
     }
+    gpu_prefetch(); /* CUDA start-up overlaps the reads */
     blob cod = {0}, sym = {0};
     _modules_error err = blob_read(p_cod, &cod);
     free(p_cod);

@@ -29,39 +29,6 @@ static void summary(const char *what, double ms, const uint64_t *before, const u
     printf("Module runtime (in milliseconds): %f\nGenerated file %s\n", ms, out_path);
 }
 
-/* expand nb RLE blocks that already sit on the device; returns pinned host output */
-static _modules_error expand_on_device(shafa_cuda_ctx *g, const void *d_rle, const uint64_t *offsets, uint64_t nb, uint64_t *fin,
-                                       uint8_t **h_out, uint64_t *out_size)
-{
-    uint64_t cap = 0;
-    for (uint64_t b = 0; b < nb; b++) cap += rle_guess(offsets[b + 1] - offsets[b]);
-    _modules_error err = _SUCCESS;
-    void *d_out = NULL;
-    for (int attempt = 0; attempt < 2; attempt++) {
-        d_out = shafa_cuda_dev_alloc(g, cap + 64);
-        if (!d_out) return _LACK_OF_MEMORY;
-        err = gpu_status(shafa_cuda_rle_decode_blocks(g, d_rle, offsets, nb, d_out, cap, fin));
-        if (err != _LACK_OF_MEMORY || attempt) break;
-        /* the guess was too small (d.c:154-170 grows stepwise); sizes are exact now */
-        shafa_cuda_dev_free(g, d_out);
-        d_out = NULL;
-        cap = 0;
-        for (uint64_t b = 0; b < nb; b++) cap += fin[b];
-    }
-    if (!err) {
-        uint64_t tot = 0;
-        for (uint64_t b = 0; b < nb; b++) tot += fin[b];
-        *h_out = cli_host_alloc(tot + 16);
-        if (!*h_out)
-            err = _LACK_OF_MEMORY;
-        else if (!(err = gpu_status(shafa_cuda_memcpy_d2h(g, *h_out, d_out, tot))))
-            err = gpu_status(shafa_cuda_synchronize(g));
-        *out_size = tot;
-    }
-    if (d_out) shafa_cuda_dev_free(g, d_out);
-    return err;
-}
-
 _modules_error rle_decompress(char **const path)
 {
     const double t0 = now_ms();
@@ -74,8 +41,8 @@ _modules_error rle_decompress(char **const path)
     blob rle = {0}, freq = {0};
     uint64_t nb = 0, *offsets = NULL, *sizes = NULL, *fin = NULL, out_size = 0;
     uint8_t *h_out = NULL;
-    void *d_rle = NULL;
-    shafa_cuda_ctx *g = NULL;
+    shafa_cuda_multi *m = NULL;
+    gpu_prefetch(); /* CUDA start-up overlaps the reads */
     _modules_error err = blob_read(*path, &rle);
     if (!err) err = blob_read(p_freq, &freq);
     free(p_freq);
@@ -116,23 +83,32 @@ _modules_error rle_decompress(char **const path)
             goto out;
         }
     }
-    g = gpu();
-    if (!g) {
+    m = gpu_multi();
+    if (!m) {
         err = _THREAD_CREATION_FAILED;
         goto out;
     }
     if (nb) {
-        d_rle = shafa_cuda_dev_alloc(g, offsets[nb] + 64);
-        if (!d_rle) {
-            err = _LACK_OF_MEMORY;
-            goto out;
+        /* all blocks through the chunked multi-stream (multi-GPU) expansion; the reference's first guess per block
+         * (d.c:129-136) sizes the output, the exact total comes back if that was too small (d.c:154-170 grows) */
+        uint64_t cap = 0;
+        for (uint64_t b = 0; b < nb; b++) cap += rle_guess(sizes[b]);
+        for (int attempt = 0; attempt < 2; attempt++) {
+            h_out = cli_host_alloc(cap + 64);
+            if (!h_out) {
+                err = _LACK_OF_MEMORY;
+                goto out;
+            }
+            err = gpu_status(shafa_cuda_rle_decode_host_multi(m, rle.data, offsets, nb, h_out, cap, &out_size, fin));
+            if (err != _LACK_OF_MEMORY || attempt || out_size <= cap) break;
+            cli_host_free(h_out);
+            h_out = NULL;
+            cap = out_size;
         }
-        if ((err = gpu_status(shafa_cuda_memcpy_h2d(g, d_rle, rle.data, offsets[nb])))) goto out;
-        if ((err = expand_on_device(g, d_rle, offsets, nb, fin, &h_out, &out_size))) goto out;
+        if (err) goto out;
     }
     err = write_all(p_out, h_out, out_size); /* d.c:218 */
 out:
-    if (g && d_rle) shafa_cuda_dev_free(g, d_rle);
     if (h_out) cli_host_free(h_out);
     if (!err) {
         summary("RLE", now_ms() - t0, sizes, fin, nb, p_out);
@@ -167,8 +143,8 @@ _modules_error shafa_decompress(char **const path, const bool decompress_rle)
     blob shaf = {0}, cod = {0};
     uint64_t nb = 0, nb_shaf = 0, *z = NULL, *poff = NULL, *n = NULL, *offsets = NULL, *fin = NULL, *code = NULL, out_size = 0;
     uint8_t *len = NULL, *h_payload = NULL, *h_out = NULL;
-    void *d_payload = NULL, *d_len = NULL, *d_code = NULL, *d_sym = NULL;
-    shafa_cuda_ctx *g = NULL;
+    shafa_cuda_multi *m = NULL;
+    gpu_prefetch(); /* CUDA start-up overlaps the reads */
     _modules_error err = blob_read(*path, &shaf);
     if (!err) err = blob_read(p_cod, &cod);
     free(p_cod);
@@ -229,47 +205,31 @@ _modules_error shafa_decompress(char **const path, const bool decompress_rle)
         }
         offsets[b + 1] = offsets[b] + n[b];
     }
-    g = gpu();
-    if (!g) {
+    m = gpu_multi();
+    if (!m) {
         err = _THREAD_CREATION_FAILED;
         goto out;
     }
     if (nb) {
-        const uint64_t stotal = offsets[nb];
-        d_payload = shafa_cuda_dev_alloc(g, ptotal + 64);
-        d_len = shafa_cuda_dev_alloc(g, nb * 256);
-        d_code = shafa_cuda_dev_alloc(g, nb * 256 * 8);
-        d_sym = shafa_cuda_dev_alloc(g, stotal + 64);
-        if (!d_payload || !d_len || !d_code || !d_sym) {
-            err = _LACK_OF_MEMORY;
-            goto out;
-        }
-        if ((err = gpu_status(shafa_cuda_memcpy_h2d(g, d_payload, h_payload, ptotal)))) goto out;
-        if ((err = gpu_status(shafa_cuda_memcpy_h2d(g, d_len, len, nb * 256)))) goto out;
-        if ((err = gpu_status(shafa_cuda_memcpy_h2d(g, d_code, code, nb * 256 * 8)))) goto out;
-        if ((err = gpu_status(shafa_cuda_sf_decode_blocks(g, d_payload, poff, z, n, nb, d_len, d_code, d_sym, stotal + 64)))) goto out;
-        if (decompress_rle) { /* d.c:574-586 */
-            if ((err = expand_on_device(g, d_sym, offsets, nb, fin, &h_out, &out_size))) goto out;
-        } else {
-            h_out = cli_host_alloc(stotal + 16);
+        /* SF decode (+ RLE expansion, d.c:574-586) of all blocks: chunks of blocks on worker streams of every device */
+        uint64_t cap = 0;
+        for (uint64_t b = 0; b < nb; b++) cap += decompress_rle ? rle_guess(n[b]) : n[b];
+        for (int attempt = 0; attempt < 2; attempt++) {
+            h_out = cli_host_alloc(cap + 64);
             if (!h_out) {
                 err = _LACK_OF_MEMORY;
                 goto out;
             }
-            if ((err = gpu_status(shafa_cuda_memcpy_d2h(g, h_out, d_sym, stotal)))) goto out;
-            if ((err = gpu_status(shafa_cuda_synchronize(g)))) goto out;
-            out_size = stotal;
-            memcpy(fin, n, nb * sizeof *fin);
+            err = gpu_status(shafa_cuda_decode_host_multi(m, h_payload, poff, z, n, nb, len, code, decompress_rle, h_out, cap, &out_size, fin));
+            if (err != _LACK_OF_MEMORY || attempt || out_size <= cap) break;
+            cli_host_free(h_out);
+            h_out = NULL;
+            cap = out_size;
         }
+        if (err) goto out;
     }
     err = write_all(p_out, h_out, out_size); /* d.c:613 */
 out:
-    if (g) {
-        if (d_payload) shafa_cuda_dev_free(g, d_payload);
-        if (d_len) shafa_cuda_dev_free(g, d_len);
-        if (d_code) shafa_cuda_dev_free(g, d_code);
-        if (d_sym) shafa_cuda_dev_free(g, d_sym);
-    }
     if (h_payload) cli_host_free(h_payload);
     if (h_out) cli_host_free(h_out);
     if (!err) {

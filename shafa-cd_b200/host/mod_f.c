@@ -38,6 +38,7 @@ _modules_error freq_rle_compress(char **const path, const bool force_rle, const 
     if (bs == 0) bs = 524288;                    /* utils/file.c:62 */
     if (bs < 512) bs = 512;                      /* utils/file.c:63 */
 
+    gpu_prefetch(); /* CUDA start-up overlaps the reads */
     blob in;
     _modules_error err = blob_read(*path, &in);
     if (err) return err;

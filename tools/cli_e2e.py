@@ -96,7 +96,14 @@ def main():
                                 "cores": os.cpu_count()}
             out["reference"]["one_process_encode"] = run_combined(ref, Path(td), data)
             out["files_identical"] = (o["digests"] == r["digests"])
-            out["speedup"] = round(out["ours"]["gbs"] / out["reference"]["gbs"], 1)
+            out["speedup"] = round(out["ours"]["gbs"] / out["reference"]["gbs"], 2)
+            oo, rr = out["ours"]["one_process_encode"]["seconds"], out["reference"]["one_process_encode"]["seconds"]
+            out["speedup_one_process_encode"] = round(rr["FTC"] / oo["FTC"], 2)     # `shafa x -b m` (F, T, C fused in one pass)
+            out["speedup_decode"] = round(rr["D"] / oo["D"], 2)                      # `shafa x.rle.shaf -m d`
+        # where the fused invocation spends its time (stderr of SHAFA_VERBOSE=1)
+        (Path(td) / "x").write_bytes(data)
+        r = subprocess.run([str(ours), "x", "-b", "m"], cwd=td, stdout=subprocess.PIPE, stderr=subprocess.PIPE, env={**os.environ, "SHAFA_VERBOSE": "1"})
+        out["ours"]["fused_breakdown"] = [l for l in r.stderr.decode(errors="replace").splitlines() if l.startswith("fused")]
     print(json.dumps(out))
 
 
