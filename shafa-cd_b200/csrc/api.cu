@@ -237,6 +237,10 @@ int shafa_cuda_destroy(shafa_cuda_ctx *ctx)
     for (int i = 0; i < SCR_COUNT; i++)
         if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    for (int i = 0; i < 2; i++) {
+        if (ctx->bounce[i]) cudaFreeHost(ctx->bounce[i]);
+        if (ctx->bounce_ev[i]) cudaEventDestroy(ctx->bounce_ev[i]);
+    }
     for (auto e : ctx->event_pool) cudaEventDestroy(e);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;

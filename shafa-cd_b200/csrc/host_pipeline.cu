@@ -58,6 +58,76 @@ bool gather_workers(shafa_cuda_ctx *const *ctxs, int n_ctx, std::vector<shafa_cu
     return true;
 }
 
+// ---- copies from / to PAGEABLE host memory ------------------------------------------------------------------
+// cudaMemcpyAsync on pageable memory goes through the driver's own staging at a few GB/s and blocks the calling
+// thread.  A caller that cannot pin its buffers (the `shafa` CLI reads a file once: pinning a GiB costs more than it
+// saves) gets the same effect from two small pinned bounce buffers per worker: memcpy into one while the other is
+// on the wire.  Several workers run side by side, so the host memcpy bandwidth adds up.
+constexpr size_t BOUNCE_BYTES = 8u << 20;
+
+bool is_pageable(const void *p)
+{
+    if (!p) return false;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return true;
+    }
+    return a.type == cudaMemoryTypeUnregistered;
+}
+
+bool bounce_ready(shafa_cuda_ctx *w)
+{
+    if (w->bounce_cap) return true;
+    for (int i = 0; i < 2; i++) {
+        if (cudaHostAlloc((void **)&w->bounce[i], BOUNCE_BYTES, cudaHostAllocDefault) != cudaSuccess ||
+            cudaEventCreateWithFlags(&w->bounce_ev[i], cudaEventDisableTiming) != cudaSuccess) {
+            cudaGetLastError();
+            return false;
+        }
+    }
+    w->bounce_cap = BOUNCE_BYTES;
+    return true;
+}
+
+int copy_h2d(shafa_cuda_ctx *w, void *d_dst, const uint8_t *h_src, size_t bytes, bool pageable)
+{
+    if (!pageable || bytes < (1u << 20) || !bounce_ready(w)) return shafa_cuda_memcpy_h2d(w, d_dst, h_src, bytes);
+    int k = 0;
+    for (size_t off = 0; off < bytes; off += BOUNCE_BYTES, k ^= 1) {
+        const size_t piece = bytes - off < BOUNCE_BYTES ? bytes - off : BOUNCE_BYTES;
+        SHAFA_CUDA_TRY(w, cudaEventSynchronize(w->bounce_ev[k]));  // the copy that last used this buffer is done
+        memcpy(w->bounce[k], h_src + off, piece);
+        SHAFA_CUDA_TRY(w, cudaMemcpyAsync((uint8_t *)d_dst + off, w->bounce[k], piece, cudaMemcpyHostToDevice, w->stream));
+        SHAFA_CUDA_TRY(w, cudaEventRecord(w->bounce_ev[k], w->stream));
+    }
+    return SHAFA_SUCCESS;
+}
+
+int copy_d2h(shafa_cuda_ctx *w, uint8_t *h_dst, const void *d_src, size_t bytes, bool pageable)
+{
+    if (!pageable || bytes < (1u << 20) || !bounce_ready(w)) return shafa_cuda_memcpy_d2h(w, h_dst, d_src, bytes);
+    // piece i travels into buffer i & 1 while piece i - 1 is copied out of the other one
+    size_t prev_off = 0, prev_piece = 0;
+    int k = 0;
+    for (size_t off = 0; off < bytes; off += BOUNCE_BYTES, k ^= 1) {
+        const size_t piece = bytes - off < BOUNCE_BYTES ? bytes - off : BOUNCE_BYTES;
+        SHAFA_CUDA_TRY(w, cudaMemcpyAsync(w->bounce[k], (const uint8_t *)d_src + off, piece, cudaMemcpyDeviceToHost, w->stream));
+        SHAFA_CUDA_TRY(w, cudaEventRecord(w->bounce_ev[k], w->stream));
+        if (prev_piece) {
+            SHAFA_CUDA_TRY(w, cudaEventSynchronize(w->bounce_ev[k ^ 1]));
+            memcpy(h_dst + prev_off, w->bounce[k ^ 1], prev_piece);
+        }
+        prev_off = off;
+        prev_piece = piece;
+    }
+    if (prev_piece) {
+        SHAFA_CUDA_TRY(w, cudaEventSynchronize(w->bounce_ev[k ^ 1]));
+        memcpy(h_dst + prev_off, w->bounce[k ^ 1], prev_piece);
+    }
+    return SHAFA_SUCCESS;
+}
+
 struct Chain {
     std::mutex m;
     std::condition_variable cv;
@@ -188,6 +258,7 @@ int encode_host_pipelined(shafa_cuda_ctx *const *ctxs, int n_ctx, const uint8_t 
     std::atomic<uint64_t> next{0};
     std::atomic<int> err{0};
     const bool rle_mode = out->rle_mode, want_orig = out->hist_orig != nullptr;
+    const bool in_pageable = is_pageable(h_in), rle_pageable = is_pageable(out->rle), pay_pageable = is_pageable(out->payload);
 
     std::mutex err_m;
     std::string err_text;
@@ -216,7 +287,7 @@ int encode_host_pipelined(shafa_cuda_ctx *const *ctxs, int n_ctx, const uint8_t 
             uint64_t *d_code = (uint64_t *)scratch_get(w, SCR_STAGE_D, cb * 256 * (sizeof(uint64_t) + 1));
             if (!d_in || !d_hist || !d_code) return fail(SHAFA_LACK_OF_MEMORY);
             uint8_t *d_len = (uint8_t *)(d_code + cb * 256);
-            if ((r = shafa_cuda_memcpy_h2d(w, d_in, h_in + lo, cn))) return fail(r);
+            if ((r = copy_h2d(w, d_in, h_in + lo, cn, in_pageable))) return fail(r);
             std::vector<uint64_t> offsets(cb + 1, 0);
             const uint8_t *d_sym = d_in;
             if (rle_mode) {
@@ -230,7 +301,7 @@ int encode_host_pipelined(shafa_cuda_ctx *const *ctxs, int n_ctx, const uint8_t 
                 if (!rle_chain.wait(c, &base)) return;
                 if (base + tot > rle_cap) return fail(SHAFA_LACK_OF_MEMORY);
                 rle_chain.publish(c + 1, base + tot);
-                if ((r = shafa_cuda_memcpy_d2h(w, out->rle + base, d_rle, tot))) return fail(r);
+                if ((r = copy_d2h(w, out->rle + base, d_rle, tot, rle_pageable))) return fail(r);
                 d_sym = d_rle;
                 if (want_orig) {  // f.c:322-331: the original's histograms too
                     uint64_t *d_ho = (uint64_t *)scratch_get(w, SCR_STAGE_E, cb * 256 * sizeof(uint64_t));
@@ -262,7 +333,7 @@ int encode_host_pipelined(shafa_cuda_ctx *const *ctxs, int n_ctx, const uint8_t 
             if (pbase + ptot > pay_cap) return fail(SHAFA_LACK_OF_MEMORY);
             pay_chain.publish(c + 1, pbase + ptot);
             for (uint64_t b = b0; b < b1; b++) out->payload_offsets[b] += pbase;
-            if ((r = shafa_cuda_memcpy_d2h(w, out->payload + pbase, d_payload, ptot))) return fail(r);
+            if ((r = copy_d2h(w, out->payload + pbase, d_payload, ptot, pay_pageable))) return fail(r);
             if ((r = shafa_cuda_synchronize(w))) return fail(r);
         }
     };
@@ -319,6 +390,7 @@ int decode_host_pipelined(shafa_cuda_ctx *const *ctxs, int n_ctx, const uint8_t 
     std::vector<shafa_cuda_ctx *> workers;
     if (!gather_workers(ctxs, n_ctx, workers)) return set_error(ctx, SHAFA_LACK_OF_MEMORY, "pipelined decode: worker contexts could not be created");
     const Chunks ch = plan_chunks(nb, sym_total, workers.size());
+    const bool in_pageable = is_pageable(h_payload ? h_payload : h_sym), out_pageable = is_pageable(h_out);
     Chain out_chain(ch.count);
     std::atomic<uint64_t> next{0};
     std::atomic<int> err{0};
@@ -353,7 +425,7 @@ int decode_host_pipelined(shafa_cuda_ctx *const *ctxs, int n_ctx, const uint8_t 
                 for (uint64_t b = 0; b < cb; b++) offsets[b + 1] = offsets[b] + h_n[b0 + b];
                 uint8_t *d_sym = (uint8_t *)scratch_get(w, SCR_STAGE_B, round16(stot) + 64);
                 if (!d_sym) return fail(SHAFA_LACK_OF_MEMORY);
-                if ((r = shafa_cuda_memcpy_h2d(w, d_sym, h_sym + slo, stot))) return fail(r);
+                if ((r = copy_h2d(w, d_sym, h_sym + slo, stot, in_pageable))) return fail(r);
                 uint64_t cap = 0;
                 for (uint64_t b = 0; b < cb; b++) {
                     const uint64_t s = h_n[b0 + b];
@@ -376,7 +448,7 @@ int decode_host_pipelined(shafa_cuda_ctx *const *ctxs, int n_ctx, const uint8_t 
                 if (!out_chain.wait(c, &base)) return;
                 out_chain.publish(c + 1, base + produced);
                 if (base + produced <= out_capacity) {
-                    if ((r = shafa_cuda_memcpy_d2h(w, h_out + base, d_out, produced))) return fail(r);
+                    if ((r = copy_d2h(w, h_out + base, (const uint8_t *)d_out, produced, out_pageable))) return fail(r);
                     if ((r = shafa_cuda_synchronize(w))) return fail(r);
                 }
                 continue;
@@ -401,7 +473,7 @@ int decode_host_pipelined(shafa_cuda_ctx *const *ctxs, int n_ctx, const uint8_t 
             uint64_t *d_code = (uint64_t *)scratch_get(w, SCR_STAGE_D, cb * 256 * (sizeof(uint64_t) + 1));
             if (!d_payload || !d_sym || !d_code) return fail(SHAFA_LACK_OF_MEMORY);
             uint8_t *d_len = (uint8_t *)(d_code + cb * 256);
-            if ((r = shafa_cuda_memcpy_h2d(w, d_payload, h_payload + plo, phi - plo))) return fail(r);
+            if ((r = copy_h2d(w, d_payload, h_payload + plo, phi - plo, in_pageable))) return fail(r);
             if ((r = shafa_cuda_memcpy_h2d(w, d_code, h_code + b0 * 256, cb * 256 * sizeof(uint64_t)))) return fail(r);
             if ((r = shafa_cuda_memcpy_h2d(w, d_len, h_len + b0 * 256, cb * 256))) return fail(r);
             if ((r = shafa_cuda_sf_decode_blocks(w, d_payload, poff.data(), h_z + b0, h_n + b0, cb, d_len, d_code, d_sym,
@@ -438,7 +510,7 @@ int decode_host_pipelined(shafa_cuda_ctx *const *ctxs, int n_ctx, const uint8_t 
             if (!out_chain.wait(c, &base)) return;
             out_chain.publish(c + 1, base + produced);
             if (base + produced <= out_capacity) {
-                if ((r = shafa_cuda_memcpy_d2h(w, h_out + base, d_result, produced))) return fail(r);
+                if ((r = copy_d2h(w, h_out + base, d_result, produced, out_pageable))) return fail(r);
                 if ((r = shafa_cuda_synchronize(w))) return fail(r);
             }  // else: keep going so that the total size is reported (the caller may retry with a larger buffer)
         }

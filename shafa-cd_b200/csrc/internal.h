@@ -64,6 +64,10 @@ struct shafa_cuda_ctx {
     shafa_cuda_ctx *workers[4] = {nullptr, nullptr, nullptr, nullptr};
     // per-context (= per-device) cache of kernel attributes / occupancy, see shafa::OccId
     int occ[16] = {0};
+    // pinned bounce buffers for copies from / to PAGEABLE host memory (host_pipeline.cu): 2 x bounce_cap bytes
+    uint8_t *bounce[2] = {nullptr, nullptr};
+    cudaEvent_t bounce_ev[2] = {nullptr, nullptr};
+    size_t bounce_cap = 0;
 };
 
 namespace shafa {

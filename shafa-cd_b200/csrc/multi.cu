@@ -9,6 +9,7 @@
 // reduced or gathered between GPUs, so NCCL/NVLink are not used; the only file-wide scalar is block
 // 0's R/N decision (f.c:246-258), taken on the first device before the other chunks start.
 #include <stdlib.h>
+#include <sys/mman.h>
 
 #include <new>
 
@@ -88,16 +89,18 @@ int shafa_cuda_encode_host_multi(shafa_cuda_multi *m, const uint8_t *h_in, uint6
     if (!out->rle || !out->rle_capacity) {
         out->rle_capacity = 2 * n + 3 * nb + 64;  // f.c:244 per block (untouched pages cost nothing)
         out->rle = nullptr;
-        if (posix_memalign((void **)&out->rle, 4096, out->rle_capacity) != 0) return SHAFA_LACK_OF_MEMORY;
+        if (posix_memalign((void **)&out->rle, 2u << 20, out->rle_capacity) != 0) return SHAFA_LACK_OF_MEMORY;
+        madvise(out->rle, out->rle_capacity, MADV_HUGEPAGE);  // GiB-sized, written once: 512x fewer first-touch faults
         own_rle = true;
     }
     if (!out->payload || !out->payload_capacity) {
         out->payload_capacity = 2 * n + n / 8 + 32 * nb + 4096;  // Fano codes average <= H + 1 <= 9 bits per symbol of <= 2n + 3 symbols
         out->payload = nullptr;
-        if (posix_memalign((void **)&out->payload, 4096, out->payload_capacity) != 0) {
+        if (posix_memalign((void **)&out->payload, 2u << 20, out->payload_capacity) != 0) {
             if (own_rle) free(out->rle);
             return SHAFA_LACK_OF_MEMORY;
         }
+        madvise(out->payload, out->payload_capacity, MADV_HUGEPAGE);
         own_pay = true;
     }
     uint8_t *rle = out->rle, *pay = out->payload;

@@ -175,19 +175,20 @@ k_rle_decode(const uint8_t *__restrict__ in, const uint64_t *__restrict__ off, c
     for (int i = tid; i < 64 * 64; i += RLD_THREADS) sh.compose[i] = (uint8_t)fsm_compose((uint32_t)i >> 6, (uint32_t)i & 63u);
     const uint32_t compose_s = smem_opaque(sh.compose), stage_s = smem_opaque(sh.stage);
 
-    // tickets are taken one tile ahead (the atomic's round trip overlaps the tile), and warp 0 finds the ticket's
-    // block by probing the 32 blocks after its previous one at once
-    uint32_t next_ticket = 0, last_block = 0;
-    if (tid == 0) next_ticket = atomicAdd(counter, 1u);
+    // A ticket is taken only when the CTA is ready to work on it (a tile reserved ahead of time stalls every later
+    // tile of the look-back chains: measured).  Warp 0 finds the ticket's block by probing the 32 blocks after its
+    // previous one at once instead of a dependent binary search.
+    uint32_t last_block = 0;
     for (;;) {
         __syncthreads();
         if (warp == 0) {
-            const uint32_t tk = __shfl_sync(FULL, next_ticket, 0);
+            uint32_t tk = 0;
+            if (lane == 0) tk = atomicAdd(counter, 1u);
+            tk = __shfl_sync(FULL, tk, 0);
             if (tk < total_tiles) last_block = find_block_forward(tile0, nb, tk, last_block);
             if (lane == 0) {
                 sh.ticket = tk;
                 sh.block = last_block;
-                if (tk < total_tiles) next_ticket = atomicAdd(counter, 1u);
             }
         }
         __syncthreads();

@@ -381,12 +381,37 @@ k_dec_sync(const uint8_t *__restrict__ payload, DecPlan plan, DecTablesGlobal g,
                 // one sub-sequence at a time.  Instead every thread decodes its sub-sequence from EVERY start
                 // that can occur (an overshoot is shorter than the longest code) and one thread follows the
                 // chain through the resulting tables.
-                for (uint32_t st = 0; st < maxlen; st++) {
+                {
                     const uint32_t sub_lo = tid * DEC_SUB_BITS;
                     const uint32_t stop = limit > sub_lo ? (limit - sub_lo < (uint32_t)DEC_SUB_BITS ? limit - sub_lo : (uint32_t)DEC_SUB_BITS) : 0u;
-                    const DecSub r = dec_count_subsequence(t, tid * DEC_ROW, st, stop);
-                    const uint32_t over = r.end > (uint32_t)DEC_SUB_BITS ? r.end - DEC_SUB_BITS : 0u;
-                    s_map[tid * DEC_MAP_MAX + st] = (uint16_t)((over << 10) | r.count);
+                    // The sub-sequence's six words live in registers for all `maxlen` walks: a window is one funnel shift of
+                    // two of them (the word index is a compile-time loop counter), not a shared-memory load per code.
+                    uint32_t w[DEC_ROW_WORDS];
+#pragma unroll
+                    for (int k = 0; k < DEC_ROW; k++) {
+                        const uint64_t pr = t.pair(tid * DEC_ROW + k);
+                        w[k] = (uint32_t)(pr >> 32);
+                        if (k == DEC_ROW - 1) w[k + 1] = (uint32_t)pr;
+                    }
+                    for (uint32_t st = 0; st < maxlen; st++) {
+                        uint32_t q = st, count = 0, bad_dummy = 0;
+#pragma unroll
+                        for (int i = 0; i < DEC_SUB_BITS / 32; i++) {
+                            const uint32_t lim = stop < 32u * (i + 1) ? stop : 32u * (i + 1);
+                            while (q < lim) {
+                                const uint32_t e = t.l1(__funnelshift_l(w[i + 1], w[i], q) >> (32 - DEC_LUT_BITS));
+                                uint32_t l = e & 0xFFu;
+                                if (l - 1u >= (uint32_t)DEC_LUT_BITS) {  // a code longer than the table window (or none): generic step
+                                    uint32_t sym;
+                                    l = dec_one(t, tid * DEC_ROW, q, &sym, &bad_dummy);
+                                }
+                                q += l;
+                                count++;
+                            }
+                        }
+                        const uint32_t over = q > (uint32_t)DEC_SUB_BITS ? q - DEC_SUB_BITS : 0u;
+                        s_map[tid * DEC_MAP_MAX + st] = (uint16_t)((over << 10) | count);
+                    }
                 }
                 __syncthreads();
                 // the chain, two levels: lane s of every warp follows its warp's 32 sub-sequences from entry

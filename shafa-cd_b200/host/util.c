@@ -1,6 +1,7 @@
 #include "util.h"
 
 #include <pthread.h>
+#include <sys/mman.h>
 #include <stdlib.h>
 #include <string.h>
 #include <time.h>
@@ -106,7 +107,11 @@ void *cli_host_alloc(size_t bytes)
 {
     if (cli_pinned()) return shafa_cuda_host_alloc(bytes);
     void *p = NULL;
-    return posix_memalign(&p, 4096, bytes ? bytes : 1) == 0 ? p : NULL;
+    if (posix_memalign(&p, 2u << 20, bytes ? bytes : 1) != 0) return NULL;
+#ifdef MADV_HUGEPAGE
+    if (bytes >= (8u << 20)) madvise(p, bytes, MADV_HUGEPAGE); /* GiB-sized one-shot buffers: 512x fewer first-touch faults */
+#endif
+    return p;
 }
 void cli_host_free(void *p)
 {
