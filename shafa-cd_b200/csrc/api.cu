@@ -441,15 +441,16 @@ int shafa_cuda_sf_decode_blocks(shafa_cuda_ctx *ctx, const uint8_t *d_payload, c
     uint32_t *d_err;
     int rc = err_reset(ctx, &d_err);
     if (rc) return rc;
-    rc = launch_sf_decode(ctx, d_payload, h_payload_offsets, h_z, h_n, nb, d_len, d_code, d_sym, d_err, false);
+    rc = launch_sf_decode(ctx, d_payload, h_payload_offsets, h_z, h_n, nb, d_len, d_code, d_sym, d_err, false, false);
     if (rc) return rc;
     rc = finish_with_err(ctx, d_err, "sf_decode_blocks");
-    if (rc == SHAFA_FILE_UNRECOGNIZABLE && (ctx->last_err_bits & ERR_SPECULATION)) {
+    if (rc == SHAFA_FILE_UNRECOGNIZABLE && (ctx->last_err_bits & (ERR_SPECULATION | ERR_STITCH))) {
         // The single-pass decoder guessed that a sequence's end does not depend on where its first code starts,
         // checked the guess, and found it wrong somewhere (codes that do not self-synchronise): its output is not
         // trusted.  Decode again with the exact path.
         if ((rc = err_reset(ctx, &d_err))) return rc;
-        rc = launch_sf_decode(ctx, d_payload, h_payload_offsets, h_z, h_n, nb, d_len, d_code, d_sym, d_err, true);
+        // (the same for the exact path's own optimism: two stitch passes without host polling were not enough)
+        rc = launch_sf_decode(ctx, d_payload, h_payload_offsets, h_z, h_n, nb, d_len, d_code, d_sym, d_err, true, true);
         if (rc) return rc;
         rc = finish_with_err(ctx, d_err, "sf_decode_blocks (exact path)");
     }

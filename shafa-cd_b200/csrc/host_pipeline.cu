@@ -272,6 +272,7 @@ int encode_host_pipelined(shafa_cuda_ctx *const *ctxs, int n_ctx, const uint8_t 
         pay_chain.abort();
     };
 
+    std::vector<uint32_t> chunks_done(workers.size(), 0);
     auto work = [&](int widx) {
         shafa_cuda_ctx *w = workers[widx];
         if (cudaSetDevice(w->device) != cudaSuccess) return fail_from(nullptr, SHAFA_THREAD_CREATION_FAILED);
@@ -279,6 +280,7 @@ int encode_host_pipelined(shafa_cuda_ctx *const *ctxs, int n_ctx, const uint8_t 
         for (;;) {
             const uint64_t c = next.fetch_add(1);
             if (c >= ch.count || err.load()) return;
+            chunks_done[widx]++;
             const uint64_t b0 = c * ch.per, b1 = (b0 + ch.per < nb) ? b0 + ch.per : nb, cb = b1 - b0;
             const uint64_t lo = b0 * block_size, hi = (b1 * block_size < n) ? b1 * block_size : n, cn = hi - lo;
             int r;
@@ -360,6 +362,11 @@ int encode_host_pipelined(shafa_cuda_ctx *const *ctxs, int n_ctx, const uint8_t 
         out->payload = nullptr;
         shafa_cuda_encoded_free(out);
         return rc;
+    }
+    if (getenv("SHAFA_VERBOSE")) {
+        fprintf(stderr, "pipelined encode: %llu chunks of %llu block(s); per worker (device:chunks):", (unsigned long long)ch.count, (unsigned long long)ch.per);
+        for (size_t i = 0; i < workers.size(); i++) fprintf(stderr, " %d:%u", workers[i]->device, chunks_done[i]);
+        fprintf(stderr, "\n");
     }
     out->rle_total = rle_mode ? rle_chain.base[ch.count] : 0;
     out->payload_total = pay_chain.base[ch.count];

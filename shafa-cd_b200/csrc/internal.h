@@ -111,6 +111,7 @@ enum ErrBits : uint32_t {
     ERR_CAPACITY = 32,       // output buffer too small
     ERR_RLE_TRUNCATED = 64,  // RLE block ends inside a triple
     ERR_SPECULATION = 128,   // fused SF decoder: a sequence's end depended on its start (decode again, exact path)
+    ERR_STITCH = 512,        // exact SF decoder: sequence ends still moved in the second stitch pass (decode again, polling)
     ERR_TIMEOUT = 256        // fused SF decoder: a bounded device-side wait gave up (never seen; keeps a bug from hanging the GPU)
 };
 enum OccId { OCC_SF_ENCODE = 0, OCC_RLE_ENC = 1 /* +variant 0..3 */, OCC_RLE_DEC = 5, OCC_DEC_SYNC = 6, OCC_DEC_WRITE = 7, OCC_HIST = 8, OCC_DEC_FUSED = 9 };
@@ -144,7 +145,7 @@ int launch_sf_encode(shafa_cuda_ctx *ctx, const uint8_t *d_sym, const uint64_t *
 // sf_decode.cu
 int launch_sf_decode(shafa_cuda_ctx *ctx, const uint8_t *d_payload, const uint64_t *h_payload_off,
                      const uint64_t *h_z, const uint64_t *h_n, uint64_t nb, const uint8_t *d_len,
-                     const uint64_t *d_code, uint8_t *d_sym, uint32_t *d_err, bool force_exact);
+                     const uint64_t *d_code, uint8_t *d_sym, uint32_t *d_err, bool force_exact, bool careful_stitch);
 
 // rle_encode.cu (synchronises: returns per-block sizes)
 int launch_rle_encode(shafa_cuda_ctx *ctx, const uint8_t *d_in, uint64_t n, uint64_t block_size, uint8_t *d_rle,

@@ -549,8 +549,11 @@ k_dec_stitch(const uint8_t *__restrict__ payload, DecPlan plan, DecTablesGlobal 
 // one CTA per block: exclusive scan of its sequences' counts; checks the block holds >= n symbols
 __global__ void __launch_bounds__(256)
 k_dec_scan(DecPlan plan, const uint32_t *__restrict__ seq_count, uint64_t *__restrict__ seq_excl,
-           uint32_t *__restrict__ err)
+           uint32_t *__restrict__ err, const uint32_t *__restrict__ still_moving)
 {
+    // the stitch passes ran without the host looking at their flag: if the last one still moved a sequence end, the
+    // counts below are not final -- say so, the caller decodes again with the polling loop
+    if (blockIdx.x == 0 && threadIdx.x == 0 && still_moving && *still_moving) atomicOr(err, (uint32_t)ERR_STITCH);
     __shared__ uint32_t scan[9];
     __shared__ unsigned long long s_carry;
     const uint32_t b = blockIdx.x;
@@ -750,7 +753,7 @@ static DecPlan plan_at(const uint64_t *dp, uint64_t nb)
 
 // the exact path: sync / stitch / scan / write over the blocks of `plan`
 static int launch_sf_decode_exact(shafa_cuda_ctx *ctx, const uint8_t *d_payload, const DecPlan &plan, const DecTablesGlobal &g,
-                                  uint64_t nb, uint64_t nseq, uint8_t *d_sym, uint32_t *d_err)
+                                  uint64_t nb, uint64_t nseq, uint8_t *d_sym, uint32_t *d_err, bool careful_stitch)
 {
     if (nseq == 0) return SHAFA_SUCCESS;
     uint16_t *sub_info = (uint16_t *)scratch_get(ctx, SCR_DEC_SUB, nseq * DEC_THREADS * sizeof(uint16_t));
@@ -780,10 +783,22 @@ static int launch_sf_decode_exact(shafa_cuda_ctx *ctx, const uint8_t *d_payload,
     SHAFA_LAUNCH(ctx, "dec_sync", k_dec_sync, dim3((unsigned)grid_sync), dim3(DEC_THREADS), 0, d_payload, plan, g, sub_info,
                  seq_end, seq_count, nseq, fb);
     SHAFA_CHECK_LAUNCH(ctx);
-    // stitch across chunk boundaries until a pass moves no sequence end (normally the first pass)
+    // Stitch across chunk boundaries until a pass moves no sequence end.  The first pass almost always settles it and the
+    // second then moves nothing, so the normal path launches two passes back to back with NO host round trip in
+    // between; k_dec_scan raises ERR_STITCH if the second pass still moved an end, and only then (careful_stitch) the
+    // passes are repeated under host polling.
     uint32_t *h_flag = (uint32_t *)pinned_get(ctx, 64);
     if (!h_flag) return SHAFA_LACK_OF_MEMORY;
-    for (uint64_t pass = 0;; pass++) {
+    const uint32_t *still_moving = nullptr;
+    if (!careful_stitch) {
+        SHAFA_CUDA_TRY(ctx, cudaMemsetAsync(flag, 0, 8, ctx->stream));
+        for (int pass = 0; pass < 2; pass++)
+            SHAFA_LAUNCH(ctx, "dec_stitch", k_dec_stitch, dim3((unsigned)((nseq + 127) / 128)), dim3(128), 0, d_payload,
+                         plan, g, sub_info, seq_end, seq_count, nseq, flag + pass);
+        SHAFA_CHECK_LAUNCH(ctx);
+        still_moving = flag + 1;
+    }
+    for (uint64_t pass = 0; careful_stitch; pass++) {
         SHAFA_CUDA_TRY(ctx, cudaMemsetAsync(flag, 0, 4, ctx->stream));
         SHAFA_LAUNCH(ctx, "dec_stitch", k_dec_stitch, dim3((unsigned)((nseq + 127) / 128)), dim3(128), 0, d_payload,
                      plan, g, sub_info, seq_end, seq_count, nseq, flag);
@@ -793,7 +808,7 @@ static int launch_sf_decode_exact(shafa_cuda_ctx *ctx, const uint8_t *d_payload,
         if (*h_flag == 0) break;
         if (pass > nseq + 2) return set_error(ctx, SHAFA_FILE_UNRECOGNIZABLE, "sf_decode: stitching did not converge");
     }
-    SHAFA_LAUNCH(ctx, "dec_scan", k_dec_scan, dim3((unsigned)nb), dim3(256), 0, plan, seq_count, seq_excl, d_err);
+    SHAFA_LAUNCH(ctx, "dec_scan", k_dec_scan, dim3((unsigned)nb), dim3(256), 0, plan, seq_count, seq_excl, d_err, still_moving);
     SHAFA_LAUNCH(ctx, "dec_write", k_dec_write, dim3((unsigned)grid_write), dim3(DEC_THREADS), smem_w, d_payload, plan, g,
                  sub_info, seq_excl, d_sym, nseq, d_err);
     SHAFA_CHECK_LAUNCH(ctx);
@@ -804,7 +819,7 @@ static int launch_sf_decode_exact(shafa_cuda_ctx *ctx, const uint8_t *d_payload,
 // SHAFA_DECODE_EXACT=1 for A/B measurements)
 int launch_sf_decode(shafa_cuda_ctx *ctx, const uint8_t *d_payload, const uint64_t *h_payload_off,
                      const uint64_t *h_z, const uint64_t *h_n, uint64_t nb, const uint8_t *d_len,
-                     const uint64_t *d_code, uint8_t *d_sym, uint32_t *d_err, bool force_exact)
+                     const uint64_t *d_code, uint8_t *d_sym, uint32_t *d_err, bool force_exact, bool careful_stitch)
 {
     if (nb == 0) return SHAFA_SUCCESS;
     {
@@ -869,7 +884,7 @@ int launch_sf_decode(shafa_cuda_ctx *ctx, const uint8_t *d_payload, const uint64
         if ((rc = launch_sf_decode_fused(ctx, d_payload, plan, g, rec, nseq_fused, d_sym, d_err))) return rc;
     }
     if (nseq_exact) {
-        rc = launch_sf_decode_exact(ctx, d_payload, plan_at(dp + plan_words, nb), g, nb, nseq_exact, d_sym, d_err);
+        rc = launch_sf_decode_exact(ctx, d_payload, plan_at(dp + plan_words, nb), g, nb, nseq_exact, d_sym, d_err, careful_stitch);
     }
     return rc;
 }

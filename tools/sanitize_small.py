@@ -1,0 +1,39 @@
+#!/usr/bin/env python3
+"""Small inputs through every kernel, meant to run under compute-sanitizer (memcheck / racecheck / synccheck):
+
+    compute-sanitizer --tool racecheck python tools/sanitize_small.py
+
+Covers what the kernel tests cover at sizes a sanitizer finishes in minutes: TMA-staged histogram, RLE encode/decode,
+SF build/encode, the exact decoder incl. its all-starts path (uniform bytes: codes of 7-9 bits), the bulk-store copy-out
+of k_dec_write, and the fused single-pass decoder (SHAFA_DECODE_FUSED=1, second half).
+"""
+import os
+import sys
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+from __graft_entry__ import load_package  # noqa: E402
+
+
+def main():
+    pkg = load_package()
+    cases = [("textlike", 300_000, 65536), ("uniform", 150_000, 65536), ("runheavy", 400_000, 65536), ("zipf", 200_000, 65536)]
+    with pkg.Shafa(device=0) as sh:
+        for fused in ("0", "1"):
+            os.environ["SHAFA_DECODE_FUSED"] = fused
+            for gen, n, bs in cases:
+                data = pkg.datagen.GENERATORS[gen](n, seed=3)
+                enc = sh.encode(data, bs, force_freq=True)
+                out = sh.decode(enc)
+                assert np.array_equal(out, data), (gen, fused)
+                if enc.rle_mode:
+                    assert np.array_equal(sh.decode(enc, rle_expand=False), enc.rle), (gen, fused)
+                print("ok", gen, "fused" if fused == "1" else "exact", "R" if enc.rle_mode else "N", flush=True)
+    print("SANITIZE_SMALL_OK")
+
+
+if __name__ == "__main__":
+    main()
