@@ -15,7 +15,9 @@ from pathlib import Path
 import numpy as np
 
 HERE = Path(__file__).resolve().parent
-LIB_PATH = HERE / "libshafa_cuda.so"
+import os as _os
+
+LIB_PATH = Path(_os.environ["SHAFA_LIB"]) if _os.environ.get("SHAFA_LIB") else HERE / "libshafa_cuda.so"   # SHAFA_LIB: A/B builds of the same library
 HEADER = HERE.parent / "include" / "shafa_cuda.h"
 
 ERRORS = {

@@ -138,7 +138,13 @@ __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t *smem, 
 // The prefix frontier of a chain advances by at most one look-back window per L2
 // round trip, so the window is LB_WINDOW = 128 descriptors (4 per lane), not 32:
 // with 4 KiB tiles a 32-wide window capped a file-wide chain at ~250 GB/s.
-constexpr int LB_PER_LANE = 4;
+#ifndef SHAFA_LB_SPINS
+#define SHAFA_LB_SPINS 2  // failed probes before a look-back starts to sleep between probes
+#endif
+#ifndef SHAFA_LB_PER_LANE
+#define SHAFA_LB_PER_LANE 4
+#endif
+constexpr int LB_PER_LANE = SHAFA_LB_PER_LANE;
 constexpr int LB_WINDOW = 32 * LB_PER_LANE;
 
 __device__ __forceinline__ uint64_t lookback_read(const uint64_t *desc, int64_t tile, int64_t first)
@@ -173,7 +179,7 @@ __device__ __forceinline__ uint64_t lookback_read(const uint64_t *desc, int64_t 
                     break;
                 }
             }
-            if (pending && ++spins > 2) __nanosleep(40);
+            if (pending && ++spins > SHAFA_LB_SPINS) __nanosleep(40);
         } while (pending);
         bool done = false;
 #pragma unroll

@@ -44,6 +44,17 @@ SHAFA_HD uint32_t bswap32(uint32_t x)
 #endif
 }
 
+// upper 32 bits of (hi:lo) << (sh & 31)
+SHAFA_HD uint32_t funnel_l(uint32_t lo, uint32_t hi, uint32_t sh)
+{
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_l(lo, hi, sh);
+#else
+    sh &= 31u;
+    return sh ? ((hi << sh) | (lo >> (32u - sh))) : hi;
+#endif
+}
+
 // =============================================================================
 // RLE encode (f.c:29-55) as a per-position rule.
 //
@@ -399,7 +410,10 @@ constexpr int ENC_THREADS = 256;
 constexpr int ENC_VECS = 4;                                // 16-byte vectors per thread, contiguous
 constexpr int ENC_ITEMS = 16 * ENC_VECS;                   // 64 symbols per thread
 constexpr int ENC_TILE = ENC_THREADS * ENC_ITEMS;          // 16 KiB of symbols per tile
-constexpr int ENC_STAGE_WORDS = 5120;                      // staging window: 20 KiB of the tile's bit range (10 bits per symbol)
+#ifndef SHAFA_ENC_STAGE_WORDS
+#define SHAFA_ENC_STAGE_WORDS 5120
+#endif
+constexpr int ENC_STAGE_WORDS = SHAFA_ENC_STAGE_WORDS;      // staging window: 20 KiB of the tile's bit range (10 bits per symbol)
 // Encoder LUT entry of a code of at most ENC_SHORT_MAX (< 28) bits: length in the top five bits -- so that
 // "bits += length" is one shift-add -- and the right-aligned code below.
 SHAFA_HD uint32_t enc_entry(uint64_t code, uint32_t len) { return (len << 27) | (uint32_t)code; }
@@ -544,6 +558,38 @@ SHAFA_HD uint32_t dec_one(const V &t, uint32_t row, uint32_t q, uint32_t *sym, u
     return l;
 }
 
+// the same from lut3 alone (first code of the entry) with the sorted search for long codes: no lut1 needed
+template <typename V>
+SHAFA_HD uint32_t dec_one3(const V &t, uint32_t row, uint32_t q, uint32_t *sym, uint32_t *bad)
+{
+    const uint32_t e3 = t.l3(dec_window32(t, row, q) >> (32 - DEC_LUT_BITS));
+    if (e3) {
+        *sym = e3 & 0xFFu;
+        return (e3 >> 20) & 0xFu;
+    }
+    // long code or no code: exact 64-bit window + sorted search (largest left-aligned code <= window)
+    const uint64_t window = dec_window64(t, row, q);
+    int lo = 0, hi = 256;
+    while (lo < hi) {
+        const int m = (lo + hi) >> 1;
+        if (t.sleft[m] <= window)
+            lo = m + 1;
+        else
+            hi = m;
+    }
+    if (lo > 0) {
+        const int r = lo - 1;
+        const uint32_t len = t.slen[r];
+        if (len != 0 && (window >> (64 - len)) == (t.sleft[r] >> (64 - len))) {
+            *sym = t.ssym[r];
+            return len;
+        }
+    }
+    *bad = 1;
+    *sym = 0;
+    return 1;
+}
+
 // Count the symbols that START in [start, stop) of the sub-sequence whose row is `row` (stop <= 128)
 // and find where decoding leaves the range.  While a whole 12-bit window lies before `stop`, all codes
 // inside it are taken at once (lut2).
@@ -591,7 +637,7 @@ SHAFA_HD DecSub dec_emit_to(const V &t, uint32_t row, uint32_t start, uint32_t s
         }
         if (q >= (int32_t)stop) break;
         uint32_t sym;
-        q += (int32_t)dec_one(t, row, (uint32_t)q, &sym, &r.bad);
+        q += (int32_t)(t.has_l3() ? dec_one3(t, row, (uint32_t)q, &sym, &r.bad) : dec_one(t, row, (uint32_t)q, &sym, &r.bad));
         em.one(sym);
     }
     r.end = (uint32_t)q;
@@ -623,6 +669,107 @@ struct DecNoEmit {
     SHAFA_HD void operator()(uint32_t, uint32_t) const {}
 };
 
+// ---- the same walks with the sub-sequence's six big-endian words IN REGISTERS ---------------------------
+// The word index is a compile-time loop counter, so a window is one funnel shift of two registers: no
+// shared-memory load (and no address arithmetic) per lookup for the payload, only for the table.  The
+// kernels use these for a thread's OWN sub-sequence; the row versions above remain for the rare rounds in
+// which a thread re-decodes somebody else's.
+template <typename V>
+SHAFA_HD uint32_t dec_long_words(const V &t, const uint32_t (&w)[DEC_ROW_WORDS], int i, uint32_t q, uint32_t *sym, uint32_t *bad)
+{
+    const uint32_t sh = q & 31u;
+    const uint64_t hi64 = ((uint64_t)w[i] << 32) | (uint64_t)w[i + 1];
+    const uint64_t window = sh ? ((hi64 << sh) | ((uint64_t)w[i + 2] >> (32u - sh))) : hi64;
+    int lo = 0, hi = 256;  // count of entries <= window
+    while (lo < hi) {
+        const int m = (lo + hi) >> 1;
+        if (t.sleft[m] <= window)
+            lo = m + 1;
+        else
+            hi = m;
+    }
+    if (lo > 0) {
+        const int r = lo - 1;
+        const uint32_t len = t.slen[r];
+        if (len != 0 && (window >> (64 - len)) == (t.sleft[r] >> (64 - len))) {
+            *sym = t.ssym[r];
+            return len;
+        }
+    }
+    *bad = 1;
+    *sym = 0;
+    return 1;
+}
+
+// dec_count_subsequence on registers (needs lut1 and lut2)
+template <typename V>
+SHAFA_HD DecSub dec_count_words(const V &t, const uint32_t (&w)[DEC_ROW_WORDS], uint32_t start, uint32_t stop)
+{
+    DecSub r;
+    r.count = 0;
+    r.bad = 0;
+    uint32_t q = start;
+    const int32_t stop13 = (int32_t)stop - DEC_LUT2_BITS;
+#pragma unroll
+    for (int i = 0; i < DEC_SUB_BITS / 32; i++) {
+        const uint32_t lim = stop < 32u * (uint32_t)(i + 1) ? stop : 32u * (uint32_t)(i + 1);
+        while (q < lim) {
+            const uint32_t win = funnel_l(w[i + 1], w[i], q);
+            if ((int32_t)q <= stop13) {
+                const uint32_t e2 = t.l2(win >> (32 - DEC_LUT2_BITS));
+                if (e2) {  // all whole codes of the 13-bit window at once
+                    q += e2 & 0xFu;
+                    r.count += e2 >> 4;
+                    continue;
+                }
+            }
+            const uint32_t e = t.l1(win >> (32 - DEC_LUT_BITS));
+            uint32_t l = e & 0xFFu;
+            if (l - 1u >= (uint32_t)DEC_LUT_BITS) {
+                uint32_t sym;
+                l = dec_long_words(t, w, i, q, &sym, &r.bad);
+            }
+            q += l;
+            r.count++;
+        }
+    }
+    r.end = q;
+    return r;
+}
+
+// dec_emit_to on registers (needs lut3 only: its entries carry the first code's length)
+template <typename V, typename Sink>
+SHAFA_HD DecSub dec_emit_words(const V &t, const uint32_t (&w)[DEC_ROW_WORDS], uint32_t start, uint32_t stop, Sink &em)
+{
+    DecSub r;
+    r.bad = 0;
+    uint32_t q = start;
+    const int32_t stop12 = (int32_t)stop - DEC_LUT_BITS;
+#pragma unroll
+    for (int i = 0; i < DEC_SUB_BITS / 32; i++) {
+        const uint32_t lim = stop < 32u * (uint32_t)(i + 1) ? stop : 32u * (uint32_t)(i + 1);
+        while (q < lim) {
+            const uint32_t e3 = t.l3(funnel_l(w[i + 1], w[i], q) >> (32 - DEC_LUT_BITS));
+            if (e3) {
+                if ((int32_t)q <= stop12) {  // both codes of the entry start before `stop`
+                    em.two(e3);
+                    q += e3 >> 24;
+                } else {
+                    em.one(e3 & 0xFFu);
+                    q += (e3 >> 20) & 0xFu;
+                }
+            } else {
+                uint32_t sym;
+                q += dec_long_words(t, w, i, q, &sym, &r.bad);
+                em.one(sym);
+            }
+        }
+    }
+    r.end = q;
+    r.count = em.count();
+    return r;
+}
+
 // lut2 entry for the 13-bit window value e, derived from lut1 (codes of up to 12 bits): how many whole codes
 // the window holds and their total length
 SHAFA_HD uint8_t dec_lut2_entry(const uint16_t *lut1, uint32_t e)
@@ -638,7 +785,10 @@ SHAFA_HD uint8_t dec_lut2_entry(const uint16_t *lut1, uint32_t e)
     return (uint8_t)(n ? ((n << 4) | pos) : 0);  // n, pos <= 13
 }
 
-// lut3 entry for the 12-bit window value e: its first one or two whole codes
+// lut3 entry for the 12-bit window value e: its first one or two whole codes.
+//   [7:0] sym0  [15:8] sym1  [17:16] how many (1|2)  [23:20] bits of the first code  [31:24] bits of the codes taken
+// The first code's own length makes the table usable for single-code steps too, so the write kernel does not need
+// lut1 in shared memory (8 KiB: one more resident CTA per SM).
 SHAFA_HD uint32_t dec_lut3_entry(const uint16_t *lut1, uint32_t e)
 {
     const uint32_t e0 = lut1[e];
@@ -647,8 +797,8 @@ SHAFA_HD uint32_t dec_lut3_entry(const uint16_t *lut1, uint32_t e)
     const uint32_t e1 = lut1[(e << l0) & (DEC_LUT_SIZE - 1)];
     const uint32_t l1 = e1 & 0xFFu;
     if (l1 - 1u < (uint32_t)DEC_LUT_BITS && l0 + l1 <= (uint32_t)DEC_LUT_BITS)
-        return ((l0 + l1) << 24) | (2u << 16) | ((e1 >> 8) << 8) | (e0 >> 8);
-    return (l0 << 24) | (1u << 16) | (e0 >> 8);
+        return ((l0 + l1) << 24) | (l0 << 20) | (2u << 16) | ((e1 >> 8) << 8) | (e0 >> 8);
+    return (l0 << 24) | (l0 << 20) | (1u << 16) | (e0 >> 8);
 }
 
 

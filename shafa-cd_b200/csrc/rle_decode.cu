@@ -163,7 +163,10 @@ __device__ __noinline__ void rld_expand_direct(const uint8_t *__restrict__ in, u
     }
 }
 
-__global__ void __launch_bounds__(RLD_THREADS, 6)
+#ifndef SHAFA_RLD_MIN_CTAS
+#define SHAFA_RLD_MIN_CTAS 6
+#endif
+__global__ void __launch_bounds__(RLD_THREADS, SHAFA_RLD_MIN_CTAS)
 k_rle_decode(const uint8_t *__restrict__ in, const uint64_t *__restrict__ off, const uint64_t *__restrict__ tile0,
              uint32_t nb, uint8_t *__restrict__ out, uint64_t out_capacity, uint64_t *__restrict__ blk_end,
              uint64_t *__restrict__ desc_state_chain, uint64_t *__restrict__ desc_out, uint32_t *__restrict__ counter,

@@ -577,8 +577,12 @@ k_dec_scan(DecPlan plan, const uint32_t *__restrict__ seq_count, uint64_t *__res
 // Symbols of a sequence are staged in shared memory (co-aligned with their destination) and
 // copied out with 16-byte stores; a sequence that decodes to more than DEC_STAGE symbols
 // (codes of 1-2 bits) writes straight to global memory instead.
-struct DecWriteShared {
-    DecShared d;
+struct DecWriteShared {  // no lut1 (lut3 entries carry the first code's length, core.h dec_lut3_entry) and no payload rows (a thread only
+                         // ever decodes its own sub-sequence here: six words in registers): 31 KB
+    uint64_t sleft[256];
+    uint8_t slen[256];
+    uint8_t ssym[256];
+    uint32_t scan[DEC_THREADS / 32 + 1];
     alignas(16) uint32_t lut3[DEC_LUT_SIZE];
     alignas(16) uint8_t stage[DEC_STAGE + 48];  // + the destination's misalignment (< 16)
 };
@@ -611,19 +615,19 @@ struct StageSink {
             asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(e3) : "memory");
             put_if(addr + 1, e3 >> 8, second);
         }
-        addr += __byte_perm(e3, 0, 0x4442);  // byte 2: one or two symbols
+        addr += (e3 >> 16) & 3u;  // one or two symbols
     }
     __device__ __forceinline__ uint32_t count() const { return addr - base; }
 };
 
-__global__ void __launch_bounds__(DEC_THREADS)
+__global__ void __launch_bounds__(DEC_THREADS, 5)
 k_dec_write(const uint8_t *__restrict__ payload, DecPlan plan, DecTablesGlobal g,
             const uint16_t *__restrict__ sub_info, const uint64_t *__restrict__ seq_excl, uint8_t *__restrict__ out,
             uint64_t nseq, uint32_t *__restrict__ err)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     DecWriteShared &ws = *reinterpret_cast<DecWriteShared *>(smem_raw);
-    DecShared &sh = ws.d;
+    DecWriteShared &sh = ws;
     const unsigned tid = threadIdx.x;
     uint64_t seq_first, seq_last;
     dec_chunk(nseq, &seq_first, &seq_last);
@@ -650,17 +654,29 @@ k_dec_write(const uint8_t *__restrict__ payload, DecPlan plan, DecTablesGlobal g
         if (b != cur_block) {
             cur_block = b;
             __syncthreads();  // nobody decodes with the old tables any more
-            dec_load_tables(sh, g, b, nullptr);
+            sh.sleft[tid] = g.sleft[(uint64_t)b * 256 + tid];
+            sh.slen[tid] = g.slen[(uint64_t)b * 256 + tid];
+            sh.ssym[tid] = g.ssym[(uint64_t)b * 256 + tid];
             const uint4 *src3 = reinterpret_cast<const uint4 *>(g.lut3 + (uint64_t)b * DEC_LUT_SIZE);
             uint4 *dst3 = reinterpret_cast<uint4 *>(ws.lut3);
             for (int i = tid; i < DEC_LUT_SIZE * 4 / 16; i += DEC_THREADS) dst3[i] = src3[i];
         }
-        dec_store_row(sh.pairs, cur.row, z, sib);  // read back by this thread only
+        uint32_t words[DEC_ROW_WORDS];
+        dec_row_words(cur.row, z, sib, words);
         if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the previous sequence's bulk store has read the stage
         uint32_t total;
         // the scan's barriers also fence the table loads above and the previous sequence's copy-out
         const uint32_t excl = block_excl_scan<DEC_THREADS>(sub_count(rec), sh.scan, &total);
-        const DecViewS t = dec_view_of(sh, nullptr, ws.lut3);
+        DecViewS t;
+        t.pairs_s = 0u;
+        t.lut1_s = 0u;
+        t.lut2_s = 0u;
+        t.lut3_s = smem_u32(ws.lut3);
+        asm volatile("" : "+r"(t.lut3_s));  // not rebuilt from the shared window inside the loops
+        t.lut1 = nullptr;
+        t.sleft = sh.sleft;
+        t.slen = sh.slen;
+        t.ssym = sh.ssym;
         const uint64_t bits_left = (z - sib * DEC_SEQ_BYTES) * 8;
         const uint32_t limit = bits_left < (uint64_t)DEC_SEQ_BYTES * 8 ? (uint32_t)bits_left : DEC_SEQ_BYTES * 8;
         const uint32_t sub_lo = tid * DEC_SUB_BITS;
@@ -682,10 +698,10 @@ k_dec_write(const uint8_t *__restrict__ payload, DecPlan plan, DecTablesGlobal g
                 DecSub r;
                 if (seq_room >= total) {  // every symbol of this sequence is real (all but a block's last sequences)
                     StageSink<false> sink{dst_s, room, dst_s};
-                    r = dec_emit_to(t, tid * DEC_ROW, sub_start(rec), stop, sink);
+                    r = dec_emit_words(t, words, sub_start(rec), stop, sink);
                 } else {
                     StageSink<true> sink{dst_s, room, dst_s};
-                    r = dec_emit_to(t, tid * DEC_ROW, sub_start(rec), stop, sink);
+                    r = dec_emit_words(t, words, sub_start(rec), stop, sink);
                 }
                 bad |= r.bad && room;
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // my stores to the stage, before the bulk copy reads them
@@ -704,9 +720,11 @@ k_dec_write(const uint8_t *__restrict__ payload, DecPlan plan, DecTablesGlobal g
                 }
             } else {
                 uint8_t *dst = gdst + excl;
-                const DecSub r = dec_emit_subsequence(t, tid * DEC_ROW, sub_start(rec), stop, [&](uint32_t i, uint32_t sym) {
+                auto put = [&](uint32_t i, uint32_t sym) {
                     if (i < room) dst[i] = (uint8_t)sym;
-                });
+                };
+                DecFnSink<decltype(put)> sink{put, 0u};
+                const DecSub r = dec_emit_words(t, words, sub_start(rec), stop, sink);
                 bad |= r.bad && room;
             }
         }

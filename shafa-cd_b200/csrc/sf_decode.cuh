@@ -46,11 +46,11 @@ struct RowRegs {
     uint4 v;
     uint2 u;
 };
-__device__ __forceinline__ void dec_store_row(uint64_t *pairs, const RowRegs &r, uint64_t z, uint64_t seq_in_block)
+// the six big-endian words of this thread's sub-sequence (bytes at or past z read as zero)
+__device__ __forceinline__ void dec_row_words(const RowRegs &r, uint64_t z, uint64_t seq_in_block, uint32_t (&w)[DEC_ROW_WORDS])
 {
-    const unsigned tid = threadIdx.x;
-    const uint64_t o = seq_in_block * DEC_SEQ_BYTES + (uint64_t)tid * 16;
-    uint32_t w[DEC_ROW_WORDS] = {r.v.x, r.v.y, r.v.z, r.v.w, r.u.x, r.u.y};
+    const uint64_t o = seq_in_block * DEC_SEQ_BYTES + (uint64_t)threadIdx.x * 16;
+    w[0] = r.v.x, w[1] = r.v.y, w[2] = r.v.z, w[3] = r.v.w, w[4] = r.u.x, w[5] = r.u.y;
     if (o + 4 * DEC_ROW_WORDS > z) {  // only at the end of a block
 #pragma unroll
         for (int k = 0; k < DEC_ROW_WORDS; k++) {
@@ -63,6 +63,12 @@ __device__ __forceinline__ void dec_store_row(uint64_t *pairs, const RowRegs &r,
     }
 #pragma unroll
     for (int k = 0; k < DEC_ROW_WORDS; k++) w[k] = bswap32(w[k]);
+}
+__device__ __forceinline__ void dec_store_row(uint64_t *pairs, const RowRegs &r, uint64_t z, uint64_t seq_in_block)
+{
+    const unsigned tid = threadIdx.x;
+    uint32_t w[DEC_ROW_WORDS];
+    dec_row_words(r, z, seq_in_block, w);
     uint64_t row[DEC_ROW];
     dec_row_from_words(w, row);
 #pragma unroll

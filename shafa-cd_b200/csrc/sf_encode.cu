@@ -121,8 +121,8 @@ k_sf_offsets(const uint64_t *__restrict__ bits, const uint32_t *__restrict__ fla
 // ---- fast path ------------------------------------------------------------------------
 struct EncShared {
     uint32_t lut[256 * ENC_COPIES];       // lut[sym*32 + lane]
-    uint32_t stage[ENC_STAGE_WORDS + 8];  // big-endian words of (a window of) this tile's bit range
-    uint32_t entry[256];
+    uint32_t stage[ENC_STAGE_WORDS + 8];  // big-endian words of (a window of) this tile's bit range; its first 256 words double as
+                                          // the scratch of the LUT build at a block change (barrier-separated from the tile's use)
     uint32_t scan[ENC_THREADS / 32 + 1];
     uint64_t prefix;
     uint32_t ticket;
@@ -233,7 +233,10 @@ __device__ __forceinline__ void enc_pack_thread(uint32_t lut_lane, uint32_t stag
     }
 }
 
-__global__ void __launch_bounds__(ENC_THREADS, 4)
+#ifndef SHAFA_ENC_MIN_CTAS
+#define SHAFA_ENC_MIN_CTAS 4
+#endif
+__global__ void __launch_bounds__(ENC_THREADS, SHAFA_ENC_MIN_CTAS)
 k_sf_encode(const uint8_t *__restrict__ in, const uint64_t *__restrict__ off, const uint64_t *__restrict__ tile0,
             uint32_t nb, const uint8_t *__restrict__ lens, const uint64_t *__restrict__ codes,
             const uint64_t *__restrict__ pay_off, uint8_t *__restrict__ payload, uint64_t *__restrict__ desc,
@@ -273,12 +276,12 @@ k_sf_encode(const uint8_t *__restrict__ in, const uint64_t *__restrict__ off, co
             cur_long = __syncthreads_or(l > (uint32_t)ENC_SHORT_MAX) != 0;
             cur_pair = __syncthreads_or(l > 16u) == 0;
             if (!cur_long) {
-                sh.entry[tid] = enc_entry(c, l);
+                sh.stage[tid] = enc_entry(c, l);
                 __syncthreads();
 #pragma unroll 4
                 for (int i = 0; i < ENC_COPIES; i++) {
                     const int idx = i * ENC_THREADS + tid;  // consecutive lanes -> consecutive banks
-                    sh.lut[idx] = sh.entry[idx / ENC_COPIES];
+                    sh.lut[idx] = sh.stage[idx / ENC_COPIES];
                 }
                 __syncthreads();
             }

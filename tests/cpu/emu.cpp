@@ -562,6 +562,7 @@ static Bytes emu_sf_decode(const Bytes &payload, uint64_t n, const uint8_t *len,
     const uint64_t nseq = (z + DEC_SEQ_BYTES - 1) / DEC_SEQ_BYTES;
     std::vector<uint16_t> start(nseq * DEC_THREADS), count(nseq * DEC_THREADS);
     std::vector<uint32_t> seq_end(nseq);
+    std::vector<uint32_t> wordsv(DEC_THREADS * DEC_ROW_WORDS);  // the same sub-sequences as register words (dec_*_words)
     auto load_pairs = [&](uint64_t seq, std::vector<uint64_t> &pairs) {  // dec_load_rows: one row per sub-sequence
         pairs.assign(DEC_PAIR_SLOTS, 0);
         for (int sid = 0; sid < DEC_THREADS; sid++) {
@@ -573,9 +574,13 @@ static Bytes emu_sf_decode(const Bytes &payload, uint64_t n, const uint8_t *len,
                     w = (w << 8) | (bo < z ? payload[bo] : 0);
                 }
                 words[i] = w;
+                wordsv[(size_t)sid * DEC_ROW_WORDS + i] = w;
             }
             dec_row_from_words(words, pairs.data() + (size_t)sid * DEC_ROW);
         }
+    };
+    auto words_of = [&](int sid) -> const uint32_t (&)[DEC_ROW_WORDS] {
+        return *reinterpret_cast<const uint32_t (*)[DEC_ROW_WORDS]>(wordsv.data() + (size_t)sid * DEC_ROW_WORDS);
     };
     auto sub_stop = [](uint32_t limit, uint32_t sub_lo) -> uint32_t {
         return limit > sub_lo ? std::min<uint32_t>(limit - sub_lo, DEC_SUB_BITS) : 0u;
@@ -593,6 +598,8 @@ static Bytes emu_sf_decode(const Bytes &payload, uint64_t n, const uint8_t *len,
             DecSub r = dec_count_subsequence(t, tid * DEC_ROW, st[tid], stop);
             DecSub r1 = dec_emit_subsequence(t, tid * DEC_ROW, st[tid], stop, DecNoEmit());
             CHECK(r.end == r1.end && r.count == r1.count, "multi-symbol and single-symbol walks disagree");
+            const DecSub rw = dec_count_words(t, words_of(tid), st[tid], stop);
+            CHECK(rw.end == r.end && rw.count == r.count && rw.bad == r.bad, "register-window count walk disagrees with the row walk");
             en[tid] = r.end > (uint32_t)DEC_SUB_BITS ? r.end - DEC_SUB_BITS : 0;
             cn[tid] = r.count;
         };
@@ -661,6 +668,15 @@ static Bytes emu_sf_decode(const Bytes &payload, uint64_t n, const uint8_t *len,
                 DecSub r = dec_emit_subsequence(t, tid * DEC_ROW, start[gi], sub_stop(limit, tid * DEC_SUB_BITS),
                                                 [&](uint32_t i, uint32_t sym) { if (i < room) dst[i] = (uint8_t)sym; });
                 CHECK(r.count == count[gi], "final decode count differs from the recorded count");
+                {
+                    Bytes alt(r.count + 2);
+                    auto put = [&](uint32_t i, uint32_t sym) { alt[i] = (uint8_t)sym; };
+                    DecFnSink<decltype(put)> sink{put, 0u};
+                    const DecSub rw = dec_emit_words(t, words_of(tid), start[gi], sub_stop(limit, tid * DEC_SUB_BITS), sink);
+                    Bytes ref(r.count + 2);
+                    dec_emit_subsequence(t, tid * DEC_ROW, start[gi], sub_stop(limit, tid * DEC_SUB_BITS), [&](uint32_t i, uint32_t sym) { ref[i] = (uint8_t)sym; });
+                    CHECK(rw.end == r.end && rw.count == r.count && alt == ref, "register-window emit walk disagrees with the row walk");
+                }
                 if (r.bad) bad = true;
             }
             first += count[gi];
