@@ -143,7 +143,6 @@ k_dec_seqrec(DecPlan plan, DecSeqRec *__restrict__ rec)
 
 // ---- shared helpers -----------------------------------------------------------------------
 constexpr int DEC_MAP_MAX = 16;     // longest code for which the all-starts fallback of k_dec_sync is used
-constexpr int DEC_FB_BYTES = DEC_THREADS * DEC_MAP_MAX * 2 + (DEC_THREADS / 32) * DEC_MAP_MAX * 33;  // per CTA: map + paths
 constexpr int DEC_MAX_ROUNDS = 12;  // sync rounds before that fallback is taken in any case
 constexpr int DEC_STAGE = 12288;  // symbols of one sequence staged in shared memory before the coalesced copy-out
 
@@ -293,7 +292,7 @@ __device__ __forceinline__ void dec_chunk(uint64_t nseq, uint64_t *first, uint64
 // ---- phase 1: synchronise inside each sequence ----------------------------------------------
 __global__ void __launch_bounds__(DEC_THREADS, 6)
 k_dec_sync(const uint8_t *__restrict__ payload, DecPlan plan, DecTablesGlobal g, uint16_t *__restrict__ sub_info,
-           uint32_t *__restrict__ seq_end, uint32_t *__restrict__ seq_count, uint64_t nseq, uint8_t *__restrict__ fallback)
+           uint32_t *__restrict__ seq_end, uint32_t *__restrict__ seq_count, uint64_t nseq)
 {
     __shared__ DecShared sh;
     __shared__ __align__(16) uint8_t s_lut2[DEC_LUT2_SIZE];
@@ -304,11 +303,15 @@ k_dec_sync(const uint8_t *__restrict__ payload, DecPlan plan, DecTablesGlobal g,
     __shared__ uint32_t s_wcnt[DEC_THREADS / 32];
     __shared__ uint32_t s_nlist;
     __shared__ uint32_t s_wsum[DEC_THREADS / 32];
-    // tables of the all-starts fallback: rarely used, so they live in this CTA's slice of a global scratch buffer
-    // (L2-resident) instead of costing every launch 12 KiB of shared memory and a CTA per SM
-    uint16_t *const s_map = reinterpret_cast<uint16_t *>(fallback + (size_t)blockIdx.x * DEC_FB_BYTES);  // [sub-sequence][start] -> (overshoot << 10) | count
-    uint8_t *const s_path = reinterpret_cast<uint8_t *>(s_map + DEC_THREADS * DEC_MAP_MAX);               // [warp][entry offset][i]: start of the warp's i-th sub-sequence
-    uint8_t *const s_path_out = s_path + (DEC_THREADS / 32) * DEC_MAP_MAX * 32;                          // [warp][entry offset]: offset handed to the next warp
+    // Tables of the all-starts path.  They alias shared memory that path does not need: the maps take the place of lut2
+    // (all starts are walked with lut1), the chain paths the place of the payload rows (every thread has moved its row into
+    // registers by then).  They were in a global scratch slice before: on C4 (every block takes this path) the 2-byte map
+    // stores of a warp, 32 bytes apart, cost 18 x the payload in L2 sector writes (dec_sync 8.7 -> 6.7 ms/GiB).
+    static_assert(DEC_THREADS * DEC_MAP_MAX * 2 <= DEC_LUT2_SIZE, "maps fit the lut2 area");
+    static_assert((DEC_THREADS / 32) * DEC_MAP_MAX * 33 <= DEC_PAIR_SLOTS * 8, "paths fit the row area");
+    uint16_t *const s_map = reinterpret_cast<uint16_t *>(s_lut2);                             // [sub-sequence][start] -> (overshoot << 10) | count
+    uint8_t *const s_path = reinterpret_cast<uint8_t *>(sh.pairs);                            // [warp][entry offset][i]: start of the warp's i-th sub-sequence
+    uint8_t *const s_path_out = s_path + (DEC_THREADS / 32) * DEC_MAP_MAX * 32;               // [warp][entry offset]: offset handed to the next warp
     __shared__ uint32_t s_maxlen;
     __shared__ uint32_t s_nosync;  // the block's code has nearly one length (k_dec_tables): go to all starts at once
     const unsigned tid = threadIdx.x, lane = lane_id(), warp = warp_id();
@@ -442,6 +445,7 @@ k_dec_sync(const uint8_t *__restrict__ payload, DecPlan plan, DecTablesGlobal g,
                     s_ends[tid] = e >> 10;
                 }
                 __syncthreads();
+                if (!all_starts_now) cur_block = 0xffffffffu;  // the maps overwrote lut2: it has to come back before the next sequence
                 break;
             }
             if (total > DEC_THREADS / 4) {
@@ -620,7 +624,10 @@ struct StageSink {
     __device__ __forceinline__ uint32_t count() const { return addr - base; }
 };
 
-__global__ void __launch_bounds__(DEC_THREADS, 5)
+#ifndef SHAFA_DECW_MIN_CTAS
+#define SHAFA_DECW_MIN_CTAS 5
+#endif
+__global__ void __launch_bounds__(DEC_THREADS, SHAFA_DECW_MIN_CTAS)
 k_dec_write(const uint8_t *__restrict__ payload, DecPlan plan, DecTablesGlobal g,
             const uint16_t *__restrict__ sub_info, const uint64_t *__restrict__ seq_excl, uint8_t *__restrict__ out,
             uint64_t nseq, uint32_t *__restrict__ err)
@@ -796,10 +803,8 @@ static int launch_sf_decode_exact(shafa_cuda_ctx *ctx, const uint8_t *d_payload,
     uint64_t grid_sync = (uint64_t)ctx->sm_count * occ_sync * 4, grid_write = (uint64_t)ctx->sm_count * occ_write * 4;
     if (grid_sync > nseq) grid_sync = nseq;
     if (grid_write > nseq) grid_write = nseq;
-    uint8_t *fb = (uint8_t *)scratch_get(ctx, SCR_DEC_FB, (size_t)grid_sync * DEC_FB_BYTES);
-    if (!fb) return SHAFA_LACK_OF_MEMORY;
     SHAFA_LAUNCH(ctx, "dec_sync", k_dec_sync, dim3((unsigned)grid_sync), dim3(DEC_THREADS), 0, d_payload, plan, g, sub_info,
-                 seq_end, seq_count, nseq, fb);
+                 seq_end, seq_count, nseq);
     SHAFA_CHECK_LAUNCH(ctx);
     // Stitch across chunk boundaries until a pass moves no sequence end.  The first pass almost always settles it and the
     // second then moves nothing, so the normal path launches two passes back to back with NO host round trip in

@@ -1,7 +1,10 @@
-timeout 600 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_configs.py -x -q -m gpu > gpurun_out/t11.log 2>&1; tail -3 gpurun_out/t11.log
-bash tools/ab_bench.sh
-timeout 600 python bench.py --workload C4 --steps 3 --warmup 3 --no-cpu --no-files > gpurun_out/b11_c4.json 2> gpurun_out/b11_c4.err; python - <<P
+timeout 600 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_configs.py -x -q -m gpu > gpurun_out/t13.log 2>&1; tail -3 gpurun_out/t13.log
+bash tools/ab_bench.sh dw6 enc5 dw6enc5
+for w in C4 C5; do timeout 600 python bench.py --workload $w --steps 3 --warmup 3 --no-cpu --no-files > gpurun_out/b13_$w.json 2> gpurun_out/b13_$w.err; python - <<P
 import json
-j=json.load(open("gpurun_out/b11_c4.json"))
-print(j["value"], j["encode_gbs"], j["decode_gbs"], {k:(v.get("ms_per_step")) for k,v in j["kernels"].items() if v.get("ms_per_step",0)>0.05})
+try:
+    j=json.load(open("gpurun_out/b13_$w.json"))
+    print("$w", j["value"], j.get("encode_gbs"), j.get("decode_gbs"), {k:(v.get("ms_per_step")) for k,v in j["kernels"].items() if v.get("ms_per_step",0)>0.05})
+except Exception as e: print("$w failed", e)
 P
+done
