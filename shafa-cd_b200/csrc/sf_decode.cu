@@ -244,6 +244,12 @@ struct DecViewS {
         asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(lut1_s + i * 2u));
         return v;
     }
+    __device__ __forceinline__ uint32_t l1len(uint32_t i) const  // low byte of the entry: the code length
+    {
+        uint32_t v;
+        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(lut1_s + i * 2u));
+        return v;
+    }
     __device__ __forceinline__ uint32_t l2(uint32_t i) const
     {
         uint32_t v;
@@ -314,6 +320,7 @@ k_dec_sync(const uint8_t *__restrict__ payload, DecPlan plan, DecTablesGlobal g,
     uint8_t *const s_path_out = s_path + (DEC_THREADS / 32) * DEC_MAP_MAX * 32;               // [warp][entry offset]: offset handed to the next warp
     __shared__ uint32_t s_maxlen;
     __shared__ uint32_t s_nosync;  // the block's code has nearly one length (k_dec_tables): go to all starts at once
+    __shared__ uint32_t s_lean;    // ... and it is complete with no code longer than the lut1 window: lengths come straight from lut1
     const unsigned tid = threadIdx.x, lane = lane_id(), warp = warp_id();
     uint64_t seq_first, seq_last;
     dec_chunk(nseq, &seq_first, &seq_last);
@@ -335,10 +342,21 @@ k_dec_sync(const uint8_t *__restrict__ payload, DecPlan plan, DecTablesGlobal g,
             if (tid == 0) {
                 s_maxlen = 0;
                 s_nosync = (g.flags[b] & DECB_NOSYNC) != 0;
+                s_lean = (g.flags[b] & DECB_COMPLETE) != 0;
             }
             __syncthreads();
             const uint32_t wmax = __reduce_max_sync(FULL, (uint32_t)sh.slen[tid]);
             if (lane == 0) atomicMax(&s_maxlen, wmax);
+            {
+                // the lean all-starts loop trusts lut1 blindly (a zero length would never advance): look at every entry once
+                uint32_t odd = 0;
+                const uint32_t *l32 = reinterpret_cast<const uint32_t *>(sh.lut1);
+                for (int i = tid; i < DEC_LUT_SIZE / 2; i += DEC_THREADS) {
+                    const uint32_t e2 = l32[i];
+                    odd |= (uint32_t)(((e2 & 0xFFu) - 1u >= (uint32_t)DEC_LUT_BITS) | (((e2 >> 16) & 0xFFu) - 1u >= (uint32_t)DEC_LUT_BITS));
+                }
+                if (__syncthreads_or((int)odd) && tid == 0) s_lean = 0;
+            }
         }
         // The first sub-sequence starts where the previous sequence ended.  Inside a chunk that is known;
         // the first sequence of a chunk assumes 0 and k_dec_stitch repairs it (a block's first sequence IS 0).
@@ -396,24 +414,42 @@ k_dec_sync(const uint8_t *__restrict__ payload, DecPlan plan, DecTablesGlobal g,
                         w[k] = (uint32_t)(pr >> 32);
                         if (k == DEC_ROW - 1) w[k + 1] = (uint32_t)pr;
                     }
-                    for (uint32_t st = 0; st < maxlen; st++) {
-                        uint32_t q = st, count = 0, bad_dummy = 0;
+                    if (s_lean) {
+                        // a complete code without long codes: every 12-bit window holds a code, its length is the low
+                        // byte of the lut1 entry -- one funnel shift, one byte load, two adds per code and nothing else
+                        for (uint32_t st = 0; st < maxlen; st++) {
+                            uint32_t q = st, count = 0;
 #pragma unroll
-                        for (int i = 0; i < DEC_SUB_BITS / 32; i++) {
-                            const uint32_t lim = stop < 32u * (i + 1) ? stop : 32u * (i + 1);
-                            while (q < lim) {
-                                const uint32_t e = t.l1(__funnelshift_l(w[i + 1], w[i], q) >> (32 - DEC_LUT_BITS));
-                                uint32_t l = e & 0xFFu;
-                                if (l - 1u >= (uint32_t)DEC_LUT_BITS) {  // a code longer than the table window (or none): generic step
-                                    uint32_t sym;
-                                    l = dec_one(t, tid * DEC_ROW, q, &sym, &bad_dummy);
+                            for (int i = 0; i < DEC_SUB_BITS / 32; i++) {
+                                const uint32_t lim = stop < 32u * (i + 1) ? stop : 32u * (i + 1);
+                                while (q < lim) {
+                                    q += t.l1len(__funnelshift_l(w[i + 1], w[i], q) >> (32 - DEC_LUT_BITS));
+                                    count++;
                                 }
-                                q += l;
-                                count++;
                             }
+                            const uint32_t over = q > (uint32_t)DEC_SUB_BITS ? q - DEC_SUB_BITS : 0u;
+                            s_map[tid * DEC_MAP_MAX + st] = (uint16_t)((over << 10) | count);
                         }
-                        const uint32_t over = q > (uint32_t)DEC_SUB_BITS ? q - DEC_SUB_BITS : 0u;
-                        s_map[tid * DEC_MAP_MAX + st] = (uint16_t)((over << 10) | count);
+                    } else {
+                        for (uint32_t st = 0; st < maxlen; st++) {
+                            uint32_t q = st, count = 0, bad_dummy = 0;
+#pragma unroll
+                            for (int i = 0; i < DEC_SUB_BITS / 32; i++) {
+                                const uint32_t lim = stop < 32u * (i + 1) ? stop : 32u * (i + 1);
+                                while (q < lim) {
+                                    const uint32_t e = t.l1(__funnelshift_l(w[i + 1], w[i], q) >> (32 - DEC_LUT_BITS));
+                                    uint32_t l = e & 0xFFu;
+                                    if (l - 1u >= (uint32_t)DEC_LUT_BITS) {  // a code longer than the table window (or none): generic step
+                                        uint32_t sym;
+                                        l = dec_one(t, tid * DEC_ROW, q, &sym, &bad_dummy);
+                                    }
+                                    q += l;
+                                    count++;
+                                }
+                            }
+                            const uint32_t over = q > (uint32_t)DEC_SUB_BITS ? q - DEC_SUB_BITS : 0u;
+                            s_map[tid * DEC_MAP_MAX + st] = (uint16_t)((over << 10) | count);
+                        }
                     }
                 }
                 __syncthreads();
@@ -500,8 +536,11 @@ __device__ __forceinline__ uint64_t window_global(const uint8_t *base, uint64_t 
 __global__ void __launch_bounds__(128)
 k_dec_stitch(const uint8_t *__restrict__ payload, DecPlan plan, DecTablesGlobal g, uint16_t *__restrict__ sub_info,
              uint32_t *__restrict__ seq_end, uint32_t *__restrict__ seq_count, uint64_t nseq,
-             uint32_t *__restrict__ changed_flag)
+             uint32_t *__restrict__ changed_flag, const uint32_t *__restrict__ prev_changed)
 {
+    // a pass in which no sequence end moved leaves every sequence consistent with its predecessor: the pass after it
+    // (launched blind, without a host round trip) has nothing to do
+    if (prev_changed && *prev_changed == 0) return;
     const uint64_t seq = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (seq >= nseq) return;
     const uint32_t b = find_block(plan.seq0, plan.nb, seq);
@@ -817,14 +856,14 @@ static int launch_sf_decode_exact(shafa_cuda_ctx *ctx, const uint8_t *d_payload,
         SHAFA_CUDA_TRY(ctx, cudaMemsetAsync(flag, 0, 8, ctx->stream));
         for (int pass = 0; pass < 2; pass++)
             SHAFA_LAUNCH(ctx, "dec_stitch", k_dec_stitch, dim3((unsigned)((nseq + 127) / 128)), dim3(128), 0, d_payload,
-                         plan, g, sub_info, seq_end, seq_count, nseq, flag + pass);
+                         plan, g, sub_info, seq_end, seq_count, nseq, flag + pass, pass ? (const uint32_t *)flag : (const uint32_t *)nullptr);
         SHAFA_CHECK_LAUNCH(ctx);
         still_moving = flag + 1;
     }
     for (uint64_t pass = 0; careful_stitch; pass++) {
         SHAFA_CUDA_TRY(ctx, cudaMemsetAsync(flag, 0, 4, ctx->stream));
         SHAFA_LAUNCH(ctx, "dec_stitch", k_dec_stitch, dim3((unsigned)((nseq + 127) / 128)), dim3(128), 0, d_payload,
-                     plan, g, sub_info, seq_end, seq_count, nseq, flag);
+                     plan, g, sub_info, seq_end, seq_count, nseq, flag, (const uint32_t *)nullptr);
         SHAFA_CHECK_LAUNCH(ctx);
         SHAFA_CUDA_TRY(ctx, cudaMemcpyAsync(h_flag, flag, 4, cudaMemcpyDeviceToHost, ctx->stream));
         SHAFA_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
