@@ -526,11 +526,14 @@ struct DecView {
     const uint16_t *lut1;
     const uint8_t *lut2;
     const uint32_t *lut3;
+    const uint8_t *lut16;
     const uint64_t *sleft;
     const uint8_t *slen;
     const uint8_t *ssym;
     SHAFA_HD uint64_t pair(uint32_t slot) const { return pairs[slot]; }
     SHAFA_HD uint32_t l1(uint32_t i) const { return lut1[i]; }
+    SHAFA_HD uint32_t l1len(uint32_t i) const { return lut1[i] & 0xFFu; }
+    SHAFA_HD uint32_t l16(uint32_t i) const { return lut16[i]; }
     SHAFA_HD uint32_t l2(uint32_t i) const { return lut2[i]; }
     SHAFA_HD uint32_t l3(uint32_t i) const { return lut3[i]; }
     SHAFA_HD bool has_l3() const { return lut3 != nullptr; }
@@ -783,6 +786,90 @@ SHAFA_HD uint8_t dec_lut2_entry(const uint16_t *lut1, uint32_t e)
         n++;
     }
     return (uint8_t)(n ? ((n << 4) | pos) : 0);  // n, pos <= 13
+}
+
+// ---- codes of nearly one length ("lean" blocks: complete code, no code longer than the lut1 window, 2 * shortest >
+// longest) ----------------------------------------------------------------------------------------------------------
+// Such codes never re-synchronise, so k_dec_sync_lean walks every sub-sequence from every start that can occur.  The
+// walks are bound by shared-memory table gathers (random 12-bit indices: 2.8 bank-conflict wavefronts per warp load,
+// LSU pipe 95 % busy on C4), so the remedy is fewer loads: lut16 maps a 16-bit window to ALL whole codes inside it
+// (two 8-bit codes on uniform bytes), one byte per entry: (codes << 5) | bits, at most seven codes, bits <= 16.
+constexpr int DEC_LUT16_BITS = 16;
+constexpr int DEC_LUT16_SIZE = 1 << DEC_LUT16_BITS;
+SHAFA_HD uint8_t dec_lut16_entry(const uint16_t *lut1, uint32_t v)
+{
+    uint32_t pos = 0, n = 0;
+    while (n < 7u) {
+        const uint32_t l = lut1[(((v << pos) & 0xFFFFu) >> (DEC_LUT16_BITS - DEC_LUT_BITS))] & 0xFFu;  // the 12 bits from pos, zero padded
+        if (l - 1u >= (uint32_t)DEC_LUT_BITS || pos + l > (uint32_t)DEC_LUT16_BITS) break;              // must fit entirely
+        pos += l;
+        n++;
+    }
+    return n ? (uint8_t)((n << 5) | pos) : (uint8_t)((1u << 5) | 1u);  // (n = 0 cannot happen for a lean block; one code of one bit still advances)
+}
+
+// (count, end) of the chains of codes from the NS consecutive starts start0, start0 + 1, ... while they are inside
+// [.., stop): several codes per lookup while a whole 16-bit window lies before `stop`, one code per lookup (length = low
+// byte of lut1) for the last few bits.  The NS chains are independent, so their table loads are in flight together:
+// the kernel runs two CTAs of eight warps per SM (the table is 64 KiB) and would otherwise wait for one load at a time.
+template <int NS, typename V>
+SHAFA_HD void dec_lean_walk(const V &t, const uint32_t (&w)[DEC_ROW_WORDS], uint32_t start0, uint32_t stop, uint32_t (&count)[NS], uint32_t (&end)[NS])
+{
+    uint32_t q[NS], cnt[NS];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int k = 0; k < NS; k++) {
+        q[k] = start0 + (uint32_t)k;
+        cnt[k] = 0;
+    }
+    const uint32_t multi_end = stop >= (uint32_t)DEC_LUT16_BITS ? stop - (uint32_t)DEC_LUT16_BITS + 1u : 0u;  // q < multi_end: q + 16 <= stop
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int i = 0; i < DEC_SUB_BITS / 32; i++) {  // the word of q is a compile-time index: a window is one funnel shift of two registers
+        const uint32_t lim = stop < 32u * (uint32_t)(i + 1) ? stop : 32u * (uint32_t)(i + 1);
+        const uint32_t lim16 = multi_end < lim ? multi_end : lim;
+        // (the exit tests come BEFORE the loads: a trailing iteration that only finds every chain done would cost as many
+        // table loads as a useful one -- measured: 2.2 x the instructions and 3 x the shared-memory wavefronts)
+        auto any_below = [&](uint32_t bound) {
+            bool any = false;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+            for (int k = 0; k < NS; k++) any |= q[k] < bound;
+            return any;
+        };
+        while (any_below(lim16)) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+            for (int k = 0; k < NS; k++) {  // branch-free per chain: a chain that has left the word just does not move
+                const bool a = q[k] < lim16;
+                const uint32_t e = t.l16(funnel_l(w[i + 1], w[i], q[k]) >> (32 - DEC_LUT16_BITS));
+                q[k] += a ? (e & 31u) : 0u;
+                cnt[k] += a ? (e >> 5) : 0u;
+            }
+        }
+        while (any_below(lim)) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+            for (int k = 0; k < NS; k++) {
+                const bool a = q[k] < lim;
+                const uint32_t l = t.l1len(funnel_l(w[i + 1], w[i], q[k]) >> (32 - DEC_LUT_BITS));
+                q[k] += a ? l : 0u;
+                cnt[k] += a ? 1u : 0u;
+            }
+        }
+    }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int k = 0; k < NS; k++) {
+        count[k] = cnt[k];
+        end[k] = q[k];
+    }
 }
 
 // lut3 entry for the 12-bit window value e: its first one or two whole codes.

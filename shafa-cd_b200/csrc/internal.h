@@ -27,6 +27,8 @@ enum ScratchSlot {
     SCR_DEC_SEQ,    // decode sequence info
     SCR_DEC_FB,     // decode sync: per-CTA tables of the all-starts fallback
     SCR_DEC_REC,    // fused decoder: per-sequence records
+    SCR_DEC_CLS,    // decode sync: sequence numbering of the two classes, lean table slots
+    SCR_DEC_LUT16,  // decode sync: 16-bit multi-code tables of the lean blocks
     SCR_STAGE_A,    // host API staging (input)
     SCR_STAGE_B,
     SCR_STAGE_C,
@@ -114,7 +116,7 @@ enum ErrBits : uint32_t {
     ERR_STITCH = 512,        // exact SF decoder: sequence ends still moved in the second stitch pass (decode again, polling)
     ERR_TIMEOUT = 256        // fused SF decoder: a bounded device-side wait gave up (never seen; keeps a bug from hanging the GPU)
 };
-enum OccId { OCC_SF_ENCODE = 0, OCC_RLE_ENC = 1 /* +variant 0..3 */, OCC_RLE_DEC = 5, OCC_DEC_SYNC = 6, OCC_DEC_WRITE = 7, OCC_HIST = 8, OCC_DEC_FUSED = 9 };
+enum OccId { OCC_SF_ENCODE = 0, OCC_RLE_ENC = 1 /* +variant 0..3 */, OCC_RLE_DEC = 5, OCC_DEC_SYNC = 6, OCC_DEC_WRITE = 7, OCC_HIST = 8, OCC_DEC_FUSED = 9, OCC_DEC_LEAN = 10 };
 enum MiscSlot { MISC_COUNTER = 0, MISC_FLAG = 16, MISC_ERR = 32, MISC_WORDS = 64 };  // uint32 indices into SCR_MISC
 uint32_t *misc_ptr(shafa_cuda_ctx *ctx, int which);
 shafa_cuda_ctx *worker_ctx(shafa_cuda_ctx *ctx, int i);  // lazily created child context i (0..3) on the same device

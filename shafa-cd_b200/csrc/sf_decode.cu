@@ -85,6 +85,7 @@ k_dec_tables(const uint8_t *__restrict__ lens, const uint64_t *__restrict__ code
             if (!any_clash && hi == 1ull && lo == 0ull) f |= DECB_COMPLETE;
             if (2u * minlen > maxlen) f |= DECB_NOSYNC;
             if (maxlen > 32u) f |= DECB_WIDE;
+            if (maxlen <= (uint32_t)DEC_LUT_BITS) f |= DECB_SHORT;
             s_flags = f;
             g.flags[b] = (uint8_t)f;
         }
@@ -187,22 +188,25 @@ __device__ __forceinline__ RowRegs dec_fetch_row(const uint8_t *payload, uint64_
     return r;
 }
 // Which block a sequence belongs to, tracked incrementally while a CTA walks its chunk (every thread
-// keeps the same copy: no broadcast through shared memory, no barrier).
+// keeps the same copy: no broadcast through shared memory, no barrier).  `seq0` is the numbering the
+// kernel walks: all sequences (plan.seq0), or the sequences of one class (plan.cls_seq0[c]).
 struct SeqCursor {
+    const uint64_t *seq0;
     uint32_t b;
-    uint64_t first, next;  // block b holds sequences [first, next)
-    __device__ __forceinline__ void init(const DecPlan &plan, uint64_t seq)
+    uint64_t first, next;  // block b holds sequences [first, next) of that numbering
+    __device__ __forceinline__ void init(const uint64_t *numbering, uint32_t nb, uint64_t seq)
     {
-        b = find_block(plan.seq0, plan.nb, seq);
-        first = plan.seq0[b];
-        next = plan.seq0[b + 1];
+        seq0 = numbering;
+        b = find_block(seq0, nb, seq);
+        first = seq0[b];
+        next = seq0[b + 1];
     }
-    __device__ __forceinline__ void advance_to(const DecPlan &plan, uint64_t seq)
+    __device__ __forceinline__ void advance_to(uint64_t seq)
     {
-        while (seq >= next) {  // skips blocks without payload
+        while (seq >= next) {  // skips blocks without sequences of this numbering
             b++;
             first = next;
-            next = plan.seq0[b + 1];
+            next = seq0[b + 1];
         }
     }
 };
@@ -215,13 +219,89 @@ struct SeqFetch {
 };
 __device__ __forceinline__ SeqFetch dec_fetch_seq(const uint8_t *payload, const DecPlan &plan, SeqCursor &c, uint64_t seq)
 {
-    c.advance_to(plan, seq);
+    c.advance_to(seq);
     SeqFetch f;
     f.b = c.b;
-    f.sib = seq - c.first;
+    f.sib = seq - c.first;  // a block's sequences all belong to one class: the same index in every numbering
     f.z = plan.z[c.b];
     f.row = dec_fetch_row(payload, plan.pay_off[c.b], f.z, f.sib);
     return f;
+}
+
+// ---- lean blocks: the 16-bit multi-code table and the two sequence classes ---------------------------------------
+__global__ void __launch_bounds__(256)
+k_dec_lut16(DecPlan plan, DecTablesGlobal g)
+{
+    // lut1 with one pad entry after every 16: the windows of a warp's second codes are 16 entries apart (the low four
+    // bits of a 12-bit window past the end of a 16-bit one are zero) and would all fall into one bank
+    __shared__ uint16_t lut1p[DEC_LUT_SIZE + DEC_LUT_SIZE / 16];
+    const uint32_t b = blockIdx.x;
+    if (!dec_block_lean(g.flags[b], plan.z[b])) return;
+    for (int e = threadIdx.x; e < DEC_LUT_SIZE; e += 256) lut1p[e + (e >> 4)] = g.lut[(uint64_t)b * DEC_LUT_SIZE + e];
+    __syncthreads();
+    uint32_t *dst = reinterpret_cast<uint32_t *>(g.lut16 + (uint64_t)plan.lean_slot[b] * DEC_LUT16_SIZE);
+    for (uint32_t q = threadIdx.x; q < (uint32_t)DEC_LUT16_SIZE / 4; q += 256) {
+        uint32_t four = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            // core.h: dec_lut16_entry, reading the padded table
+            const uint32_t v = 4u * q + (uint32_t)k;
+            uint32_t pos = 0, n = 0;
+            while (n < 7u) {
+                const uint32_t i = ((v << pos) & 0xFFFFu) >> (DEC_LUT16_BITS - DEC_LUT_BITS);
+                const uint32_t l = lut1p[i + (i >> 4)] & 0xFFu;
+                if (l - 1u >= (uint32_t)DEC_LUT_BITS || pos + l > (uint32_t)DEC_LUT16_BITS) break;
+                pos += l;
+                n++;
+            }
+            four |= (n ? ((n << 5) | pos) : ((1u << 5) | 1u)) << (8 * k);
+        }
+        dst[q] = four;
+    }
+}
+
+// one CTA: number the sequences of the two classes in block order, hand every lean block its table slot
+// out: cls[0][nb+1], cls[1][nb+1] (u64), slot[nb] (u32)
+__global__ void __launch_bounds__(256)
+k_dec_classes(const uint64_t *__restrict__ seq0, const uint64_t *__restrict__ z, const uint8_t *__restrict__ flags, uint32_t nb,
+              uint64_t *__restrict__ cls0, uint64_t *__restrict__ cls1, uint32_t *__restrict__ slot)
+{
+    __shared__ uint32_t scan[9];
+    __shared__ uint64_t carry[3];
+    if (threadIdx.x < 3) carry[threadIdx.x] = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < nb; base += 256) {
+        const uint32_t b = base + threadIdx.x;
+        uint32_t n0 = 0, n1 = 0, lean = 0;
+        if (b < nb) {
+            const uint32_t ns = (uint32_t)(seq0[b + 1] - seq0[b]);
+            lean = dec_block_lean(flags[b], z[b]) ? 1u : 0u;
+            n0 = lean ? 0u : ns;
+            n1 = lean ? ns : 0u;
+        }
+        uint32_t t0, t1, t2;
+        const uint32_t e0 = block_excl_scan<256>(n0, scan, &t0);
+        __syncthreads();
+        const uint32_t e1 = block_excl_scan<256>(n1, scan, &t1);
+        __syncthreads();
+        const uint32_t e2 = block_excl_scan<256>(lean, scan, &t2);
+        if (b < nb) {
+            cls0[b] = carry[0] + e0;
+            cls1[b] = carry[1] + e1;
+            slot[b] = (uint32_t)carry[2] + e2;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            carry[0] += t0;
+            carry[1] += t1;
+            carry[2] += t2;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        cls0[nb] = carry[0];
+        cls1[nb] = carry[1];
+    }
 }
 
 // The decode loops read the tables through 32-bit shared-memory addresses computed once per sequence
@@ -298,8 +378,10 @@ __device__ __forceinline__ void dec_chunk(uint64_t nseq, uint64_t *first, uint64
 // ---- phase 1: synchronise inside each sequence ----------------------------------------------
 __global__ void __launch_bounds__(DEC_THREADS, 6)
 k_dec_sync(const uint8_t *__restrict__ payload, DecPlan plan, DecTablesGlobal g, uint16_t *__restrict__ sub_info,
-           uint32_t *__restrict__ seq_end, uint32_t *__restrict__ seq_count, uint64_t nseq)
+           uint32_t *__restrict__ seq_end, uint32_t *__restrict__ seq_count)
 {
+    // this kernel's sequences: class 0 (everything but the lean blocks), numbered densely by k_dec_classes
+    const uint64_t nseq = plan.cls_seq0[0][plan.nb];
     __shared__ DecShared sh;
     __shared__ __align__(16) uint8_t s_lut2[DEC_LUT2_SIZE];
     __shared__ uint32_t s_ends[DEC_THREADS];    // overshoot of sub-sequence i into sub-sequence i+1
@@ -328,13 +410,14 @@ k_dec_sync(const uint8_t *__restrict__ payload, DecPlan plan, DecTablesGlobal g,
     uint32_t carry = 0;  // where the previous sequence of this CTA's chunk left its last sub-sequence
     if (seq_first >= seq_last) return;
     SeqCursor cursor;
-    cursor.init(plan, seq_first);
+    cursor.init(plan.cls_seq0[0], plan.nb, seq_first);
     SeqFetch cur = dec_fetch_seq(payload, plan, cursor, seq_first);
-    for (uint64_t seq = seq_first; seq < seq_last; seq++) {
+    for (uint64_t cseq = seq_first; cseq < seq_last; cseq++) {
         SeqFetch nxt = cur;
-        if (seq + 1 < seq_last) nxt = dec_fetch_seq(payload, plan, cursor, seq + 1);  // in flight during this sequence
+        if (cseq + 1 < seq_last) nxt = dec_fetch_seq(payload, plan, cursor, cseq + 1);  // in flight during this sequence
         const uint32_t b = cur.b;
         const uint64_t sib = cur.sib, z = cur.z;
+        const uint64_t seq = plan.seq0[b] + sib;  // its number among ALL sequences: where its records go
         __syncthreads();  // previous sequence fully consumed
         if (b != cur_block) {
             cur_block = b;
@@ -360,7 +443,7 @@ k_dec_sync(const uint8_t *__restrict__ payload, DecPlan plan, DecTablesGlobal g,
         }
         // The first sub-sequence starts where the previous sequence ended.  Inside a chunk that is known;
         // the first sequence of a chunk assumes 0 and k_dec_stitch repairs it (a block's first sequence IS 0).
-        if (sib == 0 || seq == seq_first) carry = 0;
+        if (sib == 0 || cseq == seq_first) carry = 0;
         dec_store_row(sh.pairs, cur.row, z, sib);
         cur = nxt;
         __syncthreads();
@@ -515,6 +598,187 @@ k_dec_sync(const uint8_t *__restrict__ payload, DecPlan plan, DecTablesGlobal g,
             seq_count[seq] = tot;
         }
         // a speculative start may hit garbage; errors are judged in k_dec_write
+    }
+}
+
+// ---- phase 1 for lean blocks -------------------------------------------------------------------------------------
+// Codes of nearly one length never re-synchronise: every thread walks its sub-sequence from EVERY start that can occur
+// (an overshoot is shorter than the longest code) and the chain through the resulting maps is followed warp-parallel.
+// The walks are bound by shared-memory table gathers (ncu on C4: LSU wavefronts 95 % of peak, 2.8 wavefronts per load
+// from bank conflicts on random indices), so this kernel takes fewer of them: a 16-bit window table holding all whole
+// codes of the window (core.h: dec_lut16_entry, dec_lean_walk) -- 64 KiB per block, which is why lean blocks have a
+// kernel (and a shared-memory budget) of their own.
+constexpr int LEAN_SEQS = 2;                            // sequences a CTA walks at a time: they share the 72 KiB of tables, and
+constexpr int LEAN_THREADS = LEAN_SEQS * DEC_THREADS;   // 16 warps per CTA x 2 CTAs per SM hide the table latency (8 warps: 22 ms on C4)
+constexpr int LEAN_WARPS = LEAN_THREADS / 32;
+constexpr int LEAN_MAP_STRIDE = LEAN_THREADS + 2;
+#ifndef SHAFA_LEAN_NS
+#define SHAFA_LEAN_NS 3
+#endif
+constexpr int LEAN_NS = SHAFA_LEAN_NS;                  // chains a thread walks at a time (independent: their table loads overlap)
+struct DecLeanShared {
+    alignas(16) uint8_t lut16[DEC_LUT16_SIZE];
+    alignas(16) uint16_t lut1[DEC_LUT_SIZE];         // single-code steps for the last bits of a sub-sequence
+    // Layouts chosen by who touches them together (the kernel is bound by shared-memory wavefronts): a warp stores the
+    // maps of 32 consecutive sub-sequences for ONE start, the chain lanes read ONE sub-sequence for all starts
+    uint16_t map[DEC_MAP_MAX * LEAN_MAP_STRIDE];     // [start][sub-sequence] -> (overshoot << 10) | count; one bank further per start
+    uint8_t path[LEAN_WARPS * 32 * DEC_MAP_MAX];     // [warp][i][entry offset]: start of the warp's i-th sub-sequence
+    uint8_t path_out[LEAN_WARPS * DEC_MAP_MAX];      // [warp][entry offset]: offset handed to the next warp
+    uint32_t wentry[LEAN_WARPS];
+    uint32_t wsum[LEAN_WARPS];
+    uint32_t wmax[LEAN_WARPS];
+    uint32_t last_over;
+};
+struct DecViewLean {
+    uint32_t lut1_s, lut16_s;
+    __device__ __forceinline__ uint32_t l1len(uint32_t i) const
+    {
+        uint32_t v;
+        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(lut1_s + i * 2u));
+        return v;
+    }
+    __device__ __forceinline__ uint32_t l16(uint32_t i) const
+    {
+        uint32_t v;
+        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(lut16_s + i));
+        return v;
+    }
+};
+
+__global__ void __launch_bounds__(LEAN_THREADS, 2)
+k_dec_sync_lean(const uint8_t *__restrict__ payload, DecPlan plan, DecTablesGlobal g, uint16_t *__restrict__ sub_info,
+                uint32_t *__restrict__ seq_end, uint32_t *__restrict__ seq_count)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    DecLeanShared &sh = *reinterpret_cast<DecLeanShared *>(smem_raw);
+    const unsigned tid = threadIdx.x, lane = lane_id(), warp = warp_id();
+    const unsigned half = tid / DEC_THREADS, sid = tid % DEC_THREADS;  // which of the CTA's sequences, which sub-sequence of it
+    const uint64_t nseq = plan.cls_seq0[1][plan.nb];
+    uint64_t seq_first, seq_last;
+    dec_chunk(nseq, &seq_first, &seq_last);
+    if (seq_first >= seq_last) return;
+    uint32_t cur_block = 0xffffffffu, carry = 0, maxlen = 0;
+    SeqCursor cursor;
+    cursor.init(plan.cls_seq0[1], plan.nb, seq_first);
+    DecViewLean t;
+    t.lut1_s = smem_u32(sh.lut1);
+    t.lut16_s = smem_u32(sh.lut16);
+    asm volatile("" : "+r"(t.lut1_s), "+r"(t.lut16_s));  // opaque: not rebuilt from the shared window inside the loops
+    uint64_t cseq = seq_first;
+    while (cseq < seq_last) {
+        cursor.advance_to(cseq);
+        const uint32_t b = cursor.b;
+        // this round: up to LEAN_SEQS consecutive sequences of the same block (and of this CTA's chunk)
+        uint64_t room = (cursor.next < seq_last ? cursor.next : seq_last) - cseq;
+        const uint32_t ns = room < (uint64_t)LEAN_SEQS ? (uint32_t)room : (uint32_t)LEAN_SEQS;
+        const uint64_t sib0 = cseq - cursor.first, z = plan.z[b];
+        const uint64_t sib = sib0 + half;           // my sequence inside the block
+        const uint64_t seq = plan.seq0[b] + sib;    // its number among ALL sequences: where its records go
+        const bool mine = half < ns;
+        RowRegs row;
+        row.v = make_uint4(0, 0, 0, 0);
+        row.u = make_uint2(0, 0);
+        {
+            // (dec_fetch_row indexes by threadIdx.x: here the sub-sequence number is sid)
+            const uint64_t o = sib * DEC_SEQ_BYTES + (uint64_t)sid * 16;
+            const uint64_t slot = (z + 15) & ~15ull;
+            const uint8_t *base = payload + plan.pay_off[b];
+            if (mine && o < slot) row.v = __ldg(reinterpret_cast<const uint4 *>(base + o));
+            if (mine && o + 16 < slot) row.u = __ldg(reinterpret_cast<const uint2 *>(base + o + 16));
+        }
+        __syncthreads();  // previous round fully consumed
+        if (b != cur_block) {
+            cur_block = b;
+            const uint4 *src16 = reinterpret_cast<const uint4 *>(g.lut16 + (uint64_t)plan.lean_slot[b] * DEC_LUT16_SIZE);
+            uint4 *dst16 = reinterpret_cast<uint4 *>(sh.lut16);
+#pragma unroll 4
+            for (int i = tid; i < DEC_LUT16_SIZE / 16; i += LEAN_THREADS) dst16[i] = src16[i];
+            const uint4 *src1 = reinterpret_cast<const uint4 *>(g.lut + (uint64_t)b * DEC_LUT_SIZE);
+            uint4 *dst1 = reinterpret_cast<uint4 *>(sh.lut1);
+            for (int i = tid; i < DEC_LUT_SIZE * 2 / 16; i += LEAN_THREADS) dst1[i] = src1[i];
+            const uint32_t wm = __reduce_max_sync(FULL, tid < 256 ? (uint32_t)g.slen[(uint64_t)b * 256 + tid] : 0u);
+            if (lane == 0) sh.wmax[warp] = wm;
+            __syncthreads();
+            maxlen = 0;
+#pragma unroll
+            for (int k = 0; k < LEAN_WARPS; k++) maxlen = sh.wmax[k] > maxlen ? sh.wmax[k] : maxlen;
+        }
+        if (sib0 == 0 || cseq == seq_first) carry = 0;
+        uint32_t w[DEC_ROW_WORDS];
+        {
+            // dec_row_words for sub-sequence sid of sequence sib: bytes at or past z read as zero, words big-endian
+            const uint64_t o = sib * DEC_SEQ_BYTES + (uint64_t)sid * 16;
+            w[0] = row.v.x, w[1] = row.v.y, w[2] = row.v.z, w[3] = row.v.w, w[4] = row.u.x, w[5] = row.u.y;
+            if (o + 4 * DEC_ROW_WORDS > z) {
+#pragma unroll
+                for (int k = 0; k < DEC_ROW_WORDS; k++) {
+                    const uint64_t bo = o + 4 * k;
+                    if (bo >= z)
+                        w[k] = 0;
+                    else if (bo + 4 > z)
+                        w[k] &= (0xffffffffu >> (8 * (uint32_t)(bo + 4 - z)));
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < DEC_ROW_WORDS; k++) w[k] = bswap32(w[k]);
+        }
+        __syncthreads();  // tables in place
+        uint32_t stop = 0;
+        if (mine) {
+            const uint64_t bits_left = (z - sib * DEC_SEQ_BYTES) * 8;
+            const uint32_t limit = bits_left < (uint64_t)DEC_SEQ_BYTES * 8 ? (uint32_t)bits_left : DEC_SEQ_BYTES * 8;
+            const uint32_t sub_lo = sid * DEC_SUB_BITS;
+            stop = limit > sub_lo ? (limit - sub_lo < (uint32_t)DEC_SUB_BITS ? limit - sub_lo : (uint32_t)DEC_SUB_BITS) : 0u;
+        }
+        for (uint32_t st = 0; st < maxlen; st += LEAN_NS) {  // maxlen <= 12: a lean block has no longer code
+            uint32_t cnt[LEAN_NS], end[LEAN_NS];
+            dec_lean_walk<LEAN_NS>(t, w, st, stop, cnt, end);
+#pragma unroll
+            for (int k = 0; k < LEAN_NS; k++) {  // (starts at or past maxlen are computed too and never looked at: the map has 16 slots)
+                const uint32_t ov = end[k] > (uint32_t)DEC_SUB_BITS ? end[k] - DEC_SUB_BITS : 0u;
+                sh.map[(st + k) * LEAN_MAP_STRIDE + tid] = (uint16_t)((ov << 10) | cnt[k]);
+            }
+        }
+        __syncthreads();
+        // the chain, two levels: lane s of every warp follows its warp's 32 sub-sequences from entry offset s (all
+        // offsets and warps in parallel), one thread links the warps (the round's sequences are consecutive: the chain
+        // runs straight through them), and every thread then picks the path that belongs to its warp's real entry offset
+        if (lane < maxlen) {
+            uint32_t st = lane;
+            for (int i = 0; i < 32; i++) {
+                sh.path[(warp * 32 + i) * DEC_MAP_MAX + lane] = (uint8_t)st;
+                st = sh.map[st * LEAN_MAP_STRIDE + warp * 32 + i] >> 10;  // < maxlen: shorter than the longest code
+            }
+            sh.path_out[warp * DEC_MAP_MAX + lane] = (uint8_t)st;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            uint32_t st = carry < maxlen ? carry : 0u;  // carry >= maxlen cannot happen
+            for (int k = 0; k < LEAN_WARPS; k++) {
+                sh.wentry[k] = st;
+                st = sh.path_out[k * DEC_MAP_MAX + st];
+            }
+        }
+        __syncthreads();
+        const uint32_t st = sh.path[(warp * 32 + lane) * DEC_MAP_MAX + sh.wentry[warp]];
+        const uint32_t e = sh.map[st * LEAN_MAP_STRIDE + tid];
+        const uint32_t my_count = e & 1023u;
+        if (mine) sub_info[seq * DEC_THREADS + sid] = sub_pack(st, my_count);
+        if (mine && sid == DEC_THREADS - 1) {
+            if (half == ns - 1) sh.last_over = e >> 10;
+            seq_end[seq] = e >> 10;
+        }
+        const uint32_t wsum = __reduce_add_sync(FULL, my_count);
+        if (lane == 0) sh.wsum[warp] = wsum;
+        __syncthreads();
+        carry = sh.last_over;
+        if (mine && sid == 0) {
+            uint32_t tot = 0;
+#pragma unroll
+            for (int k = 0; k < DEC_THREADS / 32; k++) tot += sh.wsum[half * (DEC_THREADS / 32) + k];
+            seq_count[seq] = tot;
+        }
+        cseq += ns;
     }
 }
 
@@ -681,7 +945,7 @@ k_dec_write(const uint8_t *__restrict__ payload, DecPlan plan, DecTablesGlobal g
     uint32_t bad = 0;
     if (seq_first >= seq_last) return;
     SeqCursor cursor;
-    cursor.init(plan, seq_first);
+    cursor.init(plan.seq0, plan.nb, seq_first);
     SeqFetch cur = dec_fetch_seq(payload, plan, cursor, seq_first);
     uint16_t rec = sub_info[seq_first * DEC_THREADS + tid];
     uint64_t sfirst = seq_excl[seq_first];  // index of the sequence's first symbol inside the block
@@ -812,14 +1076,38 @@ static DecPlan plan_at(const uint64_t *dp, uint64_t nb)
     plan.out_off = dp + 3 * nb;
     plan.seq0 = dp + 4 * nb;
     plan.nb = (uint32_t)nb;
+    plan.cls_seq0[0] = plan.cls_seq0[1] = nullptr;
+    plan.lean_slot = nullptr;
     return plan;
 }
 
 // the exact path: sync / stitch / scan / write over the blocks of `plan`
-static int launch_sf_decode_exact(shafa_cuda_ctx *ctx, const uint8_t *d_payload, const DecPlan &plan, const DecTablesGlobal &g,
-                                  uint64_t nb, uint64_t nseq, uint8_t *d_sym, uint32_t *d_err, bool careful_stitch)
+// n_big: how many of the plan's blocks have enough payload to be lean (dec_block_lean; whether their code is of that
+// kind is only known on the device): the number of 64 KiB table slots to provide
+static int launch_sf_decode_exact(shafa_cuda_ctx *ctx, const uint8_t *d_payload, const DecPlan &plan_in, const DecTablesGlobal &g_in,
+                                  uint64_t nb, uint64_t nseq, uint64_t n_big, uint8_t *d_sym, uint32_t *d_err, bool careful_stitch)
 {
     if (nseq == 0) return SHAFA_SUCCESS;
+    DecPlan plan = plan_in;
+    DecTablesGlobal g = g_in;
+    {
+        // the two sequence classes (lean blocks / everything else) and the lean blocks' tables, all decided on the device
+        uint64_t *cls = (uint64_t *)scratch_get(ctx, SCR_DEC_CLS, 2 * (nb + 1) * sizeof(uint64_t) + nb * sizeof(uint32_t));
+        if (!cls) return SHAFA_LACK_OF_MEMORY;
+        plan.cls_seq0[0] = cls;
+        plan.cls_seq0[1] = cls + nb + 1;
+        uint32_t *slot = (uint32_t *)(cls + 2 * (nb + 1));
+        plan.lean_slot = slot;
+        SHAFA_LAUNCH(ctx, "dec_classes", k_dec_classes, dim3(1), dim3(256), 0, plan.seq0, plan.z, (const uint8_t *)g.flags, (uint32_t)nb, cls,
+                     cls + nb + 1, slot);
+        g.lut16 = nullptr;
+        if (n_big) {
+            g.lut16 = (uint8_t *)scratch_get(ctx, SCR_DEC_LUT16, n_big * (size_t)DEC_LUT16_SIZE);
+            if (!g.lut16) return SHAFA_LACK_OF_MEMORY;
+            SHAFA_LAUNCH(ctx, "dec_lut16", k_dec_lut16, dim3((unsigned)nb), dim3(256), 0, plan, g);
+        }
+        SHAFA_CHECK_LAUNCH(ctx);
+    }
     uint16_t *sub_info = (uint16_t *)scratch_get(ctx, SCR_DEC_SUB, nseq * DEC_THREADS * sizeof(uint16_t));
     // seq arrays: seq_end u32[nseq], seq_count u32[nseq], seq_excl u64[nseq]
     uint8_t *seqbuf = (uint8_t *)scratch_get(ctx, SCR_DEC_SEQ, nseq * 16 + 64);
@@ -843,7 +1131,20 @@ static int launch_sf_decode_exact(shafa_cuda_ctx *ctx, const uint8_t *d_payload,
     if (grid_sync > nseq) grid_sync = nseq;
     if (grid_write > nseq) grid_write = nseq;
     SHAFA_LAUNCH(ctx, "dec_sync", k_dec_sync, dim3((unsigned)grid_sync), dim3(DEC_THREADS), 0, d_payload, plan, g, sub_info,
-                 seq_end, seq_count, nseq);
+                 seq_end, seq_count);
+    if (n_big) {
+        int &occ_lean = ctx->occ[OCC_DEC_LEAN];
+        const size_t smem_l = sizeof(DecLeanShared);
+        if (!occ_lean) {
+            SHAFA_CUDA_TRY(ctx, cudaFuncSetAttribute(k_dec_sync_lean, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_l));
+            SHAFA_CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_lean, k_dec_sync_lean, LEAN_THREADS, smem_l));
+            if (occ_lean < 1) occ_lean = 1;
+        }
+        uint64_t grid_lean = (uint64_t)ctx->sm_count * occ_lean * 4;
+        if (grid_lean > nseq) grid_lean = nseq;
+        SHAFA_LAUNCH(ctx, "dec_sync_lean", k_dec_sync_lean, dim3((unsigned)grid_lean), dim3(LEAN_THREADS), smem_l, d_payload, plan, g,
+                     sub_info, seq_end, seq_count);
+    }
     SHAFA_CHECK_LAUNCH(ctx);
     // Stitch across chunk boundaries until a pass moves no sequence end.  The first pass almost always settles it and the
     // second then moves nothing, so the normal path launches two passes back to back with NO host round trip in
@@ -946,7 +1247,9 @@ int launch_sf_decode(shafa_cuda_ctx *ctx, const uint8_t *d_payload, const uint64
         if ((rc = launch_sf_decode_fused(ctx, d_payload, plan, g, rec, nseq_fused, d_sym, d_err))) return rc;
     }
     if (nseq_exact) {
-        rc = launch_sf_decode_exact(ctx, d_payload, plan_at(dp + plan_words, nb), g, nb, nseq_exact, d_sym, d_err, careful_stitch);
+        uint64_t n_big = 0;  // blocks of the exact plan that are large enough to be lean (fill_plan zeroes z of the other path's blocks)
+        for (uint64_t b = 0; b < nb; b++) n_big += hp[plan_words + nb + b] >= DEC_LEAN_MIN_Z ? 1 : 0;
+        rc = launch_sf_decode_exact(ctx, d_payload, plan_at(dp + plan_words, nb), g, nb, nseq_exact, n_big, d_sym, d_err, careful_stitch);
     }
     return rc;
 }

@@ -18,15 +18,25 @@ struct DecTablesGlobal {
     uint8_t *slen;    // [nb][256]
     uint8_t *ssym;    // [nb][256]
     uint8_t *flags;   // [nb]        DecBlockFlags
+    uint8_t *lut16;   // [lean slots][65536]  all whole codes of a 16-bit window (core.h: dec_lut16_entry), lean blocks only
 };
 
 enum DecBlockFlags : uint8_t {
     DECB_COMPLETE = 1,  // the table is a complete prefix-free code: every bit pattern decodes
     DECB_NOSYNC = 2,    // nearly one code length: such codes do not self-synchronise
-    DECB_WIDE = 4       // a code longer than 32 bits (the fused decoder's end offsets are bytes)
+    DECB_WIDE = 4,      // a code longer than 32 bits (the fused decoder's end offsets are bytes)
+    DECB_SHORT = 8      // no code longer than the lut1 window (12 bits)
 };
+// "lean" block: complete code of nearly one length without long codes, and enough payload to pay for a 64 KiB table.
+// Its sequences are synchronised by k_dec_sync_lean (every start walked, several codes per lookup), everybody else's by
+// k_dec_sync.
+constexpr uint64_t DEC_LEAN_MIN_Z = 4ull * 65536;
+__host__ __device__ inline bool dec_block_lean(uint8_t f, uint64_t z)
+{
+    return (f & (DECB_COMPLETE | DECB_NOSYNC | DECB_SHORT)) == (DECB_COMPLETE | DECB_NOSYNC | DECB_SHORT) && z >= DEC_LEAN_MIN_Z;
+}
 // a block goes through the fused kernel iff its table is complete, synchronising and not wide
-__host__ __device__ inline bool dec_block_fused_ok(uint8_t f) { return f == DECB_COMPLETE; }
+__host__ __device__ inline bool dec_block_fused_ok(uint8_t f) { return (f & (DECB_COMPLETE | DECB_NOSYNC | DECB_WIDE)) == DECB_COMPLETE; }
 
 struct DecPlan {
     const uint64_t *pay_off;  // [nb]
@@ -35,6 +45,9 @@ struct DecPlan {
     const uint64_t *out_off;  // [nb] output offset of each block
     const uint64_t *seq0;     // [nb+1] first sequence of each block
     uint32_t nb;
+    // the sequences split into two classes, each numbered densely in block order (k_dec_classes):
+    const uint64_t *cls_seq0[2];  // [nb+1] first class-c sequence number of each block (class 0: k_dec_sync, 1: k_dec_sync_lean)
+    const uint32_t *lean_slot;    // [nb] which lut16 table a lean block uses
 };
 
 // what a ticket of the fused kernel needs before anything else: {payload offset lo, hi, block, bytes to copy}

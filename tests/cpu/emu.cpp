@@ -492,6 +492,8 @@ struct EmuTables {
     std::vector<uint16_t> lut;
     std::vector<uint8_t> lut2;
     std::vector<uint32_t> lut3;
+    std::vector<uint8_t> lut16;  // only for "lean" codes (complete, <= 12 bits): all whole codes of a 16-bit window
+    bool lean = false;
     uint64_t sleft[256];
     uint8_t slen[256], ssym[256];
     DecView view(const uint64_t *pairs) const
@@ -501,6 +503,7 @@ struct EmuTables {
         t.lut1 = lut.data();
         t.lut2 = lut2.data();
         t.lut3 = lut3.data();
+        t.lut16 = lut16.data();
         t.sleft = sleft;
         t.slen = slen;
         t.ssym = ssym;
@@ -552,8 +555,16 @@ static void emu_dec_tables(const uint8_t *len, const uint64_t *code, EmuTables &
         T.lut2[2 * e + 1] = dec_lut2_entry(T.lut.data(), 2u * (uint32_t)e + 1u);
         T.lut3[e] = dec_lut3_entry(T.lut.data(), (uint32_t)e);
     }
+    // lean: every 12-bit window holds a whole code (what k_dec_sync checks before it trusts lut1 blindly)
+    T.lean = true;
+    for (int e = 0; e < DEC_LUT_SIZE; e++)
+        if ((uint32_t)(T.lut[e] & 0xFF) - 1u >= (uint32_t)DEC_LUT_BITS) T.lean = false;
+    T.lut16.assign(DEC_LUT16_SIZE, 0);
+    if (T.lean)
+        for (int v = 0; v < DEC_LUT16_SIZE; v++) T.lut16[v] = dec_lut16_entry(T.lut.data(), (uint32_t)v);
 }
 
+static long g_lean_walks = 0;
 static Bytes emu_sf_decode(const Bytes &payload, uint64_t n, const uint8_t *len, const uint64_t *code, bool &bad, int *stitch_passes)
 {
     EmuTables T;
@@ -602,6 +613,18 @@ static Bytes emu_sf_decode(const Bytes &payload, uint64_t n, const uint8_t *len,
             CHECK(rw.end == r.end && rw.count == r.count && rw.bad == r.bad, "register-window count walk disagrees with the row walk");
             en[tid] = r.end > (uint32_t)DEC_SUB_BITS ? r.end - DEC_SUB_BITS : 0;
             cn[tid] = r.count;
+            if (T.lean) {  // the multi-code walk of k_dec_sync_lean, from this start and from every other one it would try
+                for (uint32_t s2 = 0; s2 < 15; s2 += 3) {
+                    const uint32_t st2 = s2 == 12 ? st[tid] : s2;
+                    uint32_t c3[3], e3[3];
+                    dec_lean_walk<3>(t, words_of(tid), st2, stop, c3, e3);
+                    for (uint32_t k = 0; k < 3; k++) {
+                        const DecSub r2 = dec_count_subsequence(t, tid * DEC_ROW, st2 + k, stop);
+                        CHECK(c3[k] == r2.count && e3[k] == r2.end, "lean multi-code walk differs from the plain walk");
+                        g_lean_walks++;
+                    }
+                }
+            }
         };
         for (int tid = 0; tid < DEC_THREADS; tid++) run(tid);
         for (int iter = 0;; iter++) {
@@ -941,6 +964,7 @@ static void test_sf_codec(std::mt19937 &rng)
         CHECK(!bad && decf == raw, "sf_decode_fused big rep %d n %zu maxlen %d", rep, n, maxlen);
         if (getenv("EMU_VERBOSE")) printf("  big rep %d maxlen %d: cumulative met/left/rebuilt %d/%d/%d\n", rep, maxlen, g_fused_kind[0], g_fused_kind[1], g_fused_kind[2]);
     }
+    printf("lean multi-code walks checked: %ld\n", g_lean_walks);
     printf("fused decoder: splices met/left/rebuilt %d/%d/%d, speculation failures %d\n", g_fused_kind[0], g_fused_kind[1], g_fused_kind[2],
            g_fused_specfail);
 }
