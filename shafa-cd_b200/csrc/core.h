@@ -326,7 +326,13 @@ SHAFA_HD FsmWalk fsm_walk64(uint64_t Z, int n, uint32_t entry)
 SHAFA_HD uint32_t fsm_map64(uint64_t Z, int n)
 {
     if (Z == 0 && n >= 2) return 0u;  // no escape at all: every entry state is back in state 0 and stays there
-    return fsm_walk64(Z, n, 0).exit | (fsm_walk64(Z, n, 1).exit << 2) | (fsm_walk64(Z, n, 2).exit << 4);
+    // The walks from entry states 1 and 2 start in state 0 at positions 2 and 1.  If the walk from entry state 0 is in
+    // state 0 there as well (no escape at positions 0/1 resp. 0 swallowed them) the walks coincide from then on: one
+    // walk instead of three for all but the threads whose first two bytes hold a zero.
+    const FsmWalk w0 = fsm_walk64(Z, n, 0);
+    const uint32_t e1 = (n >= 3 && (w0.esc & 3ull) == 0) ? w0.exit : fsm_walk64(Z, n, 1).exit;
+    const uint32_t e2 = (n >= 3 && (w0.esc & 1ull) == 0) ? w0.exit : fsm_walk64(Z, n, 2).exit;
+    return w0.exit | (e1 << 2) | (e2 << 4);
 }
 // positions that emit: lit = literal bytes, run = count bytes of triples (the run's byte is the one before)
 struct RleDecMasks {

@@ -34,6 +34,7 @@ constexpr int RLE_WARPS = RLE_THREADS / 32;
 constexpr int RLE_PER_THREAD = RLE_ITEMS * RLE_VECS;     // 64
 constexpr int RLE_STAGE = 2 * RLE_TILE + 48;             // worst case 2n+3 (f.c:244) + the read-ahead of copy_out_unaligned
 constexpr int RLE_HIST_COPIES = 8;
+constexpr int RLE_SPARSE_MAX = 3;  // literals per 16-byte vector up to which every lane of a warp takes the sparse literal loop
 
 struct RleEncShared {
     alignas(16) uint8_t stage[RLE_STAGE];
@@ -267,8 +268,19 @@ k_rle_encode(const uint8_t *__restrict__ in, uint64_t n, uint64_t block_size, ui
 #pragma unroll
                     for (int j = 0; j < 16; j++) sts_u8(o_s + j, byte_of(v[c], j));
                     o_s += 16;
-                } else if (__any_sync(__activemask(), (l16 | t16) != 0)) {
-                    rle_lit_steps<0>(o_s, v[c], l16, t16);
+                } else if (__any_sync(__activemask(), __popc(l16) > RLE_SPARSE_MAX)) {
+                    rle_lit_steps<0>(o_s, v[c], l16, t16);  // dense: sixteen predicated steps, whatever the masks are
+                } else {
+                    // sparse (run-heavy data: a vector emits a triple or two and hardly any literal): one iteration per
+                    // literal instead of sixteen predicated steps per vector -- nothing at all for a vector without literals
+                    uint32_t lb = l16;
+                    while (lb) {
+                        const uint32_t j = (uint32_t)ctz32(lb);
+                        lb &= lb - 1u;
+                        const uint32_t below = (1u << j) - 1u;
+                        sts_u8(o_s + (uint32_t)__popc(l16 & below) + 3u * (uint32_t)__popc(t16 & below), in[pos + 16 * c + j]);  // L1 hit
+                    }
+                    o_s += (uint32_t)__popc(l16) + 3u * (uint32_t)__popc(t16);
                 }
             }
             // triples: sparse loop over their positions (the count needs a look-ahead in the head bitmask)
