@@ -275,7 +275,7 @@ class ClockSampler:
 
 ALGO_BYTES_DOC = {
     "rle_encode": "N + R", "rle_encode_sizes": "n0 (block-0 probe)", "histogram": "S", "sf_encode": "S + Z",
-    "dec_fused": "Z + S", "dec_sync": "Z", "dec_write": "Z + S", "rle_decode": "R + N",
+    "dec_fused": "Z + S", "dec_sync": "Z", "dec_sync_lean": "Z", "dec_sync (both kernels)": "Z", "dec_write": "Z + S", "rle_decode": "R + N",
 }
 
 
@@ -598,6 +598,21 @@ def run_ours(args):
         R = info["R"]
         algo = {"rle_encode": n + R, "rle_encode_sizes": min(n, bs), "histogram": S, "sf_encode": S + Z, "dec_fused": Z + S,
                 "dec_sync": Z, "dec_write": Z + S, "rle_decode": R + n}
+        # The synchronisation pass is two kernels over disjoint sets of blocks (k_dec_sync, and k_dec_sync_lean for complete
+        # codes of nearly one length): a kernel that ran alone is credited with Z, a mixed file only with their sum.
+        sync_ms = {k: kstats[k]["ms"] for k in ("dec_sync", "dec_sync_lean") if k in kstats and kstats[k]["launches"]}
+        if len(sync_ms) == 2:
+            small, big = sorted(sync_ms, key=sync_ms.get)
+            if sync_ms[small] < 0.1 * sync_ms[big]:    # the other one only looked at its (empty) class
+                algo["dec_sync_lean" if big == "dec_sync_lean" else "dec_sync"] = Z
+                algo.pop(small, None)
+            else:
+                algo.pop("dec_sync", None)
+                algo["dec_sync (both kernels)"] = Z
+                kstats = dict(kstats)
+                kstats["dec_sync (both kernels)"] = {"ms": sum(sync_ms.values()), "launches": kstats["dec_sync"]["launches"]}
+        elif "dec_sync_lean" in sync_ms:
+            algo["dec_sync_lean"] = Z
         kernels = {}
         for name, st in kstats.items():
             per_step_ms = st["ms"] / args.steps

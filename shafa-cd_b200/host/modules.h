@@ -28,7 +28,11 @@ typedef enum _error { /* utils/errors.h:5-16 */
 
 const char *error_msg(int num); /* utils/errors.c:26-36 */
 
-/* f.h:16.  On success in R mode *path becomes "<path>.rle" (f.c:396-399). */
+/* f.h:16.  On success in R mode *path becomes "<path>.rle" (f.c:396-399).
+ * block_size: 0 = the reference's default (524288, utils/file.c:62), values below 512 are raised to 512
+ * (utils/file.c:63) and values above 64 MiB are refused, like the reference.  ONE DEVIATION: the block
+ * size must be a multiple of 16 (every size the CLI can select -- 64 KiB, K, m, M -- is); any other value
+ * returns _FILE_STREAM_FAILED with a message that says so, instead of being accepted as fsize() would. */
 _modules_error freq_rle_compress(char **path, bool force_rle, bool force_freq, unsigned long block_size);
 /* t.h:11.  Reads "<path>.freq", writes "<path>.cod". */
 _modules_error get_shafa_codes(const char *path);

@@ -10,6 +10,6 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
     python bench.py --steps 2 --warmup 3 --no-cpu > "$OUT/bench_under_ncu.log" 2>&1
 fi
 # hot kernels, full set, one step after warm-up (6 matching launches per step; three warm-up steps come first)
-ncu --set full --clock-control none --import-source on -k regex:'k_(rle_encode|sf_encode|dec_sync|dec_write|rle_decode)' \
+ncu --set full --clock-control none --import-source on -k regex:'^k_(rle_encode|sf_encode|dec_sync|dec_write|rle_decode)$' \
     --launch-skip 18 --launch-count 6 -o "$OUT/prof" -f python bench.py --steps 1 --warmup 3 --no-cpu > "$OUT/bench_under_ncu_full.log" 2>&1
 ls -la "$OUT"

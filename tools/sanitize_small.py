@@ -4,7 +4,7 @@
     compute-sanitizer --tool racecheck python tools/sanitize_small.py
 
 Covers what the kernel tests cover at sizes a sanitizer finishes in minutes: TMA-staged histogram, RLE encode/decode,
-SF build/encode, the exact decoder incl. its all-starts path (uniform bytes: codes of 7-9 bits), the bulk-store copy-out
+SF build/encode, the exact decoder incl. its all-starts path and the lean kernel (uniform bytes: codes of 7-9 bits), the bulk-store copy-out
 of k_dec_write, and the fused single-pass decoder (SHAFA_DECODE_FUSED=1, second half).
 """
 import os
@@ -20,7 +20,10 @@ from __graft_entry__ import load_package  # noqa: E402
 
 def main():
     pkg = load_package()
-    cases = [("textlike", 300_000, 65536), ("uniform", 150_000, 65536), ("runheavy", 400_000, 65536), ("zipf", 200_000, 65536)]
+    # the 700 kB uniform case has one block above DEC_LEAN_MIN_Z (k_dec_lut16 + k_dec_sync_lean) and one below it (the all-starts
+    # path inside k_dec_sync)
+    cases = [("textlike", 300_000, 65536), ("uniform", 150_000, 65536), ("uniform", 700_000, 655360), ("runheavy", 400_000, 65536),
+             ("zipf", 200_000, 65536)]
     with pkg.Shafa(device=0) as sh:
         for fused in ("0", "1"):
             os.environ["SHAFA_DECODE_FUSED"] = fused
