@@ -1,10 +1,6 @@
-timeout 900 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_configs.py -x -q -m gpu > gpurun_out/t21.log 2>&1; tail -3 gpurun_out/t21.log
-bash tools/ab_bench.sh
-for w in C3; do timeout 600 python bench.py --workload $w --steps 3 --warmup 3 --no-cpu --no-files > gpurun_out/b21_$w.json 2> gpurun_out/b21_$w.err; tail -3 gpurun_out/b21_$w.err; python - <<P
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 10 --warmup 3 --no-cpu --no-files > gpurun_out/r02c_bench_2gpu.json 2> gpurun_out/r02c_bench_2gpu.err; tail -3 gpurun_out/r02c_bench_2gpu.err; python - <<P
 import json
-try:
-    j=json.load(open("gpurun_out/b21_$w.json"))
-    print("$w", j["value"], j.get("encode_gbs"), j.get("decode_gbs"), {k:(v.get("ms_per_step")) for k,v in j["kernels"].items() if v.get("ms_per_step",0)>0.05})
-except Exception as e: print("$w failed", e)
+j=json.loads(open("gpurun_out/r02c_bench_2gpu.json").read().strip().splitlines()[-1])
+print(j["n_gpus"], j["value"], "e2e", j["e2e"]["value"], "one_file", json.dumps(j.get("one_file"))[:600])
 P
-done
+timeout 600 python tools/multi_gpu_e2e.py C3 > gpurun_out/r02c_one_file_2gpu_C3.json 2> gpurun_out/r02c_one_file_2gpu_C3.err; tail -c 700 gpurun_out/r02c_one_file_2gpu_C3.json
