@@ -246,6 +246,39 @@ def test_sf_decode_reference_payloads(shafa, orc, pkg):
             assert_same(out, orig, f"{case}: -m d")
 
 
+@pytest.mark.parametrize("alphabet,n", [(2, 6_000_000), (4, 3_000_000), (6, 2_500_000), (24, 1_600_000), (200, 900_000), (256, 700_000)])
+def test_sf_decode_codes_of_nearly_one_length(shafa, orc, pkg, alphabet, n):
+    """Uniformly drawn symbols give complete codes of nearly one length (1-bit codes for two symbols, 7..9 bits for 256):
+    k_dec_classes / k_dec_lut16 / k_dec_sync_lean for the block large enough to be "lean" (>= 256 KiB of payload), the
+    all-starts path inside k_dec_sync for the small one behind it, both in one call; against the oracle's decode."""
+    rng = np.random.default_rng(alphabet)
+    syms = rng.permutation(256)[:alphabet].astype(np.uint8)
+    big = syms[rng.integers(0, alphabet, size=n)]
+    small = syms[rng.integers(0, alphabet, size=40_000)]
+    lens, codes, payloads = [], [], []
+    for blk in (big, small):
+        h = orc.histogram(blk)
+        ln, cd, _ = orc.sf_codes_packed(h)
+        lens.append(ln); codes.append(cd)
+        payloads.append(orc.sf_encode_block(blk, orc.sf_codes(h)))
+    assert payloads[0].size >= 4 * 65536 > payloads[1].size
+    used = lens[0][lens[0] > 0]
+    assert 2 * int(used.min()) > int(used.max()) and int(used.max()) <= 12, "not the code shape this test is about"
+    z = np.array([p.size for p in payloads], dtype=np.uint64)
+    slot0 = (int(z[0]) + 15) & ~15
+    offs = np.array([0, slot0], dtype=np.uint64)
+    buf = np.zeros(slot0 + ((int(z[1]) + 15) & ~15) + 32, dtype=np.uint8)
+    buf[: int(z[0])] = payloads[0]
+    buf[slot0: slot0 + int(z[1])] = payloads[1]
+    sizes = np.array([big.size, small.size], dtype=np.uint64)
+    shafa.profile(True); shafa.profile_reset()
+    sym, _ = shafa.decode_tables(buf, offs, z, sizes, np.stack(lens), np.stack(codes), False, int(sizes.sum()) + 64)
+    stats = shafa.profile_read()
+    shafa.profile(False)
+    assert_same(sym, np.concatenate([big, small]), f"{alphabet} symbols")
+    assert "dec_sync_lean" in stats and "dec_lut16" in stats, stats.keys()
+
+
 def test_sf_decode_rejects_short_payload(shafa, orc, pkg):
     data = pkg.datagen.zipf(100_000, seed=2)
     codes = orc.sf_codes(orc.histogram(data))
