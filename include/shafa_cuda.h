@@ -207,6 +207,30 @@ int shafa_cuda_decode_host(shafa_cuda_ctx *ctx, const uint8_t *h_payload,
                            const uint64_t *h_code, int rle_expand, uint8_t *h_out,
                            uint64_t out_capacity, uint64_t *h_out_size, uint64_t *h_final_sizes);
 
+/* ---- code tables with codes longer than 64 bits ------------------------------
+ * Module T cannot produce them, but a .cod file may carry them: the reference's packer keeps up to 32
+ * bytes per code (c.c:18, 115-160) and its decoder builds its tree from the strings whatever their
+ * length (d.c:422-504).  Here a code is FOUR 64-bit words (h_code4[B][256][4], word 0 the least
+ * significant) of 1..255 bits (h_len); host buffers in and out, plain block-parallel kernels
+ * (csrc/sf_wide.cu) -- the path exists for parity with every file the reference accepts, not for speed.
+ *
+ * c.c:52-83 (binary_coding): block b is h_sym[h_offsets[b] .. h_offsets[b+1]).  Payload slots are laid out
+ * like shafa_cuda_sf_encode_blocks does (16-byte aligned, h_payload_offsets / h_z filled);
+ * *h_payload_total = bytes used of h_payload.  Errors: a symbol that occurs without a code ->
+ * SHAFA_FILE_UNRECOGNIZABLE; capacity -> SHAFA_LACK_OF_MEMORY (with *h_payload_total set). */
+int shafa_cuda_sf_encode_wide_host(shafa_cuda_ctx *ctx, const uint8_t *h_sym, const uint64_t *h_offsets,
+                                   uint64_t n_blocks, const uint8_t *h_len, const uint64_t *h_code4,
+                                   uint8_t *h_payload, uint64_t payload_capacity,
+                                   uint64_t *h_payload_offsets, uint64_t *h_z, uint64_t *h_payload_total);
+/* d.c:514-551 (shafa_block_decompressor): h_n[b] symbols of block b into h_sym, blocks back to back.  A bit
+ * pattern that is no code, or a payload that ends inside a code -> SHAFA_FILE_UNRECOGNIZABLE (the
+ * reference dereferences NULL there, d.c:533-536).  RLE expansion, if wanted, is
+ * shafa_cuda_rle_decode_host on the result. */
+int shafa_cuda_sf_decode_wide_host(shafa_cuda_ctx *ctx, const uint8_t *h_payload,
+                                   const uint64_t *h_payload_offsets, const uint64_t *h_z,
+                                   const uint64_t *h_n, uint64_t n_blocks, const uint8_t *h_len,
+                                   const uint64_t *h_code4, uint8_t *h_sym, uint64_t sym_capacity);
+
 /* RLE-only decode (rle_decompress, d.c:232-388) for host buffers. */
 int shafa_cuda_rle_decode_host(shafa_cuda_ctx *ctx, const uint8_t *h_rle, const uint64_t *h_offsets,
                                uint64_t n_blocks, uint8_t *h_out, uint64_t out_capacity,

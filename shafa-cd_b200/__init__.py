@@ -20,6 +20,7 @@ from .binding import (  # noqa: F401
     freq_text,
     load_library,
     parse_cod,
+    parse_cod_wide,
     parse_shaf,
     shaf_bytes,
 )

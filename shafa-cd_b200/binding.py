@@ -104,6 +104,8 @@ def load_library() -> C.CDLL:
     L.shafa_cuda_encoded_free.argtypes = [C.POINTER(EncodedC)]
     L.shafa_cuda_decode_host.argtypes = [vp, vp, vp, vp, vp, u64, vp, vp, C.c_int, vp, u64, u64p, vp]
     L.shafa_cuda_rle_decode_host.argtypes = [vp, vp, vp, u64, vp, u64, u64p, vp]
+    L.shafa_cuda_sf_encode_wide_host.argtypes = [vp, vp, vp, u64, vp, vp, vp, u64, vp, vp, u64p]
+    L.shafa_cuda_sf_decode_wide_host.argtypes = [vp, vp, vp, vp, vp, u64, vp, vp, vp, u64]
     L.shafa_cuda_multi_create.argtypes = [C.POINTER(C.c_int), C.c_int, C.POINTER(vp)]
     L.shafa_cuda_multi_destroy.argtypes = [vp]
     L.shafa_cuda_multi_device_count.argtypes = [vp]
@@ -196,6 +198,36 @@ def parse_cod(text: bytes):
             cd[b, s] = int(f, 2) if f else 0
         pos = m.end()
     return mode, sizes, ln, cd
+
+
+def parse_cod_wide(text: bytes):
+    """`.cod` with codes of up to 255 bits -> (mode, sizes[B], code_len[B,256] u8, code4[B,256,4] u64, word 0 least significant):
+    the form of shafa_cuda_sf_encode_wide_host / shafa_cuda_sf_decode_wide_host."""
+    m = re.match(rb"@(.)@(\d+)", text)
+    if not m:
+        raise ShafaError(4, "bad .cod header")
+    mode, B = m.group(1).decode(), int(m.group(2))
+    pos = m.end()
+    sizes = np.zeros(B, dtype=np.uint64)
+    ln = np.zeros((B, 256), dtype=np.uint8)
+    c4 = np.zeros((B, 256, 4), dtype=np.uint64)
+    for b in range(B):
+        m = re.compile(rb"@(\d+)@([01;]*)").match(text, pos)
+        if not m:
+            raise ShafaError(5, ".cod block header")
+        sizes[b] = int(m.group(1))
+        fields = m.group(2).split(b";")
+        if len(fields) != 256:
+            raise ShafaError(4, ".cod block does not have 256 fields")
+        for s, f in enumerate(fields):
+            if len(f) > 255:
+                raise ShafaError(4, "code longer than 255 bits")
+            ln[b, s] = len(f)
+            v = int(f, 2) if f else 0
+            for k in range(4):
+                c4[b, s, k] = (v >> (64 * k)) & 0xFFFFFFFFFFFFFFFF
+        pos = m.end()
+    return mode, sizes, ln, c4
 
 
 def shaf_bytes(z, payload: np.ndarray, payload_offsets) -> bytes:
@@ -465,6 +497,32 @@ class Shafa:
             return Encoded(c)
         finally:
             self.encoded_free(c)
+
+    def sf_encode_wide_host(self, sym, offsets, code_len, code4):
+        """Tables with codes of 65..255 bits (c.c:18): -> (payload with 16-byte aligned slots, payload_offsets[B], z[B])."""
+        sym, code_len = _u8(sym), _u8(code_len)
+        offsets, code4 = _u64(offsets), _u64(code4)
+        nb = len(offsets) - 1
+        poff, z = np.zeros(nb, dtype=np.uint64), np.zeros(nb, dtype=np.uint64)
+        total = C.c_uint64(0)
+        cap = int(offsets[-1] - offsets[0]) * 2 + 64 * nb + 4096
+        for _ in range(2):
+            payload = np.zeros(cap, dtype=np.uint8)
+            rc = self.lib.shafa_cuda_sf_encode_wide_host(self.ctx, sym.ctypes.data, offsets.ctypes.data, nb, code_len.ctypes.data, code4.ctypes.data,
+                                                        payload.ctypes.data, cap, poff.ctypes.data, z.ctypes.data, C.byref(total))
+            if rc != 2 or total.value <= cap:
+                break
+            cap = total.value
+        self._check(rc)
+        return payload[: total.value], poff, z
+
+    def sf_decode_wide_host(self, payload, payload_offsets, z, n, code_len, code4):
+        payload, code_len = _u8(payload), _u8(code_len)
+        payload_offsets, z, n, code4 = _u64(payload_offsets), _u64(z), _u64(n), _u64(code4)
+        out = np.empty(int(n.sum()) + 64, dtype=np.uint8)
+        self._check(self.lib.shafa_cuda_sf_decode_wide_host(self.ctx, payload.ctypes.data, payload_offsets.ctypes.data, z.ctypes.data, n.ctypes.data,
+                                                           len(n), code_len.ctypes.data, code4.ctypes.data, out.ctypes.data, out.nbytes))
+        return out[: int(n.sum())]
 
     def decode_tables(self, payload, payload_offsets, z, n, code_len, code_bits, rle_expand: bool, out_capacity: int,
                       out: np.ndarray | None = None):

@@ -5,6 +5,8 @@
 #include <new>
 #include <stdlib.h>
 
+#include <vector>
+
 #include "internal.h"
 
 using namespace shafa;
@@ -652,6 +654,84 @@ int shafa_cuda_encode_shard_host(shafa_cuda_ctx *ctx, const uint8_t *h_in, uint6
         ctx->stream == ctx->own_stream)
         return encode_host_pipelined(&ctx, 1, h_in, n, block_size, 0, force_freq, rle_mode ? 1 : 0, out);
     return encode_host_impl(ctx, h_in, n, block_size, 0, force_freq, rle_mode ? 1 : 0, out);
+}
+
+// ---- code tables with codes of 65..255 bits (sf_wide.cu) ---------------------------------------------------------------
+int shafa_cuda_sf_encode_wide_host(shafa_cuda_ctx *ctx, const uint8_t *h_sym, const uint64_t *h_offsets, uint64_t nb,
+                                   const uint8_t *h_len, const uint64_t *h_code4, uint8_t *h_payload, uint64_t payload_capacity,
+                                   uint64_t *h_payload_offsets, uint64_t *h_z, uint64_t *h_payload_total)
+{
+    CTX_ENTER(ctx);
+    if (h_payload_total) *h_payload_total = 0;
+    if (nb == 0) return SHAFA_SUCCESS;
+    if (nb > (1ull << 32)) return SHAFA_LACK_OF_MEMORY;
+    const uint64_t lo = h_offsets[0], total = h_offsets[nb] - lo;
+    std::vector<uint64_t> rel(nb + 1);
+    for (uint64_t b = 0; b <= nb; b++) rel[b] = h_offsets[b] - lo;
+    uint32_t *d_err;
+    int rc = err_reset(ctx, &d_err);
+    if (rc) return rc;
+    uint8_t *d_sym = (uint8_t *)scratch_get(ctx, SCR_STAGE_A, round16(total) + 64);
+    uint64_t *d_code4 = (uint64_t *)scratch_get(ctx, SCR_STAGE_D, nb * 256 * (4 * sizeof(uint64_t) + 1));
+    uint64_t *d_hist = (uint64_t *)scratch_get(ctx, SCR_HIST, nb * 256 * sizeof(uint64_t));
+    uint64_t *sz = (uint64_t *)scratch_get(ctx, SCR_SIZES, (3 * nb + 2) * sizeof(uint64_t) + nb * sizeof(uint32_t));
+    if (!d_sym || !d_code4 || !d_hist || !sz) return SHAFA_LACK_OF_MEMORY;
+    uint8_t *d_len = (uint8_t *)(d_code4 + nb * 256 * 4);
+    uint64_t *d_bits = sz, *d_z = sz + nb, *d_off = sz + 2 * nb, *d_sum = sz + 3 * nb;
+    uint32_t *d_flags = (uint32_t *)(sz + 3 * nb + 2);
+    if ((rc = shafa_cuda_memcpy_h2d(ctx, d_sym, h_sym + lo, total))) return rc;
+    if ((rc = shafa_cuda_memcpy_h2d(ctx, d_code4, h_code4, nb * 256 * 4 * sizeof(uint64_t)))) return rc;
+    if ((rc = shafa_cuda_memcpy_h2d(ctx, d_len, h_len, nb * 256))) return rc;
+    if ((rc = launch_histogram(ctx, d_sym, rel.data(), nb, d_hist))) return rc;
+    if ((rc = launch_sf_sizes(ctx, d_hist, d_len, nb, d_bits, d_flags, d_z, d_off, d_sum))) return rc;
+    uint64_t *h = (uint64_t *)pinned_get(ctx, (2 * nb + 2) * sizeof(uint64_t));
+    if (!h) return SHAFA_LACK_OF_MEMORY;
+    SHAFA_CUDA_TRY(ctx, cudaMemcpyAsync(h, d_z, (2 * nb + 2) * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    SHAFA_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    memcpy(h_z, h, nb * sizeof(uint64_t));
+    memcpy(h_payload_offsets, h + nb, nb * sizeof(uint64_t));
+    const uint64_t ptotal = h[2 * nb], flags = h[2 * nb + 1];
+    if (flags & 2) return set_error(ctx, SHAFA_FILE_UNRECOGNIZABLE, "sf_encode_wide: a symbol occurs in the data but has no code");
+    if (h_payload_total) *h_payload_total = ptotal;
+    if (ptotal > payload_capacity) return set_error(ctx, SHAFA_LACK_OF_MEMORY, "sf_encode_wide: payload needs %llu bytes, capacity %llu", (unsigned long long)ptotal, (unsigned long long)payload_capacity);
+    uint8_t *d_payload = (uint8_t *)scratch_get(ctx, SCR_STAGE_F, round16(ptotal) + 64);
+    if (!d_payload) return SHAFA_LACK_OF_MEMORY;
+    if ((rc = launch_sf_encode_wide(ctx, d_sym, rel.data(), nb, d_len, d_code4, d_off, d_z, d_payload, d_err))) return rc;
+    if ((rc = finish_with_err(ctx, d_err, "sf_encode_wide"))) return rc;
+    if ((rc = shafa_cuda_memcpy_d2h(ctx, h_payload, d_payload, ptotal))) return rc;
+    return shafa_cuda_synchronize(ctx);
+}
+
+int shafa_cuda_sf_decode_wide_host(shafa_cuda_ctx *ctx, const uint8_t *h_payload, const uint64_t *h_payload_offsets,
+                                   const uint64_t *h_z, const uint64_t *h_n, uint64_t nb, const uint8_t *h_len,
+                                   const uint64_t *h_code4, uint8_t *h_sym, uint64_t sym_capacity)
+{
+    CTX_ENTER(ctx);
+    if (nb == 0) return SHAFA_SUCCESS;
+    if (nb > (1ull << 32)) return SHAFA_LACK_OF_MEMORY;
+    uint64_t extent = 0, stotal = 0;
+    for (uint64_t b = 0; b < nb; b++) {
+        const uint64_t e = h_payload_offsets[b] + h_z[b];
+        if (e < h_payload_offsets[b]) return SHAFA_FILE_UNRECOGNIZABLE;
+        if (e > extent) extent = e;
+        stotal += h_n[b];
+    }
+    if (stotal > sym_capacity) return set_error(ctx, SHAFA_LACK_OF_MEMORY, "sf_decode_wide: output needs %llu bytes", (unsigned long long)stotal);
+    uint32_t *d_err;
+    int rc = err_reset(ctx, &d_err);
+    if (rc) return rc;
+    uint8_t *d_payload = (uint8_t *)scratch_get(ctx, SCR_STAGE_A, round16(extent) + 64);
+    uint8_t *d_sym = (uint8_t *)scratch_get(ctx, SCR_STAGE_B, round16(stotal) + 64);
+    uint64_t *d_code4 = (uint64_t *)scratch_get(ctx, SCR_STAGE_D, nb * 256 * (4 * sizeof(uint64_t) + 1));
+    if (!d_payload || !d_sym || !d_code4) return SHAFA_LACK_OF_MEMORY;
+    uint8_t *d_len = (uint8_t *)(d_code4 + nb * 256 * 4);
+    if ((rc = shafa_cuda_memcpy_h2d(ctx, d_payload, h_payload, extent))) return rc;
+    if ((rc = shafa_cuda_memcpy_h2d(ctx, d_code4, h_code4, nb * 256 * 4 * sizeof(uint64_t)))) return rc;
+    if ((rc = shafa_cuda_memcpy_h2d(ctx, d_len, h_len, nb * 256))) return rc;
+    if ((rc = launch_sf_decode_wide(ctx, d_payload, h_payload_offsets, h_z, h_n, nb, d_len, d_code4, d_sym, d_err))) return rc;
+    if ((rc = finish_with_err(ctx, d_err, "sf_decode_wide"))) return rc;
+    if ((rc = shafa_cuda_memcpy_d2h(ctx, h_sym, d_sym, stotal))) return rc;
+    return shafa_cuda_synchronize(ctx);
 }
 
 int shafa_cuda_rle_decode_host(shafa_cuda_ctx *ctx, const uint8_t *h_rle, const uint64_t *h_offsets, uint64_t nb,

@@ -149,6 +149,14 @@ int launch_sf_decode(shafa_cuda_ctx *ctx, const uint8_t *d_payload, const uint64
                      const uint64_t *h_z, const uint64_t *h_n, uint64_t nb, const uint8_t *d_len,
                      const uint64_t *d_code, uint8_t *d_sym, uint32_t *d_err, bool force_exact, bool careful_stitch);
 
+// sf_wide.cu: tables with codes of 65..255 bits (four 64-bit words per code, word 0 least significant)
+int launch_sf_encode_wide(shafa_cuda_ctx *ctx, const uint8_t *d_sym, const uint64_t *h_off, uint64_t nb, const uint8_t *d_len,
+                          const uint64_t *d_code4, const uint64_t *d_payload_off, const uint64_t *d_z, uint8_t *d_payload,
+                          uint32_t *d_err);
+int launch_sf_decode_wide(shafa_cuda_ctx *ctx, const uint8_t *d_payload, const uint64_t *h_payload_off, const uint64_t *h_z,
+                          const uint64_t *h_n, uint64_t nb, const uint8_t *d_len, const uint64_t *d_code4, uint8_t *d_sym,
+                          uint32_t *d_err);
+
 // rle_encode.cu (synchronises: returns per-block sizes)
 int launch_rle_encode(shafa_cuda_ctx *ctx, const uint8_t *d_in, uint64_t n, uint64_t block_size, uint8_t *d_rle,
                       uint64_t rle_capacity, uint64_t *h_rle_sizes, uint64_t *d_hist, uint32_t *d_err);

@@ -33,8 +33,11 @@ _modules_error shafa_compress(char **const path)
     blob cod = {0}, sym = {0};
     _modules_error err = blob_read(p_cod, &cod);
     free(p_cod);
-    uint64_t nb = 0, *sizes = NULL, *offsets = NULL, *code = NULL, *z = NULL, *poff = NULL;
+    uint64_t nb = 0, *sizes = NULL, *offsets = NULL, *code = NULL, *z = NULL, *poff = NULL, *code4 = NULL;
     uint8_t *len = NULL, *h_payload = NULL;
+    const uint8_t **fld = NULL; /* the blocks' code fields, kept for the wide parser */
+    size_t *fll = NULL;
+    bool wide = false;          /* some code has more than 64 bits (c.c:18 allows 32 bytes): the plain kernels of sf_wide.cu */
     void *d_sym = NULL, *d_len = NULL, *d_code = NULL, *d_payload = NULL;
     shafa_cuda_ctx *g = NULL;
     if (err) goto out;
@@ -64,7 +67,9 @@ _modules_error shafa_compress(char **const path)
     len = malloc(nb * 256 + 1);
     z = malloc((nb + 1) * sizeof *z);
     poff = malloc((nb + 1) * sizeof *poff);
-    if (!sizes || !offsets || !code || !len || !z || !poff) {
+    fld = malloc((nb + 1) * sizeof *fld);
+    fll = malloc((nb + 1) * sizeof *fll);
+    if (!sizes || !offsets || !code || !len || !z || !poff || !fld || !fll) {
         err = _LACK_OF_MEMORY;
         goto out;
     }
@@ -76,14 +81,40 @@ _modules_error shafa_compress(char **const path)
             err = _FILE_STREAM_FAILED;
             goto out;
         }
-        if ((err = cod_parse_fields(f, fl, len + b * 256, code + b * 256))) goto out;
+        fld[b] = f;
+        fll[b] = fl;
+        if (cod_max_code_bits(f, fl) > 64) wide = true;
+        if (!wide && (err = cod_parse_fields(f, fl, len + b * 256, code + b * 256))) goto out;
         offsets[b + 1] = offsets[b] + sizes[b];
         if (sizes[b] > sym.size || offsets[b + 1] > sym.size) { /* c.c:392 short read (and no wrap-around) */
             err = _FILE_STREAM_FAILED;
             goto out;
         }
     }
-    if (nb) {
+    if (nb && wide) {
+        /* a table with codes of 65..255 bits: every block through shafa_cuda_sf_encode_wide_host */
+        code4 = malloc(nb * 256 * 4 * sizeof *code4);
+        if (!code4) {
+            err = _LACK_OF_MEMORY;
+            goto out;
+        }
+        for (uint64_t b = 0; b < nb; b++)
+            if ((err = cod_parse_fields_wide(fld[b], fll[b], len + b * 256, code4 + b * 1024))) goto out;
+        uint64_t cap = offsets[nb] + offsets[nb] / 8 + 32 * nb + 4096, ptotal = 0;
+        for (int attempt = 0; attempt < 2; attempt++) {
+            h_payload = cli_host_alloc(cap + 16);
+            if (!h_payload) {
+                err = _LACK_OF_MEMORY;
+                goto out;
+            }
+            err = gpu_status(shafa_cuda_sf_encode_wide_host(g, sym.data, offsets, nb, len, code4, h_payload, cap, poff, z, &ptotal));
+            if (err != _LACK_OF_MEMORY || attempt || ptotal <= cap) break;
+            cli_host_free(h_payload); /* the exact total is known now */
+            h_payload = NULL;
+            cap = ptotal;
+        }
+        if (err) goto out;
+    } else if (nb) {
         const uint64_t total = offsets[nb];
         /* exact sizes come back from the library; capacity: <= 64 bits per symbol is the hard bound, 9/8 the practical one */
         uint64_t cap = total + total / 8 + 32 * nb + 4096;
@@ -142,6 +173,9 @@ out:
     free(sizes);
     free(offsets);
     free(code);
+    free(code4);
+    free(fld);
+    free(fll);
     free(len);
     free(z);
     free(poff);

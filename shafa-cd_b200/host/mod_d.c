@@ -142,7 +142,11 @@ _modules_error shafa_decompress(char **const path, const bool decompress_rle)
     }
     blob shaf = {0}, cod = {0};
     uint64_t nb = 0, nb_shaf = 0, *z = NULL, *poff = NULL, *n = NULL, *offsets = NULL, *fin = NULL, *code = NULL, out_size = 0;
-    uint8_t *len = NULL, *h_payload = NULL, *h_out = NULL;
+    uint64_t *code4 = NULL;
+    uint8_t *len = NULL, *h_payload = NULL, *h_out = NULL, *h_sym = NULL;
+    const uint8_t **fld = NULL; /* the blocks' code fields, kept for the wide parser */
+    size_t *fll = NULL;
+    bool wide = false;          /* some code has more than 64 bits (d.c:422-504 takes any length): sf_wide.cu */
     shafa_cuda_multi *m = NULL;
     gpu_prefetch(); /* CUDA start-up overlaps the reads */
     _modules_error err = blob_read(*path, &shaf);
@@ -175,7 +179,9 @@ _modules_error shafa_decompress(char **const path, const bool decompress_rle)
     code = malloc((nb * 256 + 1) * sizeof *code);
     len = malloc(nb * 256 + 1);
     h_payload = cli_host_alloc(shaf.size + 16 * nb + 64);
-    if (!z || !poff || !n || !offsets || !fin || !code || !len || !h_payload) {
+    fld = malloc((nb + 1) * sizeof *fld);
+    fll = malloc((nb + 1) * sizeof *fll);
+    if (!z || !poff || !n || !offsets || !fin || !code || !len || !h_payload || !fld || !fll) {
         err = _LACK_OF_MEMORY;
         goto out;
     }
@@ -196,7 +202,10 @@ _modules_error shafa_decompress(char **const path, const bool decompress_rle)
             err = _FILE_STREAM_FAILED;
             goto out;
         }
-        if ((err = cod_parse_fields(f, fl, len + b * 256, code + b * 256))) goto out;
+        fld[b] = f;
+        fll[b] = fl;
+        if (cod_max_code_bits(f, fl) > 64) wide = true;
+        if (!wide && (err = cod_parse_fields(f, fl, len + b * 256, code + b * 256))) goto out;
         /* a block decodes to at most 64 MiB + 1 KiB of symbols in any file module C can write (2n + 3 of a 64 MiB block
          * is the hard bound); anything larger is a forged header -- and would wrap the sums below */
         if (n[b] > 2ull * MIB_64 + 3) {
@@ -210,7 +219,42 @@ _modules_error shafa_decompress(char **const path, const bool decompress_rle)
         err = _THREAD_CREATION_FAILED;
         goto out;
     }
-    if (nb) {
+    if (nb && wide) {
+        /* a table with codes of 65..255 bits: SF decode of every block by shafa_cuda_sf_decode_wide_host, then the
+         * ordinary RLE expansion of the symbol stream */
+        code4 = malloc(nb * 256 * 4 * sizeof *code4);
+        h_sym = cli_host_alloc(offsets[nb] + 64);
+        if (!code4 || !h_sym) {
+            err = _LACK_OF_MEMORY;
+            goto out;
+        }
+        for (uint64_t b = 0; b < nb; b++)
+            if ((err = cod_parse_fields_wide(fld[b], fll[b], len + b * 256, code4 + b * 1024))) goto out;
+        if ((err = gpu_status(shafa_cuda_sf_decode_wide_host(shafa_cuda_multi_ctx(m, 0), h_payload, poff, z, n, nb, len, code4, h_sym, offsets[nb]))))
+            goto out;
+        if (!decompress_rle) {
+            h_out = h_sym;
+            h_sym = NULL;
+            out_size = offsets[nb];
+            memcpy(fin, n, nb * sizeof *fin);
+        } else {
+            uint64_t cap = 0;
+            for (uint64_t b = 0; b < nb; b++) cap += rle_guess(n[b]);
+            for (int attempt = 0; attempt < 2; attempt++) {
+                h_out = cli_host_alloc(cap + 64);
+                if (!h_out) {
+                    err = _LACK_OF_MEMORY;
+                    goto out;
+                }
+                err = gpu_status(shafa_cuda_rle_decode_host_multi(m, h_sym, offsets, nb, h_out, cap, &out_size, fin));
+                if (err != _LACK_OF_MEMORY || attempt || out_size <= cap) break;
+                cli_host_free(h_out);
+                h_out = NULL;
+                cap = out_size;
+            }
+            if (err) goto out;
+        }
+    } else if (nb) {
         /* SF decode (+ RLE expansion, d.c:574-586) of all blocks: chunks of blocks on worker streams of every device */
         uint64_t cap = 0;
         for (uint64_t b = 0; b < nb; b++) cap += decompress_rle ? rle_guess(n[b]) : n[b];
@@ -232,6 +276,10 @@ _modules_error shafa_decompress(char **const path, const bool decompress_rle)
 out:
     if (h_payload) cli_host_free(h_payload);
     if (h_out) cli_host_free(h_out);
+    if (h_sym) cli_host_free(h_sym);
+    free(code4);
+    free(fld);
+    free(fll);
     if (!err) {
         summary(decompress_rle ? "SHAFA & RLE" : "SHAFA", now_ms() - t0, z, fin, nb, p_out);
         free(*path); /* d.c:814-815 */

@@ -219,6 +219,42 @@ _modules_error cod_parse_fields(const uint8_t *p, size_t n, uint8_t *len, uint64
     return p == end ? _SUCCESS : _FILE_UNRECOGNIZABLE; /* c.c:174-177 */
 }
 
+size_t cod_max_code_bits(const uint8_t *p, size_t n)
+{
+    size_t best = 0, run = 0;
+    for (size_t i = 0; i < n; i++) {
+        if (p[i] == '0' || p[i] == '1') {
+            if (++run > best) best = run;
+        } else {
+            run = 0;
+        }
+    }
+    return best;
+}
+
+_modules_error cod_parse_fields_wide(const uint8_t *p, size_t n, uint8_t *len, uint64_t *code4)
+{
+    const uint8_t *end = p + n;
+    for (int s = 0; s < 256; s++) {
+        unsigned l = 0;
+        uint64_t v[4] = {0, 0, 0, 0};
+        while (p < end && (*p == '0' || *p == '1')) {
+            if (++l > COD_WIDE_MAX_BITS) return _FILE_UNRECOGNIZABLE;
+            v[3] = (v[3] << 1) | (v[2] >> 63); /* shift the 256-bit value left by one, new bit in at the bottom */
+            v[2] = (v[2] << 1) | (v[1] >> 63);
+            v[1] = (v[1] << 1) | (v[0] >> 63);
+            v[0] = (v[0] << 1) | (uint64_t)(*p++ == '1');
+        }
+        len[s] = (uint8_t)l;
+        for (int k = 0; k < 4; k++) code4[s * 4 + k] = v[k];
+        if (s != 255) {
+            if (p >= end || *p != ';') return _FILE_UNRECOGNIZABLE; /* c.c:127-131,165-169 */
+            p++;
+        }
+    }
+    return p == end ? _SUCCESS : _FILE_UNRECOGNIZABLE; /* c.c:174-177 */
+}
+
 bool block_count_plausible(uint64_t nb, uint64_t container_bytes) { return nb <= container_bytes / 258u; }
 
 double now_ms(void)

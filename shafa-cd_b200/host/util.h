@@ -56,8 +56,15 @@ bool cur_u64(cursor *c, uint64_t *v);
 bool cur_field(cursor *c, const uint8_t **start, size_t *len);
 
 /* one .cod block: 256 ';'-separated '0'/'1' strings (c.c:115-177, d.c:479-495) -> length + right-aligned bits.
- * Codes longer than 64 bits are legal in the format but not supported: _FILE_UNRECOGNIZABLE. */
+ * Codes longer than 64 bits do not fit this form (_FILE_UNRECOGNIZABLE): callers look at cod_max_code_bits first and
+ * take the wide form for such tables. */
 _modules_error cod_parse_fields(const uint8_t *p, size_t n, uint8_t *len, uint64_t *code);
+/* longest run of '0'/'1' characters in the block = its longest code */
+size_t cod_max_code_bits(const uint8_t *p, size_t n);
+/* the same for tables with codes of up to 255 bits (the reference's packer keeps 32 bytes per code, c.c:18): four
+ * 64-bit words per code, word 0 the least significant (the library's shafa_cuda_sf_*_wide_host form) */
+#define COD_WIDE_MAX_BITS 255
+_modules_error cod_parse_fields_wide(const uint8_t *p, size_t n, uint8_t *len, uint64_t *code4);
 
 /* Block counts come from untrusted "@N@<count>" headers and size every table that follows.  A .freq / .cod
  * block is at least "@d@" plus 255 ';' = 258 bytes, so a count above file_size / 258 is a lie

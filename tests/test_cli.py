@@ -213,3 +213,46 @@ def test_cli_fused_equals_separate_modules_and_multi_device(pkg, tmp_path):
         r = subprocess.run([str(BIN), "f.rle", "-m", "d", "-d", "r"], cwd=d, capture_output=True, timeout=600, env={**os.environ, **env})
         assert r.returncode == 0 and (d / "f").read_bytes() == data.tobytes()
     assert outs["fused"] == outs["separate"] == outs["multi"]
+
+
+@pytest.mark.gpu
+def test_cli_codes_longer_than_64_bits(pkg, orc, tmp_path):
+    """`-m c` and `-m d` with a hand-made .cod whose codes reach 255 bits (c.c:18 keeps 32 bytes per code, d.c:422-504 builds
+    its tree from the strings): byte-identical to the unmodified reference's .shaf (tests/golden/wide_codes), and the R-mode
+    route (wide SF decode, then RLE expansion) against the oracle."""
+    d = GOLDEN / "wide_codes"
+    for name in ("x", "x.cod"):
+        shutil.copy(d / name, tmp_path / name)
+    r = run(["x", "-m", "c"], tmp_path)
+    assert r.returncode == 0, r.stderr
+    assert (tmp_path / "x.shaf").read_bytes() == (d / "x.shaf").read_bytes()
+    (tmp_path / "x").unlink()
+    r = run(["x.shaf", "-m", "d"], tmp_path)
+    assert r.returncode == 0, r.stderr
+    assert (tmp_path / "x").read_bytes() == (d / "x").read_bytes()
+    # R mode: our own F, then a hand-made wide table over the symbols of the .rle stream
+    data = pkg.datagen.runheavy(300_000, seed=4)
+    (tmp_path / "y").write_bytes(data.tobytes())
+    r = run(["y", "-m", "f", "-c", "r"], tmp_path)
+    assert r.returncode == 0, r.stderr
+    rle = (tmp_path / "y.rle").read_bytes()
+    freq = (tmp_path / "y.rle.freq").read_bytes()
+    sizes = [int(x) for x in freq.split(b"@")[3:-1:2]]
+    present = sorted(set(rle))
+    assert len(present) <= 255
+    codes = [""] * 256
+    for k, sym in enumerate(present[:-1]):
+        codes[sym] = "1" * (k * (254 // max(1, len(present) - 1))) + "0" if k else "0"
+    depth_last = max(len(c) for c in codes)
+    codes[present[-1]] = "1" * depth_last
+    assert 64 < depth_last <= 255
+    cod = f"@R@{len(sizes)}".encode() + b"".join(f"@{sz}@".encode() + ";".join(codes).encode() for sz in sizes) + b"@0"
+    (tmp_path / "y.rle.cod").write_bytes(cod)
+    r = run(["y.rle", "-m", "c"], tmp_path)
+    assert r.returncode == 0, r.stderr
+    assert (tmp_path / "y.rle.shaf").read_bytes() == orc.module_c(rle, cod)
+    (tmp_path / "y").unlink()
+    (tmp_path / "y.rle").unlink()
+    r = run(["y.rle.shaf", "-m", "d"], tmp_path)
+    assert r.returncode == 0, r.stderr
+    assert (tmp_path / "y").read_bytes() == data.tobytes()

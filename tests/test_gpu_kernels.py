@@ -279,6 +279,72 @@ def test_sf_decode_codes_of_nearly_one_length(shafa, orc, pkg, alphabet, n):
     assert "dec_sync_lean" in stats and "dec_lut16" in stats, stats.keys()
 
 
+def _wide_table(rng, nsym, depths):
+    """codes '1' * d + '0' for the given depths plus '1' * max(depths + 1): complete, prefix-free, up to 255 bits"""
+    syms = rng.permutation(256)[:nsym]
+    codes = [""] * 256
+    for k, dpt in enumerate(depths):
+        codes[syms[k]] = "1" * dpt + "0"
+    codes[syms[len(depths)]] = "1" * (max(depths) + 1)
+    return syms, codes
+
+
+def _codes_to_wide(codes):
+    ln = np.array([len(c) for c in codes], dtype=np.uint8)
+    c4 = np.zeros((256, 4), dtype=np.uint64)
+    for s, c in enumerate(codes):
+        v = int(c, 2) if c else 0
+        for k in range(4):
+            c4[s, k] = (v >> (64 * k)) & 0xFFFFFFFFFFFFFFFF
+    return ln, c4
+
+
+def test_sf_wide_codes_fixture(shafa, pkg):
+    """Codes of 65..255 bits (sf_wide.cu) against the reference's own .shaf for a hand-made .cod (tests/golden/wide_codes)."""
+    d = GOLDEN / "wide_codes"
+    data = np.frombuffer((d / "x").read_bytes(), dtype=np.uint8)
+    mode, sizes, ln, c4 = pkg.parse_cod_wide((d / "x.cod").read_bytes())
+    offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.uint64)
+    payload, poff, z = shafa.sf_encode_wide_host(data, offs, ln, c4)
+    want = (d / "x.shaf").read_bytes()
+    assert pkg.shaf_bytes(z, payload, poff) == want
+    z2, payload2, poff2 = pkg.parse_shaf(want)
+    assert_same(shafa.sf_decode_wide_host(payload2, poff2, z2, sizes, ln, c4), data, "wide decode of the reference's .shaf")
+
+
+@pytest.mark.parametrize("seed,n,nblocks", [(1, 5_000, 1), (2, 200_000, 4), (3, 64, 2)])
+def test_sf_wide_codes_random_tables(shafa, orc, pkg, seed, n, nblocks):
+    rng = np.random.default_rng(seed)
+    depths = sorted(set([0, 1, 2, 3] + list(rng.integers(4, 254, size=30))))
+    cuts = np.linspace(0, n, nblocks + 1).astype(int)
+    blocks, lens, c4s, want = [], [], [], []
+    for b in range(nblocks):
+        syms, codes = _wide_table(rng, len(depths) + 1, depths)
+        p = np.array([2.0 ** -min(dp + 1, 10) for dp in depths] + [2.0 ** -10])
+        blk = syms[rng.choice(len(p), size=cuts[b + 1] - cuts[b], p=p / p.sum())].astype(np.uint8)
+        blk[: min(len(syms), blk.size)] = syms[: min(len(syms), blk.size)]
+        ln, c4 = _codes_to_wide(codes)
+        blocks.append(blk); lens.append(ln); c4s.append(c4)
+        want.append(orc.sf_encode_block(blk, codes))
+    data = np.concatenate(blocks)
+    offs = np.array(cuts, dtype=np.uint64)
+    payload, poff, z = shafa.sf_encode_wide_host(data, offs, np.stack(lens), np.stack(c4s))
+    for b in range(nblocks):
+        assert int(z[b]) == want[b].size
+        assert_same(payload[int(poff[b]): int(poff[b]) + int(z[b])], want[b], f"wide payload of block {b}")
+    sizes = np.diff(cuts).astype(np.uint64)
+    assert_same(shafa.sf_decode_wide_host(payload, poff, z, sizes, np.stack(lens), np.stack(c4s)), data, "wide round trip")
+    # a payload cut short, and a table that lacks a symbol of the data: errors, not garbage
+    with pytest.raises(pkg.ShafaError) as e:
+        shafa.sf_decode_wide_host(payload, poff, np.maximum(z // 2, 1), sizes, np.stack(lens), np.stack(c4s))
+    assert e.value.code == 4
+    ln_bad = np.stack(lens).copy()
+    ln_bad[0, int(data[0])] = 0
+    with pytest.raises(pkg.ShafaError) as e:
+        shafa.sf_encode_wide_host(data, offs, ln_bad, np.stack(c4s))
+    assert e.value.code == 4
+
+
 def test_sf_decode_rejects_short_payload(shafa, orc, pkg):
     data = pkg.datagen.zipf(100_000, seed=2)
     codes = orc.sf_codes(orc.histogram(data))

@@ -127,3 +127,21 @@ def test_one_symbol_block_encode(orc, case):
     shaf = orc.module_c(f["rle"] if f["rle_mode"] else data.tobytes(), cod)
     assert shaf == (d / (base + ".shaf")).read_bytes()
     assert b"@0@" in shaf[-8:]
+
+
+def test_wide_codes_fixture(orc, pkg):
+    """tests/golden/wide_codes (make_wide_golden.py): a hand-made .cod with codes of up to 255 bits and the unmodified
+    reference's .shaf for it.  The oracle packs and decodes it like the reference; the host-side parser of the wide
+    form reads the same table."""
+    d = GOLDEN / "wide_codes"
+    data, cod, shaf = (d / "x").read_bytes(), (d / "x.cod").read_bytes(), (d / "x.shaf").read_bytes()
+    assert orc.module_c(data, cod) == shaf
+    assert orc.module_d_shaf(shaf, cod, rle=False) == data
+    mode, sizes, ln, c4 = pkg.parse_cod_wide(cod)
+    assert mode == "N" and int(sizes.sum()) == len(data) and int(ln.max()) == 255
+    fields = cod.split(b"@")[4].split(b";")   # "", N, 3, size, fields, ...
+    for s in range(256):
+        v = sum(int(c4[0, s, k]) << (64 * k) for k in range(4))
+        assert ln[0, s] == len(fields[s]) and v == (int(fields[s], 2) if fields[s] else 0)
+    with pytest.raises(pkg.ShafaError):
+        pkg.parse_cod(cod)   # the 64-bit form refuses it

@@ -35,6 +35,15 @@ def main():
                 if enc.rle_mode:
                     assert np.array_equal(sh.decode(enc, rle_expand=False), enc.rle), (gen, fused)
                 print("ok", gen, "fused" if fused == "1" else "exact", "R" if enc.rle_mode else "N", flush=True)
+        # code tables with codes of 65..255 bits (sf_wide.cu): the reference's own fixture
+        g = ROOT / "tests" / "golden" / "wide_codes"
+        data = np.frombuffer((g / "x").read_bytes(), dtype=np.uint8)
+        _, sizes, ln, c4 = pkg.parse_cod_wide((g / "x.cod").read_bytes())
+        offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.uint64)
+        payload, poff, z = sh.sf_encode_wide_host(data, offs, ln, c4)
+        assert pkg.shaf_bytes(z, payload, poff) == (g / "x.shaf").read_bytes()
+        assert np.array_equal(sh.sf_decode_wide_host(payload, poff, z, sizes, ln, c4), data)
+        print("ok wide codes", flush=True)
     print("SANITIZE_SMALL_OK")
 
 
