@@ -11,6 +11,11 @@
 //                  really ended until nothing changes (later rounds are compacted).
 //                  A sequence's first sub-sequence starts where the chunk's previous
 //                  sequence ended; per-sequence symbol counts are produced here
+//   k_dec_classes  sequences of "lean" blocks (complete code of nearly one length, <= 12 bits, >= 256 KiB of
+//                  payload) and of all other blocks, each class numbered densely on the device
+//   k_dec_lut16 +  the lean blocks' synchronisation: such codes never re-synchronise, so every start is
+//   k_dec_sync_lean walked -- with a 16-bit window table holding ALL whole codes of the window, because
+//                  that walk is bound by shared-memory table gathers (see the kernel's comment)
 //   k_dec_stitch   across chunk boundaries: feed each sequence the true end of its
 //                  predecessor and re-walk until it meets the recorded state;
 //                  repeated while a sequence end moved
