@@ -1,5 +1,6 @@
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus 4 --steps 10 --warmup 3 --no-cpu --no-files > gpurun_out/r02c_bench_4gpu.json 2> gpurun_out/r02c_bench_4gpu.err; tail -2 gpurun_out/r02c_bench_4gpu.err; python - <<P
+timeout 900 python bench.py --steps 20 --warmup 5 > gpurun_out/r02d_bench.json 2> gpurun_out/r02d_bench.err; tail -2 gpurun_out/r02d_bench.err
+python - <<P
 import json
-j=json.loads(open("gpurun_out/r02c_bench_4gpu.json").read().strip().splitlines()[-1])
-print(j["n_gpus"], j["value"], "e2e", j["e2e"]["value"], "one_file", json.dumps(j.get("one_file"))[:700])
+j = json.load(open("gpurun_out/r02d_bench.json"))
+print(j["value"], j.get("encode_gbs"), j.get("decode_gbs"), "e2e", j["e2e"]["value"], "files", j.get("e2e_files"), j["roofline"]["kernel"], j["roofline"]["frac"], j["roofline"]["traffic"], j["cpu_baseline"]["value"], j.get("parity"))
 P
