@@ -54,6 +54,9 @@ void *scratch_get(shafa_cuda_ctx *ctx, int slot, size_t bytes)
         cuda_fail(ctx, e, "cudaMalloc(scratch)");
         return nullptr;
     }
+    // Ragged streams are read with 16-byte vector loads that may reach into the padding behind the last valid byte (the
+    // bytes are masked off before use): fresh memory is zeroed once so that those loads never see uninitialised data.
+    cudaMemsetAsync(p, 0, cap, ctx->stream);
     ctx->scratch[slot] = p;
     ctx->scratch_cap[slot] = cap;
     return p;
@@ -292,6 +295,7 @@ void *shafa_cuda_dev_alloc(shafa_cuda_ctx *ctx, size_t bytes)
         cuda_fail(ctx, e, "cudaMalloc");
         return nullptr;
     }
+    cudaMemsetAsync(p, 0, bytes ? bytes : 16, ctx->stream);  // see scratch_get: padded vector loads behind ragged streams
     return p;
 }
 void shafa_cuda_dev_free(shafa_cuda_ctx *ctx, void *p)
