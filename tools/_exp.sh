@@ -1,2 +1,3 @@
-timeout 700 compute-sanitizer --tool initcheck python tools/sanitize_small.py > gpurun_out/san_initcheck.log 2>&1; echo "initcheck rc=$?"; grep -c "Uninitialized __global__" gpurun_out/san_initcheck.log; grep -c "cudaMemcpy source" gpurun_out/san_initcheck.log; tail -3 gpurun_out/san_initcheck.log
-timeout 600 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_configs.py -x -q -m gpu 2>&1 | tail -2
+# scratch: the command line of the last experiment sent to the GPU box with `gpurun -- 'bash tools/_exp.sh'`
+timeout 600 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_configs.py -x -q -m gpu | tail -2
+bash tools/ab_bench.sh
